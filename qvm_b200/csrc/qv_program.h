@@ -1,0 +1,99 @@
+// qv_program.h -- the "tile program" format executed by the sm_100a tile kernel.
+//
+// One PASS = one sweep over the (shard of the) amplitude vector in HBM.  Every
+// CTA stages a TILE of 2^T amplitudes in shared memory: T physical index bits
+// (the low L bits, so every HBM access is a run of 2^L*16 contiguous bytes, plus
+// arbitrary higher bits) vary inside the tile, the remaining bits select the
+// tile.  Inside the tile a pass runs ROUNDS: in a round each thread keeps a
+// GROUP of 2^m (m<=3) amplitudes in registers, the m "register bits" being
+// tile-local bit positions, and applies every OP of the round to them before
+// the group goes back to shared memory.  So one HBM pass can apply many gates,
+// and one shared-memory pass applies several of them.
+//
+// Everything in here is physical: the host scheduler (qv_sched.cpp) has already
+// translated logical qubits into physical index bits.  All structs are PODs
+// copied verbatim to the device.
+#pragma once
+#include <stdint.h>
+
+#define QV_MAX_TILE_BITS 12      // 2^12 amplitudes * 16 B = 64 KiB of shared memory per CTA
+#define QV_MIN_LOW_BITS 4        // low bits always inside the tile: 256-byte HBM runs at worst
+#define QV_REG_BITS 3            // 2^3 amplitudes per thread per round
+#define QV_MAX_SEGS 12
+#define QV_CHUNK_SEGS 8
+#define QV_MAX_CHUNK_BITS 8      // diagonal factor tables have <= 256 entries
+#define QV_THREADS 256
+#define QV_MAX_PEERS 8
+
+enum QvOpType : uint32_t {
+    QV_OP_DENSE1 = 1,   // 2x2 complex matrix on register bit rb0
+    QV_OP_DENSE2 = 2,   // 4x4 complex matrix on register bits rb0 < rb1 (matrix bit0 <-> rb0)
+    QV_OP_DIAG = 3,     // product of chunk-table lookups (merged diagonal gates)
+};
+
+enum QvOpFlags : uint32_t {
+    QV_F_CTRL_LOCAL = 1u,   // cm_local/cv_local restrict the op to matching tile-local indices
+    QV_F_CTRL_EXT = 2u,     // cm_ext/cv_ext restrict the op to matching tiles (CTA-uniform)
+    QV_F_REAL = 4u,         // matrix has no imaginary parts (H, X, RY, CNOT, SWAP ...)
+};
+
+// gather/deposit of one contiguous bit field: ((x >> src) & ((1<<len)-1)) << dst
+struct QvSeg {
+    uint8_t src, len, dst, pad;
+};
+
+// One factor of a merged diagonal: phase = table[gather_local(e) | gather_ext(base)]
+struct QvChunk {
+    uint32_t table_off;             // offset in complex entries into the pass's table pool
+    uint8_t n_lsegs, n_esegs;       // fields gathered from the tile-local index / the tile base
+    uint8_t reg_mask;               // which register bits of the op's round feed this chunk
+    uint8_t pad;
+    QvSeg lsegs[QV_CHUNK_SEGS];
+    QvSeg esegs[QV_CHUNK_SEGS];
+};
+
+struct QvOp {
+    uint32_t type;
+    uint32_t flags;
+    uint8_t rb0, rb1, pad0, pad1;
+    uint32_t cm_local, cv_local;    // control over the tile-local index e
+    uint64_t cm_ext, cv_ext;        // control over the physical index bits outside the tile
+    uint32_t data_off;              // DENSE: offset in complex entries into the matrix pool (row-major)
+                                    // DIAG : index of the first chunk in the chunk array
+    uint32_t n_chunks;
+    uint32_t pad2[2];
+};
+
+struct QvRound {
+    uint32_t m;                     // register bits in this round (<= QV_REG_BITS, <= T)
+    uint32_t regpos[QV_REG_BITS];   // tile-local bit positions, ascending
+    uint32_t first_op, n_ops;
+    uint32_t pad[2];
+};
+
+struct QvPassHeader {
+    uint32_t T;                     // tile bits
+    uint32_t n_tile_segs;           // tile-local index e -> physical index bits
+    QvSeg tile_segs[QV_MAX_SEGS];
+    uint32_t n_base_segs;           // tile id -> physical index bits
+    QvSeg base_segs[QV_MAX_SEGS];
+    uint64_t fixed_bits;            // OR'd into every physical index of the pass (rank bits, group split)
+    uint64_t n_tiles;               // tiles this device processes
+    uint32_t n_local_bits;          // log2(amplitudes per shard): physical bits above it select the peer
+    uint32_t n_rounds;
+    uint32_t n_ops;
+    uint32_t n_chunks;
+    // byte offsets from the start of the pass blob
+    uint32_t off_rounds, off_ops, off_chunks, off_matrices, off_tables;
+    uint32_t blob_bytes;
+    uint32_t uses_peers;            // tile bits include a physical bit >= n_local_bits
+    uint32_t pad;
+};
+
+// A k>=3 dense gate runs as its own pass through the generic kernel.
+struct QvBigGate {
+    uint32_t k;
+    uint32_t pad;
+    uint32_t pos[16];               // physical bit of matrix index bit j
+    uint64_t ctrl_mask, ctrl_val;   // physical control bits (identity when not matching)
+};

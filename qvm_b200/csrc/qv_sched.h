@@ -1,0 +1,59 @@
+// qv_sched.h -- host-side gate scheduler: logical gates -> tile programs.
+//
+// Replaces, for the GPU path, what the reference does in
+// src/compile-gate.lisp:315-361,409-526 (per-gate compiled lambdas) and the
+// external quil::fuse-gates-in-executable-code (called src/qvm.lisp:166-175):
+// instead of multiplying small matrices together it packs runs of gates into
+// passes/rounds of the tile kernel (see qv_program.h), which keeps every gate's
+// own arithmetic (and therefore its rounding) intact.
+#pragma once
+#include <complex>
+#include <cstdint>
+#include <string>
+#include <vector>
+
+#include "qv_program.h"
+
+namespace qv {
+
+using cd = std::complex<double>;
+
+// A gate on LOGICAL qubits.  qubits[j] is attached to bit j of the matrix index
+// (NAT-TUPLE order, src/utilities.lisp:43-51); mat is row-major 2^k x 2^k.
+struct Gate {
+    std::vector<int> qubits;
+    std::vector<cd> mat;
+};
+
+struct CompileOptions {
+    int tile_bits = QV_MAX_TILE_BITS;
+    int min_low_bits = QV_MIN_LOW_BITS;
+    bool fuse = true;            // false: every gate is its own HBM pass
+    bool absorb_swaps = false;   // true: exact SWAP gates only relabel qubits (l2p changes)
+    int n_local_bits = 0;        // log2(amplitudes on this device); 0 = n_bits (single device)
+    int rank = 0;                // value of the physical bits >= n_local_bits on this device
+};
+
+struct Step {
+    enum Kind { TILE = 0, BIG = 1 } kind = TILE;
+    std::vector<uint8_t> blob;   // TILE: QvPassHeader followed by rounds/ops/chunks/matrices/tables
+    QvBigGate big{};             // BIG
+    std::vector<cd> bigmat;      // BIG: row-major 2^k x 2^k
+    int n_gates = 0;             // logical gates (atoms) folded into this step
+};
+
+struct Tape {
+    int n_bits = 0;
+    std::vector<Step> steps;
+    std::vector<int> l2p;        // logical -> physical qubit map after the tape ran
+    int n_gates = 0;
+    int n_atoms = 0;
+};
+
+// l2p_in: current logical->physical map (empty = identity).
+Tape compile(const std::vector<Gate>& gates, int n_bits, const CompileOptions& opt,
+             const std::vector<int>& l2p_in = {});
+
+std::string describe(const Tape& t);
+
+}  // namespace qv

@@ -1,0 +1,71 @@
+"""Host logic: the gate scheduler's tile programs, interpreted on the CPU through the same op code
+the CUDA kernel compiles (tests/support/qv_emulator.cpp), must reproduce the oracle."""
+import numpy as np
+import pytest
+
+from helpers import assert_close, rand_state, random_circuit, run_emulator, run_oracle
+from qvm_b200 import circuits as CC
+
+
+@pytest.mark.parametrize("n,tile_bits", [(1, 12), (2, 12), (3, 12), (5, 12), (8, 4), (9, 5), (10, 6), (13, 12), (15, 12)])
+@pytest.mark.parametrize("fuse", [True, False])
+def test_qft_matches_oracle(n, tile_bits, fuse):
+    circ = CC.qft_circuit(range(n))
+    a = rand_state(n)
+    b = a.copy()
+    steps, desc, _ = run_emulator(a, n, circ, fuse=fuse, tile_bits=tile_bits)
+    run_oracle(b, circ)
+    assert_close(a, b)
+    if not fuse:
+        assert steps >= len(circ)
+
+
+@pytest.mark.parametrize("seed", range(12))
+def test_random_circuits_match_oracle(seed):
+    rng = np.random.default_rng(1000 + seed)
+    n = int(rng.integers(1, 14))
+    tile_bits = int(rng.integers(3, 13))
+    circ = random_circuit(n, int(rng.integers(5, 60)), rng, max_dense=4)
+    a = rand_state(n, seed)
+    b = a.copy()
+    run_emulator(a, n, circ, fuse=True, tile_bits=tile_bits)
+    run_oracle(b, circ)
+    assert_close(a, b)
+    c = rand_state(n, seed)
+    run_emulator(c, n, circ, fuse=False, tile_bits=tile_bits)
+    assert_close(c, b)
+
+
+def test_fusion_packs_qft_into_few_passes():
+    n = 16
+    circ = CC.qft_circuit(range(n))
+    a = rand_state(n)
+    steps, desc, _ = run_emulator(a, n, circ, fuse=True, tile_bits=12)
+    assert steps <= 4, desc
+
+
+def test_absorbed_swaps_relabel_qubits():
+    n = 10
+    circ = CC.qft_circuit(range(n))
+    a = rand_state(n)
+    b = a.copy()
+    _, _, l2p = run_emulator(a, n, circ, fuse=True, tile_bits=8, absorb_swaps=True)
+    run_oracle(b, circ)
+    # physical index bit l2p[q] holds logical qubit q: un-permute and compare
+    idx = np.arange(1 << n)
+    phys = np.zeros_like(idx)
+    for q in range(n):
+        phys |= ((idx >> q) & 1) << int(l2p[q])
+    assert_close(a[phys], b)
+
+
+def test_hadamard_and_bell_known_answers():
+    # tests/gate-tests.lisp:13-26 (H^n uniform) and :75-89 (Bell first/last probability 1/2)
+    from oracle import oracle as O
+    for n in range(1, 11):
+        a = O.zero_state(n)
+        run_emulator(a, n, CC.hadamard_circuit(n))
+        assert np.allclose(np.abs(a) ** 2, 2.0 ** -n, atol=1e-14)
+        b = O.zero_state(n)
+        run_emulator(b, n, CC.bell_circuit(n))
+        assert abs(abs(b[0]) ** 2 - 0.5) < 1e-14 and abs(abs(b[-1]) ** 2 - 0.5) < 1e-14
