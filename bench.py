@@ -1,0 +1,277 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the QVM hot path on B200.
+
+Metric (BASELINE.json): gates/s (and HBM GB/s) of gate application on a 30-qubit state, workload
+`configs[1]`: the 30-qubit QFT of examples/qft.lisp (480 gates), gate fusion on; the unfused
+per-gate-pass bandwidth is reported beside it.  A "step" = one run of the whole circuit over the
+device-resident 16 GiB state.
+
+    python bench.py --gpus N --steps K --warmup W            # our arm
+    python bench.py --impl reference --gpus N --steps K ...   # the reference's CPU path (oracle port, all host threads)
+
+Under torchrun (N > 1) every rank owns one shard (top log2(N) qubits select the rank), weak scaling:
+30 + log2(N) qubits in total.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import math
+import os
+import subprocess
+import sys
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+ALGO_BYTES_PER_AMP = 32   # one gate pass reads 16 B and writes 16 B per amplitude
+
+
+def measured_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        try:
+            return float(json.load(open(path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.proc = None
+        self.path = f"/tmp/qvm_bench_clocks_{os.getpid()}.csv"
+        try:
+            self.f = open(self.path, "w")
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(gpu_index)], stdout=self.f, stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
+        if self.proc is None:
+            return out
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        self.f.close()
+        sm, mx, reasons = [], [], set()
+        for line in open(self.path):
+            p = [x.strip() for x in line.split(",")]
+            if len(p) < 9:
+                continue
+            try:
+                sm.append(float(p[1]))
+                mx.append(float(p[2]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), p[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        if sm:
+            out = {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons),
+                   "samples": len(sm)}
+        try:
+            os.remove(self.path)
+        except OSError:
+            pass
+        return out
+
+
+def qft_gates(n):
+    from qvm_b200 import circuits
+    return circuits.qft_circuit(range(n))
+
+
+# ------------------------------------------------------------------------------- CPU arm
+def cpu_sample(n_qubits: int, budget_s: float, max_gates: int = 64):
+    """Time the oracle port (all host threads, contiguous ranges like lparallel:pdotimes) on the first
+    gates of the same circuit, bounded by budget_s."""
+    from oracle import oracle as O
+    threads = min(O.max_threads(), os.cpu_count() or 1)
+    gates = qft_gates(n_qubits)
+    psi = np.zeros(1 << n_qubits, dtype=np.complex128)
+    psi[0] = 1.0
+    O.apply_matrix(psi, gates[0][0], gates[0][1], threads=threads)     # first touch, untimed
+    done, t0 = 0, time.perf_counter()
+    for m, q in gates[1:1 + max_gates]:
+        O.apply_matrix(psi, m, q, threads=threads)
+        done += 1
+        if time.perf_counter() - t0 > budget_s:
+            break
+    dt = time.perf_counter() - t0
+    return {"value": done / dt, "unit": "gates/s", "cores": threads, "kind": "port",
+            "sample": f"gates 2..{done + 1} of the {n_qubits}-qubit QFT (unfused, one pass per gate), {dt:.1f} s, "
+                      f"oracle/qvm_oracle.c orc_apply_matrix_mt; the reference itself needs SBCL (absent)"}, psi
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    n = args.qubits
+    from oracle import oracle as O
+    threads = min(O.max_threads(), os.cpu_count() or 1)
+    gates = qft_gates(n)
+    psi = np.zeros(1 << n, dtype=np.complex128)
+    psi[0] = 1.0
+    per_step = args.ref_gates_per_step
+    pos = 0
+
+    def step():
+        nonlocal pos
+        for _ in range(per_step):
+            m, q = gates[pos % len(gates)]
+            O.apply_matrix(psi, m, q, threads=threads)
+            pos += 1
+
+    for _ in range(args.warmup):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step()
+    dt = time.perf_counter() - t0
+    val = per_step * args.steps / dt
+    sample = f"{per_step} consecutive gates of the {n}-qubit QFT per step (unfused CPU passes), {threads} threads"
+    print(json.dumps({
+        "impl": "reference", "metric": "gates/s", "value": val, "unit": "gates/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": f"qft-{n} (examples/qft.lisp qft-circuit), PURE-STATE-QVM, complex double"},
+        "cpu_baseline": {"value": val, "unit": "gates/s", "cores": threads, "kind": "port", "sample": sample},
+        "e2e": {"value": val, "unit": "gates/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }))
+
+
+# ------------------------------------------------------------------------------- GPU arm
+def run_ours(args):
+    import torch
+
+    from qvm_b200 import _lib, qvm
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1:
+        from qvm_b200 import dist
+        return dist.bench_sharded(args, rank, world, local_rank)
+
+    n = args.qubits
+    torch.cuda.set_device(local_rank)
+    stream = torch.cuda.Stream()
+    vec = qvm.DeviceVector(1 << n, device=local_rank)
+    vec.set_stream(stream.cuda_stream)
+    gates = qft_gates(n)
+    tape = qvm.Tape(n, gates, fuse=True)
+    info = tape.info()
+    peak, peak_src = measured_peaks()
+    bytes_per_pass = ALGO_BYTES_PER_AMP * (1 << n)
+
+    def timed(fn, steps, warmup):
+        for _ in range(warmup):
+            fn()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        l0 = _lib.launch_count()
+        with torch.cuda.stream(stream):
+            e0.record(stream)
+            for _ in range(steps):
+                fn()
+            e1.record(stream)
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / 1e3, _lib.launch_count() - l0
+
+    # ---- headline: fused tape, state resident in HBM
+    vec.set_zero_state()
+    clocks = ClockSampler(local_rank)
+    dt, launches = timed(lambda: vec.run_tape(tape), args.steps, args.warmup)
+    clk = clocks.stop()
+    value = len(gates) * args.steps / dt
+    pass_s = dt / (args.steps * info["passes"])
+    roofline = {"bound": "hbm", "achieved": bytes_per_pass / pass_s / 1e9, "peak": peak, "unit": "GB/s",
+                "frac": bytes_per_pass / pass_s / 1e9 / peak, "traffic": None,
+                "kernel": "qv_tile_kernel (fused passes)", "peak_source": peak_src,
+                "bytes_per_launch": bytes_per_pass, "launches_per_step": info["passes"]}
+
+    # ---- unfused: every gate its own HBM pass (bounded sample of the same circuit)
+    sample = gates[: args.unfused_gates]
+    tape_u = qvm.Tape(n, sample, fuse=False)
+    dtu, _ = timed(lambda: vec.run_tape(tape_u), 1, 1)
+    pass_u = dtu / tape_u.info()["passes"]
+    unfused = {"gates_per_s": len(sample) / dtu, "hbm_gbs": bytes_per_pass / pass_u / 1e9,
+               "frac_of_peak": bytes_per_pass / pass_u / 1e9 / peak, "ms_per_gate_pass": 1e3 * pass_u,
+               "sample": f"first {len(sample)} gates of the circuit, one tile-kernel launch per gate"}
+
+    # ---- e2e: through the public API with host buffers: reset, program (host arrays) -> device, run,
+    #      10^3-shot sample + one probability back to the host.
+    u = np.random.default_rng(2024).random(1000)
+    ks, qf, mf = _lib.flatten_gates(gates)
+    h2d = ks.nbytes + qf.nbytes + mf.nbytes + u.nbytes + info["table_bytes"]
+    d2h = u.size * 8 + 8
+
+    def e2e_step():
+        vec.set_zero_state()
+        vec.apply_gates(gates, fuse=True)
+        vec.sample(u, strict=False)
+        vec.prob_excited(0)
+
+    for _ in range(2):
+        e2e_step()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        e2e_step()
+    torch.cuda.synchronize()
+    e2e_dt = time.perf_counter() - t0
+    e2e = {"value": len(gates) * args.steps / e2e_dt, "unit": "gates/s", "h2d_bytes_per_step": int(h2d),
+           "d2h_bytes_per_step": int(d2h),
+           "what": "qvm reset + apply_gates(host gate arrays, scheduled and uploaded inside) + 1000-shot sample + prob readback"}
+
+    vec.close()
+    cpu = None
+    if not args.no_cpu_baseline:
+        cpu, _ = cpu_sample(n, args.cpu_budget)
+
+    print(json.dumps({
+        "metric": "gates/s", "value": value, "unit": "gates/s", "n_gpus": 1, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f64", "data": "synthetic",
+        "config": {"workload": f"qft-{n} (examples/qft.lisp qft-circuit, {len(gates)} gates), PURE-STATE-QVM, complex double, gate fusion on",
+                   "state_bytes": 16 << n, "l2_policy": "state (16 GiB at 30 qubits) is far larger than the 126 MB L2; no flush needed",
+                   "hbm_passes_per_step": info["passes"]},
+        "roofline": roofline, "unfused": unfused, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches),
+        "clocks": clk,
+    }))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--qubits", type=int, default=30)
+    ap.add_argument("--unfused-gates", type=int, default=60)
+    ap.add_argument("--cpu-budget", type=float, default=15.0)
+    ap.add_argument("--ref-gates-per-step", type=int, default=4)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,133 @@
+/* qvmcuda.h -- C ABI of libqvmcuda, the B200 (sm_100a) engine behind the QVM's
+ * gate-application / probability / measurement / sampling hot path.
+ *
+ * The reference (quil-lang/qvm, Common Lisp) has no C plugin interface for this
+ * path; the seam is a set of CLOS protocols.  Each entry point
+ * below is what a CFFI binding for one of those protocol methods calls; the
+ * reference interface it stands behind is cited as file:line (paths relative to
+ * the reference checkout).  The Lisp-side bindings are in lisp/ and
+ * INTEGRATION.md.
+ *
+ * Conventions
+ *   - every function returns 0 on success, nonzero on failure;
+ *     qvmcuda_last_error() gives the message for the calling thread (the
+ *     reference's FFI style: C int status -> Lisp ERROR, src/shm.lisp:198-206).
+ *   - amplitudes are interleaved (re, im) doubles = the reference's CFLONUM
+ *     (src/floats.lisp:13-26); a state is a flat vector of 2^n of them
+ *     (src/linear-algebra.lisp:9-11); operators are row-major 2^k x 2^k
+ *     (src/linear-algebra.lisp:21-24).
+ *   - qubit lists are in NAT-TUPLE order (src/utilities.lisp:43-51): entry j is
+ *     the qubit attached to bit j of the matrix index, i.e. the Quil argument
+ *     list REVERSED.
+ *   - the library never draws random numbers: uniforms come from the host's
+ *     mt19937 (src/measurement.lisp:99, :136, :257).
+ *   - handles are thread-safe (one mutex per handle); destroy may be called
+ *     from any thread (tg:finalize runs finalizers on arbitrary threads,
+ *     src/state-representation.lisp:92-102).
+ *   - there is no CPU fallback: without a CUDA device every call fails.
+ */
+#ifndef QVMCUDA_H
+#define QVMCUDA_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct qvmcuda_state qvmcuda_state;   /* a device-resident amplitude vector */
+typedef struct qvmcuda_tape qvmcuda_tape;     /* a compiled (fused) gate sequence */
+
+/* flags for qvmcuda_tape_compile / qvmcuda_apply_gates */
+#define QVMCUDA_FUSE          1u   /* pack runs of gates into shared HBM passes (*fuse-gates-during-compilation*, src/config.lisp:41-58) */
+#define QVMCUDA_ABSORB_SWAPS  2u   /* exact SWAP gates relabel qubits instead of moving data */
+
+const char *qvmcuda_last_error(void);
+int qvmcuda_device_count(int *count);
+/* number of kernels this process has launched through the library (bench.py's gpu_launches) */
+int qvmcuda_launch_count(uint64_t *count);
+
+/* ---- allocation protocol: ALLOCATE-VECTOR / finalizer (src/allocator.lisp:47-62),
+ *      MAKE-PURE-STATE / MAKE-DENSITY-MATRIX-STATE (src/state-representation.lisp:76-102, 235-266).
+ *      The vector is zero-initialised, as the protocol requires. */
+int qvmcuda_state_create(uint64_t n_amplitudes, int device, qvmcuda_state **out);
+int qvmcuda_state_destroy(qvmcuda_state *s);                 /* idempotent on NULL */
+int qvmcuda_state_length(qvmcuda_state *s, uint64_t *n_amplitudes);
+/* run the handle's work on an existing CUDA stream (cudaStream_t passed as an integer) */
+int qvmcuda_state_set_stream(qvmcuda_state *s, uint64_t cuda_stream);
+int qvmcuda_synchronize(qvmcuda_state *s);
+
+/* ---- state protocol: STATE-ELEMENTS / (SETF STATE-ELEMENTS), QVM::AMPLITUDES
+ *      (src/state-representation.lisp:126-135, src/qvm.lisp:63-69): the device<->host sync points. */
+int qvmcuda_download(qvmcuda_state *s, double *dst, uint64_t offset, uint64_t count);
+int qvmcuda_upload(qvmcuda_state *s, const double *src, uint64_t offset, uint64_t count);
+/* SET-TO-ZERO-STATE / BRING-TO-ZERO-STATE (src/wavefunction.lisp:80-91) */
+int qvmcuda_set_zero_state(qvmcuda_state *s);
+/* COPY-WAVEFUNCTION (src/wavefunction.lisp:93-109): copies min(|dst|,|src|) amplitudes */
+int qvmcuda_copy(qvmcuda_state *dst, qvmcuda_state *src);
+
+/* ---- operator API: APPLY-MATRIX-OPERATOR (src/wavefunction.lisp:308-330) behind
+ *      APPLY-GATE-TO-STATE on a pure state (src/apply-gate.lisp:106-160). */
+int qvmcuda_apply_matrix(qvmcuda_state *s, int k, const int32_t *qubits, const double *matrix);
+/* a run of gates in one call (one CFFI crossing per program, SURVEY.md section 7 "per-transition host
+ * overhead"): ks[g] qubits and 2*4^ks[g] doubles per gate, concatenated. */
+int qvmcuda_apply_gates(qvmcuda_state *s, int n_gates, const int32_t *ks, const int32_t *qubits,
+                        const double *matrices, uint32_t flags);
+
+/* ---- compile protocol: COMPILE-LOADED-PROGRAM (src/qvm.lisp:166-175, src/compile-gate.lisp:484-526):
+ *      build the fused tape once, run it many times. n_qubits = log2(state length). */
+int qvmcuda_tape_compile(int n_qubits, int n_gates, const int32_t *ks, const int32_t *qubits,
+                         const double *matrices, uint32_t flags, qvmcuda_tape **out);
+int qvmcuda_tape_run(qvmcuda_state *s, qvmcuda_tape *t);
+/* info[0]=HBM passes, [1]=gates, [2]=atoms (controlled blocks/diagonals), [3]=tile passes, [4]=generic k>=3 passes */
+int qvmcuda_tape_info(qvmcuda_tape *t, int64_t info[8]);
+int qvmcuda_tape_describe(qvmcuda_tape *t, char *buf, uint64_t buflen);
+int qvmcuda_tape_destroy(qvmcuda_tape *t);
+
+/* ---- measurement protocol (src/measurement.lisp:7-150) */
+/* WAVEFUNCTION-EXCITED-STATE-PROBABILITY src/wavefunction.lisp:64-70 */
+int qvmcuda_prob_excited(qvmcuda_state *s, int qubit, double *p);
+/* WAVEFUNCTION-GROUND-STATE-PROBABILITY src/wavefunction.lisp:54-60 (compiled MEASURE, src/compile-gate.lisp:231) */
+int qvmcuda_prob_ground(qvmcuda_state *s, int qubit, double *p);
+/* NORM / NORMALIZE-WAVEFUNCTION src/wavefunction.lisp:333-364 */
+int qvmcuda_norm2(qvmcuda_state *s, double *sum_of_squares);
+int qvmcuda_scale(qvmcuda_state *s, double factor);
+int qvmcuda_normalize(qvmcuda_state *s);
+/* FORCE-MEASUREMENT (pure-state) src/measurement.lisp:10-41: amplitudes whose QUBIT bit differs from
+ * keep_bit become 0, the others are multiplied by inv_norm. */
+int qvmcuda_collapse(qvmcuda_state *s, int qubit, int keep_bit, double inv_norm);
+/* multi-shot sampling.  strict=0: smallest index whose inclusive CDF is >= u
+ * (SAMPLE-WAVEFUNCTION-MULTIPLE-TIMES src/measurement.lisp:246-288);
+ * strict=1: smallest index whose inclusive CDF is > u
+ * (SAMPLE-WAVEFUNCTION-AS-DISTRIBUTION-IN-PARALLEL-TRULY src/measurement.lisp:179-225, used by MEASURE-ALL :128-143).
+ * The CDF is accumulated in the blocked order documented in oracle/qvm_oracle.c (orc_sample_tree). */
+int qvmcuda_sample(qvmcuda_state *s, const double *uniforms, uint64_t n_shots, uint64_t *out, int strict);
+/* psi <- |basis> (second half of MEASURE-ALL-STATE src/measurement.lisp:137-141) */
+int qvmcuda_set_basis_state(qvmcuda_state *s, uint64_t basis);
+
+/* ---- density-matrix state: vec(rho) row-major on 2n index bits (src/state-representation.lisp:235-286) */
+/* superoperator application src/apply-gate.lisp:42-99,196-212: rho <- sum_j K_j rho K_j^dagger for the m
+ * Kraus operators (each 2^k x 2^k row-major); m == 1 is a plain gate (single-kraus). Applied as ONE
+ * operator sum_j K_j (x) conj(K_j) on the 2k bits (qubits, qubits+n). */
+int qvmcuda_density_apply_kraus(qvmcuda_state *s, int n_qubits, int k, const int32_t *qubits, int m,
+                                const double *kraus, uint32_t flags);
+/* GET-EXCITED-STATE-PROBABILITY (density-matrix-state) src/measurement.lisp:77-85 */
+int qvmcuda_density_prob_excited(qvmcuda_state *s, int n_qubits, int qubit, double *p);
+/* FORCE-MEASUREMENT (density-matrix-state) src/measurement.lisp:43-68 */
+int qvmcuda_density_collapse(qvmcuda_state *s, int n_qubits, int qubit, int keep_bit, double inv_norm);
+/* APPLY-MEASURE-DISCARD-TO-STATE (density) src/measurement.lisp:111-120 */
+int qvmcuda_density_measure_discard(qvmcuda_state *s, int n_qubits, int qubit);
+/* DENSITY-MATRIX-STATE-MEASUREMENT-PROBABILITIES src/state-representation.lisp:268-286 (2^n doubles to host) */
+int qvmcuda_density_diag_probs(qvmcuda_state *s, int n_qubits, double *out);
+
+/* ---- multi-GPU sharding (one process per GPU; layout after dqvm/src/global-addresses.lisp:99-151:
+ *      the top log2(P) physical index bits select the rank).  The 64-byte IPC handle of every rank's
+ *      shard is exchanged by the host (torch.distributed) and attached here so that the tile kernel can
+ *      read/write peer shards over NVLink. */
+int qvmcuda_shard_export(qvmcuda_state *s, uint8_t handle[64]);
+int qvmcuda_shard_attach(qvmcuda_state *s, int rank, int world, const uint8_t *handles /* world*64 */);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* QVMCUDA_H */

@@ -55,8 +55,17 @@ QV_HD qvc qv_cmadd(qvc acc, qvc m, qvc a) {
     return r;
 }
 
+// tile-local offset of register slot s for register-bit positions p0 < p1 < p2
+QV_HD uint32_t qv_dep(int s, uint32_t p0, uint32_t p1, uint32_t p2) {
+    return ((s & 1) ? (1u << p0) : 0u) | ((s & 2) ? (1u << p1) : 0u) | ((s & 4) ? (1u << p2) : 0u);
+}
+
+struct QvRegPos {
+    uint32_t p0, p1, p2;
+};
+
 template <int RB>
-QV_HD void qv_dense1(qvc a[8], const qvc* M, uint32_t flags, uint32_t e0, const uint32_t* dep,
+QV_HD void qv_dense1(qvc a[8], const qvc* M, uint32_t flags, uint32_t e0, const QvRegPos dep,
                      uint32_t cm, uint32_t cv) {
     const qvc m00 = M[0], m01 = M[1], m10 = M[2], m11 = M[3];
 #pragma unroll
@@ -75,7 +84,7 @@ QV_HD void qv_dense1(qvc a[8], const qvc* M, uint32_t flags, uint32_t e0, const 
             n1 = qv_cmadd(qv_cmul(m10, a0), m11, a1);
         }
         bool ok = true;
-        if (flags & QV_F_CTRL_LOCAL) ok = (((e0 | dep[r]) & cm) == cv);
+        if (flags & QV_F_CTRL_LOCAL) ok = (((e0 | qv_dep(r, dep.p0, dep.p1, dep.p2)) & cm) == cv);
         if (ok) {
             a[r] = n0;
             a[r1] = n1;
@@ -84,7 +93,7 @@ QV_HD void qv_dense1(qvc a[8], const qvc* M, uint32_t flags, uint32_t e0, const 
 }
 
 template <int RB0, int RB1>
-QV_HD void qv_dense2(qvc a[8], const qvc* M, uint32_t flags, uint32_t e0, const uint32_t* dep,
+QV_HD void qv_dense2(qvc a[8], const qvc* M, uint32_t flags, uint32_t e0, const QvRegPos dep,
                      uint32_t cm, uint32_t cv) {
 #pragma unroll
     for (int r = 0; r < 8; r++) {
@@ -107,7 +116,7 @@ QV_HD void qv_dense2(qvc a[8], const qvc* M, uint32_t flags, uint32_t e0, const 
             }
         }
         bool ok = true;
-        if (flags & QV_F_CTRL_LOCAL) ok = (((e0 | dep[r]) & cm) == cv);
+        if (flags & QV_F_CTRL_LOCAL) ok = (((e0 | qv_dep(r, dep.p0, dep.p1, dep.p2)) & cm) == cv);
         if (ok) {
             a[i0] = o[0];
             a[i1] = o[1];
@@ -122,7 +131,7 @@ QV_HD void qv_dense2(qvc a[8], const qvc* M, uint32_t flags, uint32_t e0, const 
 // the whole group, folded into `common` (one complex multiply per group instead
 // of one per amplitude).
 QV_HD void qv_diag(qvc a[8], const QvOp& op, const QvChunk* chunks, const qvc* tables, uint32_t e0,
-                   const uint32_t* dep, uint64_t base) {
+                   const QvRegPos dep, uint64_t base) {
     qvc common;
     common.x = 1.0;
     common.y = 0.0;
@@ -137,7 +146,7 @@ QV_HD void qv_diag(qvc a[8], const QvOp& op, const QvChunk* chunks, const qvc* t
         } else {
 #pragma unroll
             for (int r = 0; r < 8; r++) {
-                const uint32_t g = g0 | qv_gather32(dep[r], ch.lsegs, ch.n_lsegs);
+                const uint32_t g = g0 | qv_gather32(qv_dep(r, dep.p0, dep.p1, dep.p2), ch.lsegs, ch.n_lsegs);
                 a[r] = qv_cmul(a[r], tab[g]);
             }
         }
@@ -150,7 +159,7 @@ QV_HD void qv_diag(qvc a[8], const QvOp& op, const QvChunk* chunks, const qvc* t
 
 // Apply every op of a round to one register group.
 QV_HD void qv_apply_round(qvc a[8], const QvRound& rd, const QvOp* ops, const QvChunk* chunks,
-                          const qvc* mats, const qvc* tables, uint32_t e0, const uint32_t* dep,
+                          const qvc* mats, const qvc* tables, uint32_t e0, const QvRegPos dep,
                           uint64_t base) {
     for (uint32_t i = 0; i < rd.n_ops; i++) {
         const QvOp& op = ops[rd.first_op + i];

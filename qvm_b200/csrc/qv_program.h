@@ -24,6 +24,11 @@
 #define QV_MAX_CHUNK_BITS 8      // diagonal factor tables have <= 256 entries
 #define QV_THREADS 256
 #define QV_MAX_PEERS 8
+// The control part of a pass (header, rounds, ops, chunk descriptors, matrices) is handed to the
+// kernel as a __grid_constant__ parameter: it lives in the constant bank, so ptxas reads matrices
+// through uniform registers instead of spending vector registers on them.  Two size classes.
+#define QV_PROG_SMALL_BYTES 3584
+#define QV_PROG_LARGE_BYTES 28672
 
 enum QvOpType : uint32_t {
     QV_OP_DENSE1 = 1,   // 2x2 complex matrix on register bit rb0
@@ -83,8 +88,9 @@ struct QvPassHeader {
     uint32_t n_rounds;
     uint32_t n_ops;
     uint32_t n_chunks;
-    // byte offsets from the start of the pass blob
-    uint32_t off_rounds, off_ops, off_chunks, off_matrices, off_tables;
+    // byte offsets from the start of the control blob (the diagonal tables travel separately,
+    // in global memory)
+    uint32_t off_rounds, off_ops, off_chunks, off_matrices, n_table_entries;
     uint32_t blob_bytes;
     uint32_t uses_peers;            // tile bits include a physical bit >= n_local_bits
     uint32_t pad;

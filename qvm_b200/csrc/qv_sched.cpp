@@ -466,9 +466,9 @@ Step build_tile_step(const std::vector<const Atom*>& atoms, uint64_t tile_target
     off = align16(off + w.chunks.size() * sizeof(QvChunk));
     h.off_matrices = (uint32_t)off;
     off = align16(off + w.mats.size() * sizeof(cd));
-    h.off_tables = (uint32_t)off;
-    off = align16(off + w.tables.size() * sizeof(cd));
+    h.n_table_entries = (uint32_t)w.tables.size();
     h.blob_bytes = (uint32_t)off;
+    if (off > QV_PROG_LARGE_BYTES) throw std::runtime_error("scheduler bug: pass control program too large");
 
     Step st;
     st.kind = Step::TILE;
@@ -478,7 +478,7 @@ Step build_tile_step(const std::vector<const Atom*>& atoms, uint64_t tile_target
     if (!w.ops.empty()) std::memcpy(st.blob.data() + h.off_ops, w.ops.data(), w.ops.size() * sizeof(QvOp));
     if (!w.chunks.empty()) std::memcpy(st.blob.data() + h.off_chunks, w.chunks.data(), w.chunks.size() * sizeof(QvChunk));
     if (!w.mats.empty()) std::memcpy(st.blob.data() + h.off_matrices, w.mats.data(), w.mats.size() * sizeof(cd));
-    if (!w.tables.empty()) std::memcpy(st.blob.data() + h.off_tables, w.tables.data(), w.tables.size() * sizeof(cd));
+    st.tables = std::move(w.tables);
     st.n_gates = (int)atoms.size();
     return st;
 }
@@ -584,8 +584,13 @@ Tape compile(const std::vector<Gate>& gates, int n_bits, const CompileOptions& o
         }
         std::vector<const Atom*> in_pass, deferred;
         uint64_t dmix = 0, dtouch = 0, targets = 0;
+        size_t est_bytes = sizeof(QvPassHeader);
         for (const Atom* a : pending) {
             bool blocked = (a->mix & dtouch) != 0 || (dmix & a->touch) != 0;
+            // conservative size of the atom in the control program (round + op + chunk + matrix)
+            const size_t need_bytes = sizeof(QvRound) + sizeof(QvOp) +
+                                      (a->kind == Atom::DENSE ? a->mat.size() * sizeof(cd) : sizeof(QvChunk));
+            if (!blocked && est_bytes + need_bytes > QV_PROG_LARGE_BYTES - 1024) blocked = true;
             if (!blocked) {
                 if (a->kind == Atom::BIG) blocked = true;
                 else if (a->kind == Atom::DENSE) {
@@ -599,6 +604,7 @@ Tape compile(const std::vector<Gate>& gates, int n_bits, const CompileOptions& o
                 dtouch |= a->touch;
             } else {
                 in_pass.push_back(a);
+                est_bytes += need_bytes;
             }
         }
         if (in_pass.empty()) throw std::runtime_error("scheduler bug: no atom fits an empty pass");
@@ -621,7 +627,7 @@ std::string describe(const Tape& t) {
         QvPassHeader h;
         std::memcpy(&h, s.blob.data(), sizeof(h));
         os << "  [" << i << "] TILE T=" << h.T << " atoms=" << s.n_gates << " rounds=" << h.n_rounds
-           << " ops=" << h.n_ops << " chunks=" << h.n_chunks << " bytes=" << h.blob_bytes << " tilebits=";
+           << " ops=" << h.n_ops << " chunks=" << h.n_chunks << " bytes=" << h.blob_bytes << " tables=" << h.n_table_entries << " tilebits=";
         for (uint32_t k = 0; k < h.n_tile_segs; k++)
             os << (int)h.tile_segs[k].dst << "+" << (int)h.tile_segs[k].len << (k + 1 < h.n_tile_segs ? "," : "");
         os << "\n";

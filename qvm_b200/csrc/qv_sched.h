@@ -36,7 +36,8 @@ struct CompileOptions {
 
 struct Step {
     enum Kind { TILE = 0, BIG = 1 } kind = TILE;
-    std::vector<uint8_t> blob;   // TILE: QvPassHeader followed by rounds/ops/chunks/matrices/tables
+    std::vector<uint8_t> blob;   // TILE: QvPassHeader followed by rounds/ops/chunks/matrices (<= QV_PROG_LARGE_BYTES)
+    std::vector<cd> tables;      // TILE: diagonal factor tables (global memory)
     QvBigGate big{};             // BIG
     std::vector<cd> bigmat;      // BIG: row-major 2^k x 2^k
     int n_gates = 0;             // logical gates (atoms) folded into this step

@@ -1,0 +1,728 @@
+// qvmcuda.cu -- C ABI of libqvmcuda (see include/qvmcuda.h for the contract and
+// the reference interfaces each entry point stands behind).
+#include <atomic>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "../../include/qvmcuda.h"
+#include "qv_kernels.cuh"
+#include "qv_sched.h"
+
+namespace {
+
+thread_local std::string g_err;
+std::atomic<uint64_t> g_launches{0};
+
+int fail(const std::string& msg) {
+    g_err = msg;
+    return 1;
+}
+
+#define CK(call)                                                                              \
+    do {                                                                                      \
+        cudaError_t e_ = (call);                                                              \
+        if (e_ != cudaSuccess)                                                                \
+            return fail(std::string(#call) + ": " + cudaGetErrorString(e_));                  \
+    } while (0)
+
+struct DeviceGuard {
+    int prev = -1;
+    bool ok = true;
+    explicit DeviceGuard(int dev) {
+        if (cudaGetDevice(&prev) != cudaSuccess) { ok = false; return; }
+        if (prev != dev && cudaSetDevice(dev) != cudaSuccess) ok = false;
+        active = dev;
+    }
+    ~DeviceGuard() {
+        if (prev >= 0 && prev != active) cudaSetDevice(prev);
+    }
+    int active = -1;
+};
+
+int log2_exact(uint64_t n) {
+    if (n == 0 || (n & (n - 1))) return -1;
+    int b = 0;
+    while ((1ull << b) < n) b++;
+    return b;
+}
+
+constexpr uint32_t kReduceBlocks = 148 * 8;
+
+}  // namespace
+
+struct qvmcuda_state {
+    std::mutex mu;
+    int device = 0;
+    uint64_t n_amps = 0;
+    int n_bits = 0;
+    qvc* d_amps = nullptr;
+    cudaStream_t stream = nullptr;
+    bool own_stream = false;
+    double* d_partial = nullptr;   // kReduceBlocks + 1 doubles
+    int sm_count = 148;
+    std::vector<int> l2p;          // logical -> physical qubit (identity unless swaps were absorbed)
+    // multi-GPU
+    int rank = 0, world = 1;
+    QvPeers peers{};
+    std::vector<void*> opened;     // IPC-opened peer pointers
+};
+
+struct qvmcuda_tape {
+    std::mutex mu;
+    qv::Tape tape;
+    uint32_t flags = 0;
+    std::map<int, uint8_t*> d_blobs;      // device -> one buffer holding every step's blob / matrix
+    std::vector<size_t> offsets;          // per step offset into the buffer
+    size_t total_bytes = 0;
+};
+
+namespace {
+
+bool l2p_is_identity(const std::vector<int>& l2p) {
+    for (size_t i = 0; i < l2p.size(); i++)
+        if (l2p[i] != (int)i) return false;
+    return true;
+}
+
+void layout_tape(qvmcuda_tape* t) {
+    t->offsets.clear();
+    size_t off = 0;
+    for (const qv::Step& st : t->tape.steps) {
+        t->offsets.push_back(off);
+        const size_t bytes = (st.kind == qv::Step::TILE ? st.tables.size() : st.bigmat.size()) * sizeof(qv::cd);
+        off += (bytes + 255) & ~(size_t)255;
+    }
+    t->total_bytes = off;
+}
+
+int tile_grid(const qvmcuda_state* s, uint64_t n_tiles) {
+    const uint64_t cap = (uint64_t)s->sm_count * 3 * 4;   // 3 resident CTAs per SM, 4 waves of work per CTA slot
+    return (int)(n_tiles < cap ? n_tiles : cap);
+}
+
+template <typename PROG, bool PEERS>
+int launch_tile_t(qvmcuda_state* s, const qv::Step& st, const QvPassHeader& h, const uint8_t* d_tables) {
+    static std::atomic<bool> attr_set{false};
+    if (!attr_set.exchange(true)) {
+        CK(cudaFuncSetAttribute(qv_tile_kernel<PROG, PEERS>, cudaFuncAttributeMaxDynamicSharedMemorySize, 65536));
+        CK(cudaFuncSetAttribute(qv_tile_kernel<PROG, PEERS>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+    }
+    static thread_local PROG prog;   // 28 KiB: keep it off the stack
+    std::memcpy(prog.bytes, st.blob.data(), st.blob.size());
+    const size_t smem = (size_t)sizeof(qvc) << h.T;
+    qv_tile_kernel<PROG, PEERS><<<tile_grid(s, h.n_tiles), QV_THREADS, smem, s->stream>>>(prog, s->peers, (const qvc*)d_tables);
+    g_launches++;
+    CK(cudaGetLastError());
+    return 0;
+}
+
+int launch_tile(qvmcuda_state* s, const qv::Step& st, const uint8_t* d_tables) {
+    QvPassHeader h;
+    std::memcpy(&h, st.blob.data(), sizeof(h));
+    if (st.blob.size() > QV_PROG_LARGE_BYTES) return fail("pass control program too large");
+    const bool small = st.blob.size() <= QV_PROG_SMALL_BYTES;
+    if (h.uses_peers) return small ? launch_tile_t<QvProgSmall, true>(s, st, h, d_tables) : launch_tile_t<QvProgLarge, true>(s, st, h, d_tables);
+    return small ? launch_tile_t<QvProgSmall, false>(s, st, h, d_tables) : launch_tile_t<QvProgLarge, false>(s, st, h, d_tables);
+}
+
+int launch_big(qvmcuda_state* s, const qv::Step& st, const uint8_t* d_mat) {
+    if (st.big.k > 11) return fail("dense gates on more than 11 mixing qubits are not supported");
+    const uint64_t groups = 1ull << (s->n_bits - (int)st.big.k);
+    const uint64_t G = QV_BIG_ELEMS >> st.big.k;
+    uint64_t blocks = (groups + G - 1) / G;
+    const uint64_t cap = (uint64_t)s->sm_count * 16;
+    if (blocks > cap) blocks = cap;
+    qv_big_kernel<<<(int)blocks, QV_THREADS, 0, s->stream>>>(s->d_amps, st.big, (const qvc*)d_mat, (uint32_t)s->n_bits);
+    g_launches++;
+    CK(cudaGetLastError());
+    return 0;
+}
+
+// run a compiled tape whose step data already sits in d_buf
+int run_steps(qvmcuda_state* s, const qv::Tape& tape, const std::vector<size_t>& offsets, const uint8_t* d_buf) {
+    for (size_t i = 0; i < tape.steps.size(); i++) {
+        const qv::Step& st = tape.steps[i];
+        int rc = st.kind == qv::Step::TILE ? launch_tile(s, st, d_buf + offsets[i]) : launch_big(s, st, d_buf + offsets[i]);
+        if (rc) return rc;
+    }
+    return 0;
+}
+
+int gates_from_flat(int n_gates, const int32_t* ks, const int32_t* qubits, const double* matrices, std::vector<qv::Gate>& out) {
+    if (n_gates < 0) return fail("negative gate count");
+    out.resize((size_t)n_gates);
+    size_t qo = 0, mo = 0;
+    for (int g = 0; g < n_gates; g++) {
+        const int k = ks[g];
+        if (k < 1 || k > 16) return fail("gate arity out of range (1..16)");
+        out[g].qubits.assign(qubits + qo, qubits + qo + k);
+        qo += (size_t)k;
+        const size_t d = (size_t)1 << k;
+        out[g].mat.resize(d * d);
+        for (size_t i = 0; i < d * d; i++) out[g].mat[i] = qv::cd(matrices[mo + 2 * i], matrices[mo + 2 * i + 1]);
+        mo += 2 * d * d;
+    }
+    return 0;
+}
+
+qv::CompileOptions make_options(const qvmcuda_state* s, uint32_t flags) {
+    qv::CompileOptions opt;
+    opt.fuse = (flags & QVMCUDA_FUSE) != 0;
+    opt.absorb_swaps = (flags & QVMCUDA_ABSORB_SWAPS) != 0;
+    if (s) {
+        opt.rank = s->rank;
+        opt.n_local_bits = s->n_bits;
+    }
+    return opt;
+}
+
+// compile + upload + run in immediate mode (state mutex held)
+int run_gates_locked(qvmcuda_state* s, const std::vector<qv::Gate>& gates, uint32_t flags) {
+    qvmcuda_tape t;
+    try {
+        const int total_bits = s->n_bits + log2_exact((uint64_t)s->world);
+        t.tape = qv::compile(gates, total_bits, make_options(s, flags), s->l2p);
+    } catch (const std::exception& e) {
+        return fail(std::string("schedule: ") + e.what());
+    }
+    layout_tape(&t);
+    if (t.tape.steps.empty()) {
+        s->l2p = t.tape.l2p;
+        return 0;
+    }
+    std::vector<uint8_t> host(t.total_bytes, 0);
+    for (size_t i = 0; i < t.tape.steps.size(); i++) {
+        const qv::Step& st = t.tape.steps[i];
+        const std::vector<qv::cd>& src = st.kind == qv::Step::TILE ? st.tables : st.bigmat;
+        if (!src.empty()) std::memcpy(host.data() + t.offsets[i], src.data(), src.size() * sizeof(qv::cd));
+    }
+    uint8_t* d_buf = nullptr;
+    const size_t alloc_bytes = t.total_bytes ? t.total_bytes : 256;
+    host.resize(alloc_bytes, 0);
+    CK(cudaMallocAsync((void**)&d_buf, alloc_bytes, s->stream));
+    CK(cudaMemcpyAsync(d_buf, host.data(), alloc_bytes, cudaMemcpyHostToDevice, s->stream));
+    // pageable source: the copy has been staged when the call returns, `host` may go away
+    int rc = run_steps(s, t.tape, t.offsets, d_buf);
+    cudaFreeAsync(d_buf, s->stream);
+    if (rc) return rc;
+    s->l2p = t.tape.l2p;
+    return 0;
+}
+
+// Undo absorbed swaps so that physical bit q holds logical qubit q again.
+int canonicalize_locked(qvmcuda_state* s) {
+    if (l2p_is_identity(s->l2p)) return 0;
+    std::vector<int> l2p = s->l2p;
+    std::vector<qv::Gate> swaps;
+    static const double sw[16] = {1, 0, 0, 0, 0, 0, 1, 0, 0, 1, 0, 0, 0, 0, 0, 1};
+    for (int q = 0; q < (int)l2p.size(); q++) {
+        while (l2p[q] != q) {
+            const int p = l2p[q];
+            int r = -1;
+            for (int x = 0; x < (int)l2p.size(); x++)
+                if (l2p[x] == q) r = x;
+            qv::Gate g;
+            g.qubits = {p, q};   // physical bits
+            g.mat.resize(16);
+            for (int i = 0; i < 16; i++) g.mat[i] = qv::cd(sw[i], 0.0);
+            swaps.push_back(g);
+            l2p[r] = p;
+            l2p[q] = q;
+        }
+    }
+    s->l2p.clear();   // the swap gates address physical bits: identity map while they run
+    int rc = run_gates_locked(s, swaps, QVMCUDA_FUSE);
+    if (rc) return rc;
+    s->l2p = l2p;
+    return 0;
+}
+
+int reduce_locked(qvmcuda_state* s, uint64_t count, int mode, uint32_t q, uint64_t dim, double* out) {
+    uint64_t blocks = (count + QV_THREADS - 1) / QV_THREADS;
+    if (blocks > kReduceBlocks) blocks = kReduceBlocks;
+    if (blocks == 0) blocks = 1;
+    qv_reduce_kernel<<<(int)blocks, QV_THREADS, 0, s->stream>>>(s->d_amps, count, mode, q, dim, s->d_partial);
+    qv_final_sum_kernel<<<1, QV_THREADS, 0, s->stream>>>(s->d_partial, (uint32_t)blocks, s->d_partial + kReduceBlocks);
+    g_launches += 2;
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(out, s->d_partial + kReduceBlocks, sizeof(double), cudaMemcpyDeviceToHost, s->stream));
+    CK(cudaStreamSynchronize(s->stream));
+    return 0;
+}
+
+int elementwise_locked(qvmcuda_state* s, int mode, uint32_t q, uint32_t q2, uint32_t keep, double f) {
+    uint64_t blocks = (s->n_amps + QV_THREADS - 1) / QV_THREADS;
+    const uint64_t cap = (uint64_t)s->sm_count * 8 * 4;
+    if (blocks > cap) blocks = cap;
+    qv_elementwise_kernel<<<(int)blocks, QV_THREADS, 0, s->stream>>>(s->d_amps, s->n_amps, mode, q, q2, keep, f);
+    g_launches++;
+    CK(cudaGetLastError());
+    return 0;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* qvmcuda_last_error(void) { return g_err.c_str(); }
+
+int qvmcuda_device_count(int* count) {
+    if (!count) return fail("null argument");
+    CK(cudaGetDeviceCount(count));
+    return 0;
+}
+
+int qvmcuda_launch_count(uint64_t* count) {
+    if (!count) return fail("null argument");
+    *count = g_launches.load();
+    return 0;
+}
+
+int qvmcuda_state_create(uint64_t n_amplitudes, int device, qvmcuda_state** out) {
+    if (!out) return fail("null argument");
+    *out = nullptr;
+    const int nb = log2_exact(n_amplitudes);
+    if (nb < 1) return fail("state length must be a power of two >= 2");
+    int count = 0;
+    CK(cudaGetDeviceCount(&count));
+    if (count < 1) return fail("no CUDA device: libqvmcuda has no CPU fallback");
+    if (device < 0 || device >= count) return fail("device ordinal out of range");
+    DeviceGuard dg(device);
+    if (!dg.ok) return fail("cannot select device");
+    qvmcuda_state* s = new qvmcuda_state();
+    s->device = device;
+    s->n_amps = n_amplitudes;
+    s->n_bits = nb;
+    cudaError_t e = cudaMalloc((void**)&s->d_amps, n_amplitudes * sizeof(qvc));
+    if (e != cudaSuccess) {
+        delete s;
+        return fail(std::string("cudaMalloc of the amplitude vector: ") + cudaGetErrorString(e));
+    }
+    e = cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaMalloc((void**)&s->d_partial, (kReduceBlocks + 1) * sizeof(double));
+    if (e == cudaSuccess) e = cudaMemsetAsync(s->d_amps, 0, n_amplitudes * sizeof(qvc), s->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(s->stream);
+    if (e != cudaSuccess) {
+        cudaFree(s->d_amps);
+        cudaFree(s->d_partial);
+        if (s->stream) cudaStreamDestroy(s->stream);
+        delete s;
+        return fail(std::string("state setup: ") + cudaGetErrorString(e));
+    }
+    s->own_stream = true;
+    cudaDeviceGetAttribute(&s->sm_count, cudaDevAttrMultiProcessorCount, device);
+    s->l2p.resize(nb);
+    for (int i = 0; i < nb; i++) s->l2p[i] = i;
+    s->peers.base[0] = s->d_amps;
+    *out = s;
+    return 0;
+}
+
+int qvmcuda_state_destroy(qvmcuda_state* s) {
+    if (!s) return 0;
+    {
+        std::lock_guard<std::mutex> lk(s->mu);
+        DeviceGuard dg(s->device);
+        cudaStreamSynchronize(s->stream);
+        for (void* p : s->opened) cudaIpcCloseMemHandle(p);
+        cudaFree(s->d_amps);
+        cudaFree(s->d_partial);
+        if (s->own_stream && s->stream) cudaStreamDestroy(s->stream);
+        s->d_amps = nullptr;
+    }
+    delete s;
+    return 0;
+}
+
+int qvmcuda_state_length(qvmcuda_state* s, uint64_t* n) {
+    if (!s || !n) return fail("null argument");
+    *n = s->n_amps;
+    return 0;
+}
+
+int qvmcuda_state_set_stream(qvmcuda_state* s, uint64_t cuda_stream) {
+    if (!s) return fail("null argument");
+    std::lock_guard<std::mutex> lk(s->mu);
+    DeviceGuard dg(s->device);
+    CK(cudaStreamSynchronize(s->stream));
+    if (s->own_stream && s->stream) cudaStreamDestroy(s->stream);
+    s->stream = (cudaStream_t)(uintptr_t)cuda_stream;
+    s->own_stream = false;
+    return 0;
+}
+
+int qvmcuda_synchronize(qvmcuda_state* s) {
+    if (!s) return fail("null argument");
+    std::lock_guard<std::mutex> lk(s->mu);
+    DeviceGuard dg(s->device);
+    CK(cudaStreamSynchronize(s->stream));
+    return 0;
+}
+
+int qvmcuda_download(qvmcuda_state* s, double* dst, uint64_t offset, uint64_t count) {
+    if (!s || !dst) return fail("null argument");
+    std::lock_guard<std::mutex> lk(s->mu);
+    if (offset > s->n_amps || count > s->n_amps - offset) return fail("download range out of bounds");
+    DeviceGuard dg(s->device);
+    if (int rc = canonicalize_locked(s)) return rc;
+    CK(cudaMemcpyAsync(dst, s->d_amps + offset, count * sizeof(qvc), cudaMemcpyDeviceToHost, s->stream));
+    CK(cudaStreamSynchronize(s->stream));
+    return 0;
+}
+
+int qvmcuda_upload(qvmcuda_state* s, const double* src, uint64_t offset, uint64_t count) {
+    if (!s || !src) return fail("null argument");
+    std::lock_guard<std::mutex> lk(s->mu);
+    if (offset > s->n_amps || count > s->n_amps - offset) return fail("upload range out of bounds");
+    DeviceGuard dg(s->device);
+    if (int rc = canonicalize_locked(s)) return rc;
+    CK(cudaMemcpyAsync(s->d_amps + offset, src, count * sizeof(qvc), cudaMemcpyHostToDevice, s->stream));
+    CK(cudaStreamSynchronize(s->stream));
+    return 0;
+}
+
+int qvmcuda_set_basis_state(qvmcuda_state* s, uint64_t basis) {
+    if (!s) return fail("null argument");
+    std::lock_guard<std::mutex> lk(s->mu);
+    if (basis >= s->n_amps) return fail("basis state out of range");
+    DeviceGuard dg(s->device);
+    for (size_t i = 0; i < s->l2p.size(); i++) s->l2p[i] = (int)i;   // content is replaced: layout resets
+    CK(cudaMemsetAsync(s->d_amps, 0, s->n_amps * sizeof(qvc), s->stream));
+    qv_set_one_kernel<<<1, 1, 0, s->stream>>>(s->d_amps, basis);
+    g_launches++;
+    CK(cudaGetLastError());
+    return 0;
+}
+
+int qvmcuda_set_zero_state(qvmcuda_state* s) { return qvmcuda_set_basis_state(s, 0); }
+
+int qvmcuda_copy(qvmcuda_state* dst, qvmcuda_state* src) {
+    if (!dst || !src) return fail("null argument");
+    if (dst == src) return 0;
+    std::lock(dst->mu, src->mu);
+    std::lock_guard<std::mutex> l1(dst->mu, std::adopt_lock), l2(src->mu, std::adopt_lock);
+    DeviceGuard dg(src->device);
+    if (int rc = canonicalize_locked(src)) return rc;
+    CK(cudaStreamSynchronize(src->stream));
+    const uint64_t n = dst->n_amps < src->n_amps ? dst->n_amps : src->n_amps;
+    if (n == dst->n_amps)
+        for (size_t i = 0; i < dst->l2p.size(); i++) dst->l2p[i] = (int)i;
+    CK(cudaMemcpyAsync(dst->d_amps, src->d_amps, n * sizeof(qvc), cudaMemcpyDefault, dst->stream));
+    CK(cudaStreamSynchronize(dst->stream));
+    return 0;
+}
+
+int qvmcuda_apply_gates(qvmcuda_state* s, int n_gates, const int32_t* ks, const int32_t* qubits,
+                        const double* matrices, uint32_t flags) {
+    if (!s || (n_gates > 0 && (!ks || !qubits || !matrices))) return fail("null argument");
+    std::vector<qv::Gate> gates;
+    if (int rc = gates_from_flat(n_gates, ks, qubits, matrices, gates)) return rc;
+    std::lock_guard<std::mutex> lk(s->mu);
+    DeviceGuard dg(s->device);
+    return run_gates_locked(s, gates, flags);
+}
+
+int qvmcuda_apply_matrix(qvmcuda_state* s, int k, const int32_t* qubits, const double* matrix) {
+    const int32_t ks[1] = {k};
+    return qvmcuda_apply_gates(s, 1, ks, qubits, matrix, 0);
+}
+
+int qvmcuda_tape_compile(int n_qubits, int n_gates, const int32_t* ks, const int32_t* qubits,
+                         const double* matrices, uint32_t flags, qvmcuda_tape** out) {
+    if (!out) return fail("null argument");
+    *out = nullptr;
+    std::vector<qv::Gate> gates;
+    if (int rc = gates_from_flat(n_gates, ks, qubits, matrices, gates)) return rc;
+    qvmcuda_tape* t = new qvmcuda_tape();
+    t->flags = flags;
+    try {
+        t->tape = qv::compile(gates, n_qubits, make_options(nullptr, flags));
+    } catch (const std::exception& e) {
+        delete t;
+        return fail(std::string("schedule: ") + e.what());
+    }
+    layout_tape(t);
+    *out = t;
+    return 0;
+}
+
+int qvmcuda_tape_run(qvmcuda_state* s, qvmcuda_tape* t) {
+    if (!s || !t) return fail("null argument");
+    std::lock_guard<std::mutex> lk(s->mu);
+    std::lock_guard<std::mutex> lt(t->mu);
+    if (t->tape.n_bits != s->n_bits) return fail("tape was compiled for a different number of qubits");
+    if (s->world != 1) return fail("precompiled tapes are single-device; use qvmcuda_apply_gates on shards");
+    DeviceGuard dg(s->device);
+    // a tape is compiled against the identity layout
+    if (int rc = canonicalize_locked(s)) return rc;
+    if (t->tape.steps.empty()) {
+        s->l2p = t->tape.l2p;
+        return 0;
+    }
+    uint8_t*& d_buf = t->d_blobs[s->device];
+    if (!d_buf) {
+        std::vector<uint8_t> host(t->total_bytes, 0);
+        for (size_t i = 0; i < t->tape.steps.size(); i++) {
+            const qv::Step& st = t->tape.steps[i];
+            const std::vector<qv::cd>& src = st.kind == qv::Step::TILE ? st.tables : st.bigmat;
+            if (!src.empty()) std::memcpy(host.data() + t->offsets[i], src.data(), src.size() * sizeof(qv::cd));
+        }
+        host.resize(t->total_bytes ? t->total_bytes : 256, 0);
+        CK(cudaMalloc((void**)&d_buf, host.size()));
+        CK(cudaMemcpy(d_buf, host.data(), host.size(), cudaMemcpyHostToDevice));
+    }
+    if (int rc = run_steps(s, t->tape, t->offsets, d_buf)) return rc;
+    s->l2p = t->tape.l2p;
+    return 0;
+}
+
+int qvmcuda_tape_info(qvmcuda_tape* t, int64_t info[8]) {
+    if (!t || !info) return fail("null argument");
+    std::memset(info, 0, 8 * sizeof(int64_t));
+    info[0] = (int64_t)t->tape.steps.size();
+    info[1] = t->tape.n_gates;
+    info[2] = t->tape.n_atoms;
+    for (const qv::Step& st : t->tape.steps) info[st.kind == qv::Step::TILE ? 3 : 4]++;
+    info[5] = (int64_t)t->total_bytes;
+    return 0;
+}
+
+int qvmcuda_tape_describe(qvmcuda_tape* t, char* buf, uint64_t buflen) {
+    if (!t || !buf || buflen == 0) return fail("null argument");
+    const std::string s = qv::describe(t->tape);
+    std::strncpy(buf, s.c_str(), buflen - 1);
+    buf[buflen - 1] = 0;
+    return 0;
+}
+
+int qvmcuda_tape_destroy(qvmcuda_tape* t) {
+    if (!t) return 0;
+    for (auto& kv : t->d_blobs) {
+        DeviceGuard dg(kv.first);
+        cudaFree(kv.second);
+    }
+    delete t;
+    return 0;
+}
+
+int qvmcuda_prob_excited(qvmcuda_state* s, int qubit, double* p) {
+    if (!s || !p) return fail("null argument");
+    std::lock_guard<std::mutex> lk(s->mu);
+    if (qubit < 0 || qubit >= s->n_bits) return fail("qubit out of range");
+    DeviceGuard dg(s->device);
+    return reduce_locked(s, s->n_amps / 2, 1, (uint32_t)s->l2p[qubit], 0, p);
+}
+
+int qvmcuda_prob_ground(qvmcuda_state* s, int qubit, double* p) {
+    if (!s || !p) return fail("null argument");
+    std::lock_guard<std::mutex> lk(s->mu);
+    if (qubit < 0 || qubit >= s->n_bits) return fail("qubit out of range");
+    DeviceGuard dg(s->device);
+    return reduce_locked(s, s->n_amps / 2, 3, (uint32_t)s->l2p[qubit], 0, p);
+}
+
+int qvmcuda_norm2(qvmcuda_state* s, double* out) {
+    if (!s || !out) return fail("null argument");
+    std::lock_guard<std::mutex> lk(s->mu);
+    DeviceGuard dg(s->device);
+    return reduce_locked(s, s->n_amps, 0, 0, 0, out);
+}
+
+int qvmcuda_scale(qvmcuda_state* s, double factor) {
+    if (!s) return fail("null argument");
+    std::lock_guard<std::mutex> lk(s->mu);
+    DeviceGuard dg(s->device);
+    return elementwise_locked(s, 0, 0, 0, 0, factor);
+}
+
+int qvmcuda_normalize(qvmcuda_state* s) {
+    double n2 = 0.0;
+    if (int rc = qvmcuda_norm2(s, &n2)) return rc;
+    return qvmcuda_scale(s, 1.0 / sqrt(n2));
+}
+
+int qvmcuda_collapse(qvmcuda_state* s, int qubit, int keep_bit, double inv_norm) {
+    if (!s) return fail("null argument");
+    std::lock_guard<std::mutex> lk(s->mu);
+    if (qubit < 0 || qubit >= s->n_bits) return fail("qubit out of range");
+    DeviceGuard dg(s->device);
+    return elementwise_locked(s, 1, (uint32_t)s->l2p[qubit], 0, keep_bit ? 1u : 0u, inv_norm);
+}
+
+int qvmcuda_sample(qvmcuda_state* s, const double* uniforms, uint64_t n_shots, uint64_t* out, int strict) {
+    if (!s || (n_shots && (!uniforms || !out))) return fail("null argument");
+    if (n_shots == 0) return 0;
+    std::lock_guard<std::mutex> lk(s->mu);
+    DeviceGuard dg(s->device);
+    if (int rc = canonicalize_locked(s)) return rc;
+    const uint64_t n1 = (s->n_amps + QV_SB - 1) / QV_SB;
+    const uint64_t n2 = (n1 + QV_SB - 1) / QV_SB;
+    double *d_l1 = nullptr, *d_l2 = nullptr, *d_top = nullptr, *d_u = nullptr;
+    uint64_t* d_out = nullptr;
+    CK(cudaMallocAsync((void**)&d_l1, n1 * sizeof(double), s->stream));
+    CK(cudaMallocAsync((void**)&d_l2, n2 * sizeof(double), s->stream));
+    CK(cudaMallocAsync((void**)&d_top, n2 * sizeof(double), s->stream));
+    CK(cudaMallocAsync((void**)&d_u, n_shots * sizeof(double), s->stream));
+    CK(cudaMallocAsync((void**)&d_out, n_shots * sizeof(uint64_t), s->stream));
+    CK(cudaMemcpyAsync(d_u, uniforms, n_shots * sizeof(double), cudaMemcpyHostToDevice, s->stream));
+    auto warps_grid = [&](uint64_t blocks) {
+        uint64_t g = (blocks * 32 + QV_THREADS - 1) / QV_THREADS;
+        const uint64_t cap = (uint64_t)s->sm_count * 8 * 4;
+        return (int)(g > cap ? cap : (g ? g : 1));
+    };
+    qv_sample_build_kernel<<<warps_grid(n1), QV_THREADS, 0, s->stream>>>(s->d_amps, nullptr, s->n_amps, d_l1, n1);
+    qv_sample_build_kernel<<<warps_grid(n2), QV_THREADS, 0, s->stream>>>(nullptr, d_l1, n1, d_l2, n2);
+    qv_sample_top_kernel<<<1, 32, 0, s->stream>>>(d_l2, n2, d_top);
+    qv_sample_descend_kernel<<<(int)((n_shots + 127) / 128), 128, 0, s->stream>>>(s->d_amps, s->n_amps, d_l1, n1, d_top, n2,
+                                                                               d_u, n_shots, strict ? 1 : 0, d_out);
+    g_launches += 4;
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(out, d_out, n_shots * sizeof(uint64_t), cudaMemcpyDeviceToHost, s->stream));
+    cudaFreeAsync(d_l1, s->stream);
+    cudaFreeAsync(d_l2, s->stream);
+    cudaFreeAsync(d_top, s->stream);
+    cudaFreeAsync(d_u, s->stream);
+    cudaFreeAsync(d_out, s->stream);
+    CK(cudaStreamSynchronize(s->stream));
+    return 0;
+}
+
+// ------------------------------------------------------------------ density matrix
+int qvmcuda_density_apply_kraus(qvmcuda_state* s, int n_qubits, int k, const int32_t* qubits, int m,
+                                const double* kraus, uint32_t flags) {
+    if (!s || !qubits || (m > 0 && !kraus)) return fail("null argument");
+    if (s->n_bits != 2 * n_qubits) return fail("state length is not 4^n_qubits");
+    if (k < 1 || k > 8) return fail("kraus operator arity out of range (1..8)");
+    if (m == 0) return 0;
+    const size_t d = (size_t)1 << k;
+    const qv::cd* K = reinterpret_cast<const qv::cd*>(kraus);
+    std::vector<qv::Gate> gates;
+    if (m == 1) {
+        // single-kraus: conj(K) on the column bits, then K on the row bits (src/apply-gate.lisp:56-65)
+        qv::Gate gc, gr;
+        gc.mat.resize(d * d);
+        gr.mat.resize(d * d);
+        for (size_t i = 0; i < d * d; i++) {
+            gc.mat[i] = std::conj(K[i]);
+            gr.mat[i] = K[i];
+        }
+        for (int j = 0; j < k; j++) {
+            gc.qubits.push_back(qubits[j]);
+            gr.qubits.push_back(qubits[j] + n_qubits);
+        }
+        gates.push_back(std::move(gc));
+        gates.push_back(std::move(gr));
+    } else {
+        // kraus-list: ONE superoperator S = sum_j K_j (x) conj(K_j) on (row bits, column bits)
+        // instead of the reference's copy / apply / add / restore loop (src/apply-gate.lisp:79-99).
+        qv::Gate g;
+        const size_t D = d * d;
+        g.mat.assign(D * D, qv::cd(0.0, 0.0));
+        for (int j = 0; j < m; j++) {
+            const qv::cd* Kj = K + (size_t)j * d * d;
+            for (size_t r1 = 0; r1 < d; r1++)
+                for (size_t c1 = 0; c1 < d; c1++)
+                    for (size_t r2 = 0; r2 < d; r2++)
+                        for (size_t c2 = 0; c2 < d; c2++)
+                            g.mat[((r1 << k) | c1) * D + ((r2 << k) | c2)] += Kj[r1 * d + r2] * std::conj(Kj[c1 * d + c2]);
+        }
+        for (int j = 0; j < k; j++) g.qubits.push_back(qubits[j]);
+        for (int j = 0; j < k; j++) g.qubits.push_back(qubits[j] + n_qubits);
+        gates.push_back(std::move(g));
+    }
+    std::lock_guard<std::mutex> lk(s->mu);
+    DeviceGuard dg(s->device);
+    return run_gates_locked(s, gates, flags | QVMCUDA_FUSE);
+}
+
+int qvmcuda_density_prob_excited(qvmcuda_state* s, int n_qubits, int qubit, double* p) {
+    if (!s || !p) return fail("null argument");
+    std::lock_guard<std::mutex> lk(s->mu);
+    if (s->n_bits != 2 * n_qubits) return fail("state length is not 4^n_qubits");
+    if (qubit < 0 || qubit >= n_qubits) return fail("qubit out of range");
+    DeviceGuard dg(s->device);
+    if (int rc = canonicalize_locked(s)) return rc;
+    return reduce_locked(s, (1ull << n_qubits) / 2, 2, (uint32_t)qubit, 1ull << n_qubits, p);
+}
+
+int qvmcuda_density_collapse(qvmcuda_state* s, int n_qubits, int qubit, int keep_bit, double inv_norm) {
+    if (!s) return fail("null argument");
+    std::lock_guard<std::mutex> lk(s->mu);
+    if (s->n_bits != 2 * n_qubits) return fail("state length is not 4^n_qubits");
+    if (qubit < 0 || qubit >= n_qubits) return fail("qubit out of range");
+    DeviceGuard dg(s->device);
+    if (int rc = canonicalize_locked(s)) return rc;
+    return elementwise_locked(s, 2, (uint32_t)qubit, (uint32_t)(qubit + n_qubits), keep_bit ? 1u : 0u, inv_norm);
+}
+
+int qvmcuda_density_measure_discard(qvmcuda_state* s, int n_qubits, int qubit) {
+    if (!s) return fail("null argument");
+    std::lock_guard<std::mutex> lk(s->mu);
+    if (s->n_bits != 2 * n_qubits) return fail("state length is not 4^n_qubits");
+    if (qubit < 0 || qubit >= n_qubits) return fail("qubit out of range");
+    DeviceGuard dg(s->device);
+    if (int rc = canonicalize_locked(s)) return rc;
+    return elementwise_locked(s, 3, (uint32_t)qubit, (uint32_t)(qubit + n_qubits), 0, 1.0);
+}
+
+int qvmcuda_density_diag_probs(qvmcuda_state* s, int n_qubits, double* out) {
+    if (!s || !out) return fail("null argument");
+    std::lock_guard<std::mutex> lk(s->mu);
+    if (s->n_bits != 2 * n_qubits) return fail("state length is not 4^n_qubits");
+    DeviceGuard dg(s->device);
+    if (int rc = canonicalize_locked(s)) return rc;
+    const uint64_t dim = 1ull << n_qubits;
+    double* d_out = nullptr;
+    CK(cudaMallocAsync((void**)&d_out, dim * sizeof(double), s->stream));
+    qv_diag_probs_kernel<<<(int)((dim + QV_THREADS - 1) / QV_THREADS), QV_THREADS, 0, s->stream>>>(s->d_amps, dim, d_out);
+    g_launches++;
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(out, d_out, dim * sizeof(double), cudaMemcpyDeviceToHost, s->stream));
+    cudaFreeAsync(d_out, s->stream);
+    CK(cudaStreamSynchronize(s->stream));
+    return 0;
+}
+
+// ------------------------------------------------------------------ multi-GPU shards
+int qvmcuda_shard_export(qvmcuda_state* s, uint8_t handle[64]) {
+    if (!s || !handle) return fail("null argument");
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+    std::lock_guard<std::mutex> lk(s->mu);
+    DeviceGuard dg(s->device);
+    cudaIpcMemHandle_t h;
+    CK(cudaIpcGetMemHandle(&h, s->d_amps));
+    std::memcpy(handle, &h, 64);
+    return 0;
+}
+
+int qvmcuda_shard_attach(qvmcuda_state* s, int rank, int world, const uint8_t* handles) {
+    if (!s || !handles) return fail("null argument");
+    if (world < 1 || world > QV_MAX_PEERS || (world & (world - 1))) return fail("world size must be 1, 2, 4 or 8");
+    if (rank < 0 || rank >= world) return fail("rank out of range");
+    std::lock_guard<std::mutex> lk(s->mu);
+    DeviceGuard dg(s->device);
+    for (int r = 0; r < world; r++) {
+        if (r == rank) {
+            s->peers.base[r] = s->d_amps;
+            continue;
+        }
+        cudaIpcMemHandle_t h;
+        std::memcpy(&h, handles + 64 * (size_t)r, 64);
+        void* p = nullptr;
+        CK(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
+        s->opened.push_back(p);
+        s->peers.base[r] = (qvc*)p;
+    }
+    s->rank = rank;
+    s->world = world;
+    const int total = s->n_bits + log2_exact((uint64_t)world);
+    s->l2p.resize(total);
+    for (int i = 0; i < total; i++) s->l2p[i] = i;
+    return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,442 @@
+"""Host-side mirror of the reference QVM API for the hot path, over libqvmcuda.
+
+SBCL is not available in the build image, so the Lisp shim in lisp/ can only be
+written, not exercised; this module drives the SAME C ABI in the order the Lisp
+generics would (SURVEY.md section 3 call stacks) under the reference's names:
+
+    make_qvm / make_density_qvm      qvm:make-qvm (src/qvm.lisp:150-164), make-density-qvm (src/density-qvm.lisp:60-71)
+    load_program / run / run_program src/classical-memory-mixin.lisp:114-159, src/execution.lisp:13-59
+    apply_gate_to_state              src/apply-gate.lisp:106-212
+    measure / measure_all            src/measurement.lisp:87-162
+    amplitudes                       qvm::amplitudes (src/qvm.lisp:63-69)
+
+Random draws stay on the host (numpy's MT19937 RandomState, the reference uses
+mt19937 as well); the library only ever receives uniforms.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+from typing import Dict, List, Optional, Sequence, Tuple
+
+import numpy as np
+
+from . import _lib as L
+from . import gates as G
+from .quil import Declare, GateApp, Halt, Measure, Program, Reset, parse_quil
+
+# ---- src/config.lisp:41-58 switches that keep their meaning ---------------------------------
+compile_before_running = False      # *compile-before-running*
+fuse_gates_during_compilation = True  # *fuse-gates-during-compilation*
+compile_measure_chains = True       # *compile-measure-chains*
+
+
+class DeviceVector:
+    """A device-resident CFLONUM vector: what `allocate-vector` on a CUDA-ALLOCATION returns
+    (src/allocator.lisp:47-62).  Zero-initialised; freed by close() / the finalizer."""
+
+    def __init__(self, length: int, device: int = 0):
+        self.length = int(length)
+        self.device = device
+        h = C.c_void_p()
+        L.check(L.lib().qvmcuda_state_create(self.length, device, C.byref(h)))
+        self.handle = h
+
+    def close(self):
+        if getattr(self, "handle", None):
+            L.lib().qvmcuda_state_destroy(self.handle)
+            self.handle = None
+
+    __del__ = close
+
+    # -- state protocol ------------------------------------------------------------------
+    def download(self, offset: int = 0, count: Optional[int] = None) -> np.ndarray:
+        count = self.length - offset if count is None else count
+        out = np.empty(count, dtype=np.complex128)
+        L.check(L.lib().qvmcuda_download(self.handle, L.ptr(out), offset, count))
+        return out
+
+    def upload(self, data, offset: int = 0) -> None:
+        a = np.ascontiguousarray(data, dtype=np.complex128)
+        L.check(L.lib().qvmcuda_upload(self.handle, L.ptr(a), offset, a.size))
+
+    def set_zero_state(self): L.check(L.lib().qvmcuda_set_zero_state(self.handle))
+    def set_basis_state(self, b: int): L.check(L.lib().qvmcuda_set_basis_state(self.handle, int(b)))
+    def synchronize(self): L.check(L.lib().qvmcuda_synchronize(self.handle))
+    def set_stream(self, cuda_stream: int): L.check(L.lib().qvmcuda_state_set_stream(self.handle, int(cuda_stream)))
+
+    def copy_from(self, other: "DeviceVector"):
+        L.check(L.lib().qvmcuda_copy(self.handle, other.handle))
+
+    # -- operator API -----------------------------------------------------------------------
+    def apply_matrix(self, matrix, qubits: Sequence[int]) -> None:
+        """qvm:apply-matrix-operator; QUBITS in Quil argument order."""
+        ks, qf, mf = L.flatten_gates([(matrix, tuple(qubits))])
+        L.check(L.lib().qvmcuda_apply_matrix(self.handle, int(ks[0]), L.ptr(qf), L.ptr(mf)))
+
+    def apply_gates(self, gates, fuse: bool = True, absorb_swaps: bool = False) -> None:
+        if not gates:
+            return
+        ks, qf, mf = L.flatten_gates(gates)
+        flags = (L.FUSE if fuse else 0) | (L.ABSORB_SWAPS if absorb_swaps else 0)
+        L.check(L.lib().qvmcuda_apply_gates(self.handle, len(gates), L.ptr(ks), L.ptr(qf), L.ptr(mf), flags))
+
+    def run_tape(self, tape: "Tape") -> None:
+        L.check(L.lib().qvmcuda_tape_run(self.handle, tape.handle))
+
+    # -- measurement protocol ---------------------------------------------------------------
+    def prob_excited(self, q: int) -> float:
+        p = C.c_double()
+        L.check(L.lib().qvmcuda_prob_excited(self.handle, q, C.byref(p)))
+        return p.value
+
+    def prob_ground(self, q: int) -> float:
+        p = C.c_double()
+        L.check(L.lib().qvmcuda_prob_ground(self.handle, q, C.byref(p)))
+        return p.value
+
+    def norm2(self) -> float:
+        p = C.c_double()
+        L.check(L.lib().qvmcuda_norm2(self.handle, C.byref(p)))
+        return p.value
+
+    def scale(self, f: float): L.check(L.lib().qvmcuda_scale(self.handle, float(f)))
+    def normalize(self): L.check(L.lib().qvmcuda_normalize(self.handle))
+
+    def collapse(self, q: int, keep_bit: int, inv_norm: float):
+        L.check(L.lib().qvmcuda_collapse(self.handle, q, keep_bit, float(inv_norm)))
+
+    def sample(self, uniforms, strict: bool = False) -> np.ndarray:
+        u = np.ascontiguousarray(uniforms, dtype=np.float64)
+        out = np.empty(u.size, dtype=np.uint64)
+        L.check(L.lib().qvmcuda_sample(self.handle, L.ptr(u), u.size, L.ptr(out), 1 if strict else 0))
+        return out
+
+    # -- density ------------------------------------------------------------------------------
+    def density_apply_kraus(self, n: int, kraus, qubits: Sequence[int], fuse: bool = True):
+        ks = np.ascontiguousarray(np.stack([np.asarray(k, dtype=np.complex128) for k in kraus]))
+        q = np.ascontiguousarray(list(reversed([int(x) for x in qubits])), dtype=np.int32)
+        L.check(L.lib().qvmcuda_density_apply_kraus(self.handle, n, len(q), L.ptr(q), len(kraus), L.ptr(ks),
+                                                    L.FUSE if fuse else 0))
+
+    def density_prob_excited(self, n: int, q: int) -> float:
+        p = C.c_double()
+        L.check(L.lib().qvmcuda_density_prob_excited(self.handle, n, q, C.byref(p)))
+        return p.value
+
+    def density_collapse(self, n, q, keep_bit, inv_norm):
+        L.check(L.lib().qvmcuda_density_collapse(self.handle, n, q, keep_bit, float(inv_norm)))
+
+    def density_measure_discard(self, n, q):
+        L.check(L.lib().qvmcuda_density_measure_discard(self.handle, n, q))
+
+    def density_diag_probs(self, n) -> np.ndarray:
+        out = np.empty(1 << n, dtype=np.float64)
+        L.check(L.lib().qvmcuda_density_diag_probs(self.handle, n, L.ptr(out)))
+        return out
+
+
+class Tape:
+    """A compiled gate sequence: what COMPILE-LOADED-PROGRAM builds once (src/qvm.lisp:166-175)."""
+
+    def __init__(self, n_qubits: int, gates, fuse: bool = True, absorb_swaps: bool = False):
+        ks, qf, mf = L.flatten_gates(gates)
+        h = C.c_void_p()
+        flags = (L.FUSE if fuse else 0) | (L.ABSORB_SWAPS if absorb_swaps else 0)
+        L.check(L.lib().qvmcuda_tape_compile(n_qubits, len(gates), L.ptr(ks), L.ptr(qf), L.ptr(mf), flags, C.byref(h)))
+        self.handle = h
+        self.n_gates = len(gates)
+
+    def info(self) -> Dict[str, int]:
+        a = np.zeros(8, dtype=np.int64)
+        L.check(L.lib().qvmcuda_tape_info(self.handle, L.ptr(a)))
+        return {"passes": int(a[0]), "gates": int(a[1]), "atoms": int(a[2]), "tile_passes": int(a[3]),
+                "generic_passes": int(a[4]), "table_bytes": int(a[5])}
+
+    def describe(self) -> str:
+        buf = C.create_string_buffer(1 << 16)
+        L.check(L.lib().qvmcuda_tape_describe(self.handle, buf, len(buf)))
+        return buf.value.decode()
+
+    def close(self):
+        if getattr(self, "handle", None):
+            L.lib().qvmcuda_tape_destroy(self.handle)
+            self.handle = None
+
+    __del__ = close
+
+
+# ---------------------------------------------------------------------------- states
+class PureState:
+    """PURE-STATE (src/state-representation.lisp:58-167) over a device vector."""
+
+    def __init__(self, num_qubits: int, device: int = 0):
+        self.num_qubits = num_qubits
+        self.vec = DeviceVector(1 << num_qubits, device)
+        self.vec.set_zero_state()           # (setf (aref amplitudes 0) 1), :92-95
+
+    def state_elements(self) -> np.ndarray: return self.vec.download()
+    def set_state_elements(self, amps): self.vec.upload(amps)
+    def set_to_zero_state(self): self.vec.set_zero_state()
+
+
+class DensityMatrixState:
+    """DENSITY-MATRIX-STATE (src/state-representation.lisp:173-286): vec(rho), row-major, 4^n entries."""
+
+    def __init__(self, num_qubits: int, device: int = 0):
+        self.num_qubits = num_qubits
+        self.vec = DeviceVector(1 << (2 * num_qubits), device)
+        self.vec.set_zero_state()
+
+    def state_elements(self) -> np.ndarray: return self.vec.download()
+    def set_state_elements(self, v): self.vec.upload(v)
+    def set_to_zero_state(self): self.vec.set_zero_state()
+
+    def matrix_view(self) -> np.ndarray:
+        d = 1 << self.num_qubits
+        return self.state_elements().reshape(d, d)
+
+    def measurement_probabilities(self) -> np.ndarray:
+        """DENSITY-MATRIX-STATE-MEASUREMENT-PROBABILITIES :268-286."""
+        return self.vec.density_diag_probs(self.num_qubits)
+
+
+def apply_gate_to_state(gate, state, qubits: Sequence[int]) -> None:
+    """APPLY-GATE-TO-STATE (src/apply-gate.lisp:106-212).  GATE is a matrix, or a list of Kraus
+    matrices (a KRAUS-LIST superoperator).  QUBITS in Quil argument order."""
+    if isinstance(state, PureState):
+        if isinstance(gate, (list, tuple)):
+            raise NotImplementedError("stochastic Kraus evolution of pure states is a 'next' row (SURVEY.md 8f #2)")
+        state.vec.apply_matrix(gate, qubits)
+    else:
+        kraus = list(gate) if isinstance(gate, (list, tuple)) else [gate]
+        state.vec.density_apply_kraus(state.num_qubits, kraus, qubits)
+
+
+# ---------------------------------------------------------------------------- machines
+class BaseQVM:
+    def __init__(self, seed: Optional[int] = None):
+        self.program: Optional[Program] = None
+        self.pc = 0
+        self.rng = np.random.RandomState(seed)      # MT19937, like the reference's mt19937:random
+        self.registers: Dict[str, np.ndarray] = {}
+        self._compiled = None
+
+    # classical memory: only what MEASURE needs (the rest is out of the hot path)
+    def _store(self, target, bit):
+        if target is None:
+            return
+        name, off = target
+        if name not in self.registers:
+            self.registers[name] = np.zeros(max(off + 1, 1), dtype=np.int64)
+        if off >= self.registers[name].size:
+            self.registers[name] = np.resize(self.registers[name], off + 1)
+        self.registers[name][off] = bit
+
+    def load_program(self, program):
+        if isinstance(program, str):
+            program = parse_quil(program)
+        self.program = program
+        self.pc = 0
+        self._compiled = None
+        for ins in program.instructions:
+            if isinstance(ins, Declare):
+                self.registers[ins.name] = np.zeros(ins.length, dtype=np.int64)
+        return self
+
+    def number_of_qubits(self) -> int:
+        return self.state.num_qubits
+
+    def random(self) -> float:
+        return float(self.rng.random_sample())
+
+
+class PureStateQVM(BaseQVM):
+    """PURE-STATE-QVM (src/qvm.lisp:114-175)."""
+
+    def __init__(self, num_qubits: int, device: int = 0, seed: Optional[int] = None):
+        super().__init__(seed)
+        self.state = PureState(num_qubits, device)
+
+    # qvm::amplitudes / (setf qvm::amplitudes) : the device<->host sync points
+    @property
+    def amplitudes(self) -> np.ndarray:
+        return self.state.state_elements()
+
+    @amplitudes.setter
+    def amplitudes(self, v):
+        self.state.set_state_elements(v)
+
+    def reset_quantum_state(self):
+        self.state.set_to_zero_state()
+
+    # -- measurement.lisp:87-105 (interpreted) and compile-gate.lisp:221-254 (compiled) ----
+    def measure(self, q: int) -> int:
+        assert 0 <= q < self.number_of_qubits()
+        p1 = self.state.vec.prob_excited(q)
+        cbit = 0 if p1 == 0.0 else (1 if self.random() <= p1 else 0)
+        inv = 1.0 / math.sqrt(p1) if cbit == 1 else 1.0 / math.sqrt(1.0 - p1)
+        self.state.vec.collapse(q, cbit, inv)
+        return cbit
+
+    def measure_compiled(self, q: int) -> int:
+        p0 = self.state.vec.prob_ground(q)      # WAVEFUNCTION-GROUND-STATE-PROBABILITY
+        keep_zero = self.random() < p0
+        bit = 0 if keep_zero else 1
+        inv = 1.0 / math.sqrt(p0) if keep_zero else 1.0 / math.sqrt(1.0 - p0)
+        self.state.vec.collapse(q, bit, inv)
+        return bit
+
+    def measure_all(self) -> List[int]:
+        """MEASURE-ALL-STATE (pure) src/measurement.lisp:128-143: one uniform, C(b) > p rule, psi <- |b>."""
+        b = int(self.state.vec.sample([self.random()], strict=True)[0])
+        self.state.vec.set_basis_state(b)
+        return [(b >> i) & 1 for i in range(self.number_of_qubits())]
+
+    def sample_multiple(self, n_shots: int) -> np.ndarray:
+        """SAMPLE-WAVEFUNCTION-MULTIPLE-TIMES src/measurement.lisp:246-288 with host-drawn uniforms."""
+        return self.state.vec.sample(self.rng.random_sample(n_shots), strict=False)
+
+    # -- run loop (src/execution.lisp:13-59, src/transition.lisp) ---------------------------------
+    def _gate_list(self, instrs) -> List[Tuple[np.ndarray, Tuple[int, ...]]]:
+        return [(self.program.gate_matrix(i), i.qubits) for i in instrs]
+
+    def run(self):
+        prog = self.program
+        n = self.number_of_qubits()
+        ins = prog.instructions
+        i = 0
+        compiled = compile_before_running
+        while i < len(ins):
+            x = ins[i]
+            if isinstance(x, GateApp):
+                if compiled:
+                    # COMPILE-LOADED-PROGRAM: a maximal run of gates becomes one fused tape
+                    j = i
+                    while j < len(ins) and isinstance(ins[j], GateApp):
+                        j += 1
+                    self.state.vec.apply_gates(self._gate_list(ins[i:j]), fuse=fuse_gates_during_compilation)
+                    i = j
+                    continue
+                self.state.vec.apply_matrix(prog.gate_matrix(x), x.qubits)
+            elif isinstance(x, Measure):
+                if compiled and compile_measure_chains:
+                    # COMPILE-MEASURE-CHAINS src/compile-gate.lisp:551-599
+                    j = i
+                    while j < len(ins) and isinstance(ins[j], Measure):
+                        j += 1
+                    chain = ins[i:j]
+                    if len(chain) >= n and {m.qubit for m in chain} == set(range(n)):
+                        bits = self.measure_all()
+                        for m in chain:
+                            self._store(m.target, bits[m.qubit])
+                        i = j
+                        continue
+                bit = self.measure_compiled(x.qubit) if compiled else self.measure(x.qubit)
+                self._store(x.target, bit)
+            elif isinstance(x, Reset):
+                if x.qubit is None:
+                    self.state.set_to_zero_state()
+                else:
+                    # RESET q = MEASURE q, then X if 1 (src/transition.lisp:76-95)
+                    if self.measure(x.qubit) == 1:
+                        self.state.vec.apply_matrix(G.gate_matrix("X"), (x.qubit,))
+            elif isinstance(x, Halt):
+                break
+            i += 1
+        self.pc = i
+        return self
+
+
+class DensityQVM(BaseQVM):
+    """DENSITY-QVM (src/density-qvm.lisp:33-190): always interpreted (:183-190)."""
+
+    def __init__(self, num_qubits: int, device: int = 0, seed: Optional[int] = None):
+        super().__init__(seed)
+        self.state = DensityMatrixState(num_qubits, device)
+        self.noisy_gate_definitions: Dict[Tuple[str, Tuple[int, ...]], list] = {}
+        self.readout_povms: Dict[int, Tuple[float, float, float, float]] = {}
+
+    @property
+    def amplitudes(self) -> np.ndarray:
+        return self.state.state_elements()
+
+    @amplitudes.setter
+    def amplitudes(self, v):
+        self.state.set_state_elements(v)
+
+    def reset_quantum_state(self):
+        self.state.set_to_zero_state()
+
+    def set_noisy_gate(self, name: str, qubits: Sequence[int], kraus) -> None:
+        """SET-NOISY-GATE src/density-qvm.lisp:73-82."""
+        G.check_kraus_ops(list(kraus))
+        self.noisy_gate_definitions[(name, tuple(qubits))] = list(kraus)
+
+    def set_readout_povm(self, qubit: int, povm) -> None:
+        self.readout_povms[qubit] = tuple(povm)
+
+    def measure(self, q: int) -> int:
+        n = self.number_of_qubits()
+        p1 = self.state.vec.density_prob_excited(n, q)
+        cbit = 0 if p1 == 0.0 else (1 if self.random() <= p1 else 0)
+        inv = 1.0 / p1 if cbit == 1 else 1.0 / (1.0 - p1)
+        self.state.vec.density_collapse(n, q, cbit, inv)
+        return cbit
+
+    def measure_all(self) -> List[int]:
+        """NAIVE-MEASURE-ALL src/measurement.lisp:153-162, then POVM bit flips (density-qvm.lisp:169-180)."""
+        n = self.number_of_qubits()
+        bits = [0] * n
+        for q in range(n - 1, -1, -1):
+            bits[q] = self.measure(q)
+        return [self._perturb(q, b) for q, b in enumerate(bits)]
+
+    def _perturb(self, q: int, bit: int) -> int:
+        povm = self.readout_povms.get(q)
+        if povm is None:
+            return bit
+        p00, p01, p10, p11 = povm          # PERTURB-MEASUREMENT src/channel-qvm.lisp:185-195; p(observed|actual)
+        r = self.random()
+        if bit == 0:
+            return 0 if r <= p00 else 1
+        return 0 if r <= p01 else 1
+
+    def run(self):
+        prog = self.program
+        n = self.number_of_qubits()
+        for x in prog.instructions:
+            if isinstance(x, GateApp):
+                key = (x.name, tuple(x.qubits))
+                if key in self.noisy_gate_definitions and not x.modifiers:
+                    self.state.vec.density_apply_kraus(n, self.noisy_gate_definitions[key], x.qubits)
+                else:
+                    self.state.vec.density_apply_kraus(n, [prog.gate_matrix(x)], x.qubits)
+            elif isinstance(x, Measure):
+                if x.target is None:
+                    self.state.vec.density_measure_discard(n, x.qubit)
+                else:
+                    self._store(x.target, self._perturb(x.qubit, self.measure(x.qubit)))
+            elif isinstance(x, Reset):
+                if x.qubit is None:
+                    self.state.set_to_zero_state()
+                else:
+                    raise NotImplementedError("RESET q on a density matrix is outside the hot path")
+            elif isinstance(x, Halt):
+                break
+        return self
+
+
+def make_qvm(num_qubits: int, device: int = 0, seed: Optional[int] = None) -> PureStateQVM:
+    return PureStateQVM(num_qubits, device, seed)
+
+
+def make_density_qvm(num_qubits: int, device: int = 0, seed: Optional[int] = None) -> DensityQVM:
+    return DensityQVM(num_qubits, device, seed)
+
+
+def run_program(num_qubits: int, program, device: int = 0, seed: Optional[int] = None) -> PureStateQVM:
+    """RUN-PROGRAM src/execution.lisp:46-59."""
+    qvm = make_qvm(num_qubits, device, seed)
+    qvm.load_program(program)
+    return qvm.run()

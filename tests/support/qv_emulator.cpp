@@ -23,7 +23,7 @@ void run_tile_step(qvc* psi, const qv::Step& st) {
     const QvOp* ops = (const QvOp*)(blob + h.off_ops);
     const QvChunk* chunks = (const QvChunk*)(blob + h.off_chunks);
     const qvc* mats = (const qvc*)(blob + h.off_matrices);
-    const qvc* tables = (const qvc*)(blob + h.off_tables);
+    const qvc* tables = (const qvc*)st.tables.data();
     const uint32_t tile_n = 1u << h.T;
     const uint64_t local_mask = (1ull << h.n_local_bits) - 1ull;
     std::vector<qvc> smem(tile_n);
@@ -35,23 +35,18 @@ void run_tile_step(qvc* psi, const qv::Step& st) {
         }
         for (uint32_t r = 0; r < h.n_rounds; r++) {
             const QvRound& rd = rounds[r];
-            uint32_t dep[8];
-            for (uint32_t s = 0; s < 8; s++) {
-                dep[s] = 0;
-                for (uint32_t j = 0; j < rd.m; j++)
-                    if (s >> j & 1) dep[s] |= 1u << rd.regpos[j];
-            }
+            QvRegPos dep{rd.regpos[0], rd.regpos[1], rd.regpos[2]};
             const uint32_t ngroups = tile_n >> rd.m;
             for (uint32_t g = 0; g < ngroups; g++) {
                 uint32_t e0 = g;
                 for (uint32_t j = 0; j < rd.m; j++) e0 = qv_insert_zero(e0, rd.regpos[j]);
                 qvc a[8];
                 for (uint32_t s = 0; s < 8; s++) {
-                    if (s < (1u << rd.m)) a[s] = smem[qv_swz(e0 | dep[s])];
+                    if (s < (1u << rd.m)) a[s] = smem[qv_swz(e0 | qv_dep(s, dep.p0, dep.p1, dep.p2))];
                     else { a[s].x = 0.0; a[s].y = 0.0; }
                 }
                 qv_apply_round(a, rd, ops, chunks, mats, tables, e0, dep, base);
-                for (uint32_t s = 0; s < (1u << rd.m); s++) smem[qv_swz(e0 | dep[s])] = a[s];
+                for (uint32_t s = 0; s < (1u << rd.m); s++) smem[qv_swz(e0 | qv_dep(s, dep.p0, dep.p1, dep.p2))] = a[s];
             }
         }
         for (uint32_t e = 0; e < tile_n; e++) {

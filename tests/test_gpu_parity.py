@@ -1,0 +1,329 @@
+"""GPU parity tests proper (-m gpu): the CUDA path, called through the C ABI, against the oracle on the
+same seeded inputs.  Tolerance = north_star: 1e-12 relative / 1e-14 absolute on amplitudes and
+probabilities; sampled indices bit-exact for identical uniforms."""
+import math
+
+import numpy as np
+import pytest
+
+from helpers import assert_close, rand_state, rand_unitary, random_circuit, run_oracle
+from qvm_b200 import circuits as CC
+from qvm_b200 import gates as G
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def Q():
+    from qvm_b200 import qvm
+    return qvm
+
+
+@pytest.fixture(scope="module")
+def O():
+    from oracle import oracle
+    return oracle
+
+
+def gpu_run(Q, psi, circ, fuse=True, absorb=False, each=False):
+    n = int(math.log2(psi.size))
+    vec = Q.DeviceVector(1 << n)
+    vec.upload(psi)
+    if each:
+        for m, q in circ:
+            vec.apply_matrix(m, q)
+    else:
+        vec.apply_gates(circ, fuse=fuse, absorb_swaps=absorb)
+    out = vec.download()
+    vec.close()
+    return out
+
+
+def test_library_loads_on_gpu(Q):
+    from qvm_b200 import _lib
+    assert _lib.device_count() >= 1
+
+
+@pytest.mark.parametrize("n", [1, 2, 3, 5, 9, 13, 16])
+def test_1q_gate_every_position(Q, O, n):
+    rng = np.random.default_rng(n)
+    for q in range(n):
+        m = rand_unitary(1, rng)
+        a = rand_state(n, q)
+        ref = O.apply_matrix(a.copy(), m, (q,))
+        assert_close(gpu_run(Q, a, [(m, (q,))], each=True), ref)
+
+
+@pytest.mark.parametrize("n", [2, 4, 8, 13, 16])
+def test_2q_gate_positions(Q, O, n):
+    rng = np.random.default_rng(100 + n)
+    pairs = [(a, b) for a in range(n) for b in range(n) if a != b]
+    if len(pairs) > 40:
+        pairs = [pairs[i] for i in rng.choice(len(pairs), 40, replace=False)]
+    for a, b in pairs:
+        m = rand_unitary(2, rng)
+        s = rand_state(n, a * 31 + b)
+        ref = O.apply_matrix(s.copy(), m, (a, b))
+        assert_close(gpu_run(Q, s, [(m, (a, b))], each=True), ref)
+
+
+def test_named_gates_and_permutations(Q, O):
+    n = 12
+    rng = np.random.default_rng(7)
+    for name in ["CNOT", "CZ", "SWAP", "ISWAP", "CCNOT", "CSWAP"]:
+        k = G.STANDARD_GATES[name][0]
+        for _ in range(6):
+            q = tuple(int(x) for x in rng.choice(n, k, replace=False))
+            s = rand_state(n, 3)
+            ref = O.apply_matrix(s.copy(), G.gate_matrix(name), q)
+            assert_close(gpu_run(Q, s, [(G.gate_matrix(name), q)], each=True), ref)
+    # permutation gates compiled as transpositions leave psi'[i] = psi[perm[i]] (compile-gate.lisp:259-309)
+    s = rand_state(n, 4)
+    ref = O.apply_permutation(s.copy(), [0, 1, 2, 3, 4, 5, 7, 6], (2, 9, 5))
+    assert_close(gpu_run(Q, s, [(G.gate_matrix("CCNOT"), (2, 9, 5))], each=True), ref)
+
+
+@pytest.mark.parametrize("k", [3, 4, 5, 8])
+def test_dense_k_qubit_gates(Q, O, k):
+    n = 11
+    rng = np.random.default_rng(k)
+    for _ in range(3):
+        q = tuple(int(x) for x in rng.choice(n, k, replace=False))
+        m = rand_unitary(k, rng)
+        s = rand_state(n, k)
+        ref = O.apply_matrix(s.copy(), m, q)
+        assert_close(gpu_run(Q, s, [(m, q)], each=True), ref)
+
+
+@pytest.mark.parametrize("n", [2, 10, 16, 20])
+@pytest.mark.parametrize("fuse", [True, False])
+def test_qft_parity(Q, O, n, fuse):
+    circ = CC.qft_circuit(range(n))
+    a = rand_state(n)
+    ref = run_oracle(a.copy(), circ)
+    assert_close(gpu_run(Q, a, circ, fuse=fuse), ref)
+
+
+def test_qft_absorbed_swaps_download_canonical(Q, O):
+    n = 15
+    circ = CC.qft_circuit(range(n))
+    a = rand_state(n)
+    ref = run_oracle(a.copy(), circ)
+    assert_close(gpu_run(Q, a, circ, fuse=True, absorb=True), ref)
+
+
+@pytest.mark.parametrize("seed", range(10))
+def test_random_circuits(Q, O, seed):
+    rng = np.random.default_rng(500 + seed)
+    n = int(rng.integers(3, 17))
+    circ = random_circuit(n, 60, rng, max_dense=4)
+    a = rand_state(n, seed)
+    ref = run_oracle(a.copy(), circ)
+    assert_close(gpu_run(Q, a, circ, fuse=True), ref)
+    assert_close(gpu_run(Q, a, circ, fuse=False), ref)
+
+
+def test_random_layer_circuit_20q(Q, O):
+    n = 20
+    circ = CC.random_layer_circuit(n, 3, seed=0)
+    a = rand_state(n)
+    ref = run_oracle(a.copy(), circ)
+    assert_close(gpu_run(Q, a, circ, fuse=True), ref)
+
+
+def test_compiled_tape_reuse(Q, O):
+    n = 16
+    circ = CC.qft_circuit(range(n))
+    tape = Q.Tape(n, circ, fuse=True)
+    info = tape.info()
+    assert info["gates"] == len(circ) and info["passes"] <= 4
+    for seed in (1, 2):
+        a = rand_state(n, seed)
+        vec = Q.DeviceVector(1 << n)
+        vec.upload(a)
+        vec.run_tape(tape)
+        assert_close(vec.download(), run_oracle(a.copy(), circ))
+        vec.close()
+
+
+def test_reductions_and_collapse(Q, O):
+    n = 15
+    a = rand_state(n, 11)
+    vec = Q.DeviceVector(1 << n)
+    vec.upload(a)
+    assert abs(vec.norm2() - O.norm2(a)) <= 1e-12
+    for q in range(n):
+        assert abs(vec.prob_excited(q) - O.prob_excited(a, q)) <= 1e-12
+        assert abs(vec.prob_ground(q) - O.prob_ground(a, q)) <= 1e-12
+    for q, keep in [(0, 1), (7, 0), (14, 1)]:
+        p1 = O.prob_excited(a, q)
+        ref = O.force_measurement(a.copy(), q, keep, p1)
+        vec.upload(a)
+        inv = 1 / math.sqrt(p1) if keep == 1 else 1 / math.sqrt(1 - p1)
+        vec.collapse(q, keep, inv)
+        assert_close(vec.download(), ref)
+    vec.upload(3.0 * a)
+    vec.normalize()
+    assert_close(vec.download(), O.normalize(3.0 * a.copy()))
+    vec.close()
+
+
+@pytest.mark.parametrize("n", [1, 3, 10, 11, 17, 21])
+def test_sampler_bit_exact(Q, O, n):
+    a = rand_state(n, 5)
+    u = np.random.default_rng(2024).random(100000 if n >= 10 else 2000)
+    u[:3] = [0.0, 1.0, 0.5]
+    vec = Q.DeviceVector(1 << n)
+    vec.upload(a)
+    for strict in (False, True):
+        got = vec.sample(u, strict=strict)
+        want = O.sample_tree(a, u, strict)
+        assert (got == want).all(), f"{int((got != want).sum())} sampler mismatches"
+    # against the reference's sequential-scan sampler: only draws within 1e-12 of a CDF step may differ
+    got = vec.sample(u, strict=False)
+    seq = O.sample_multiple(a, u)
+    cdf = O.cdf(a)
+    for i in np.nonzero(got != seq)[0]:
+        lo, hi = sorted((int(got[i]), int(seq[i])))
+        assert np.abs(cdf[lo:hi + 1] - u[i]).min() < 1e-12
+    vec.close()
+
+
+def test_sampler_known_answers(Q, O):
+    # tests/measurement-tests.lisp:184-211 (C(b) > p rule)
+    from test_oracle_golden import SAMPLER_KATS
+    for probs, cases in SAMPLER_KATS:
+        v = np.sqrt(np.array(probs, dtype=np.float64)).astype(np.complex128)
+        vec = Q.DeviceVector(v.size)
+        vec.upload(v)
+        for p, want in cases:
+            assert int(vec.sample([p], strict=True)[0]) == want
+        vec.close()
+
+
+def test_measure_all_basis_states(Q):
+    # tests/measurement-tests.lisp:213-237
+    for i in range(8):
+        qvm = Q.make_qvm(3, seed=i)
+        prog = "\n".join(("X" if (i >> q) & 1 else "I") + f" {q}" for q in range(3))
+        qvm.load_program(prog).run()
+        bits = qvm.measure_all()
+        assert bits == [(i >> q) & 1 for q in range(3)]
+        assert abs(qvm.amplitudes[i] - 1) < 1e-14
+
+
+@pytest.mark.parametrize("n", [1, 2, 4, 6])
+def test_density_unitary_and_kraus(Q, O, n):
+    rng = np.random.default_rng(40 + n)
+    rho = O.zero_density(n)
+    vec = Q.DeviceVector(1 << (2 * n))
+    vec.set_zero_state()
+    for step in range(12):
+        k = 1 if n == 1 or rng.integers(0, 2) else 2
+        q = tuple(int(x) for x in rng.choice(n, k, replace=False))
+        if step % 3 == 2:
+            kr = G.depolarizing_kraus_map(0.1) if k == 1 else G.kraus_kron(G.depolarizing_kraus_map(0.1), G.damping_kraus_map(5.0, 1.0))
+            O.density_apply_kraus(rho, n, kr, q)
+            vec.density_apply_kraus(n, kr, q)
+        else:
+            U = rand_unitary(k, rng)
+            O.density_apply_unitary(rho, n, U, q)
+            vec.density_apply_kraus(n, [U], q)
+    assert_close(vec.download(), rho)
+    assert abs(vec.density_diag_probs(n).sum() - 1) < 1e-12
+    np.testing.assert_allclose(vec.density_diag_probs(n), O.density_diag_probs(rho, n), rtol=1e-12, atol=1e-14)
+    q = n - 1
+    p1 = O.density_prob_excited(rho, n, q)
+    assert abs(vec.density_prob_excited(n, q) - p1) < 1e-12
+    O.density_force_measurement(rho, n, q, 1, p1)
+    vec.density_collapse(n, q, 1, 1 / p1)
+    assert_close(vec.download(), rho)
+    O.density_measure_discard(rho, n, 0)
+    vec.density_measure_discard(n, 0)
+    assert_close(vec.download(), rho)
+    vec.close()
+
+
+def test_density_golden(Q):
+    # tests/state-representation-tests.lisp:41-53: H 0; CNOT 0 1 -> entries 0,3,12,15 = 1/2
+    st = Q.DensityMatrixState(2)
+    Q.apply_gate_to_state(G.gate_matrix("H"), st, (0,))
+    Q.apply_gate_to_state(G.gate_matrix("CNOT"), st, (0, 1))
+    v = st.state_elements()
+    for i in (0, 3, 12, 15):
+        assert abs(v[i] - 0.5) < 1e-14
+    # tests/density-qvm-tests.lisp:142-156: H 0; MEASURE 0 (discard) -> diag(1/2, 1/2)
+    qvm = Q.make_density_qvm(1)
+    qvm.load_program("H 0\nMEASURE 0").run()
+    m = qvm.state.matrix_view()
+    assert abs(m[0, 0] - 0.5) < 1e-14 and abs(m[1, 1] - 0.5) < 1e-14 and abs(m[0, 1]) < 1e-14
+    # tests/density-qvm-tests.lisp:36-44: force-measurement 1 on H|0> keeps trace 1, rho[1,1] = 1
+    qvm = Q.make_density_qvm(1)
+    qvm.load_program("H 0").run()
+    qvm.state.vec.density_collapse(1, 0, 1, 1 / 0.5)
+    m = qvm.state.matrix_view()
+    assert abs(np.trace(m) - 1) < 1e-14 and abs(m[1, 1] - 1) < 1e-14
+
+
+def test_qvm_api_gate_tests(Q):
+    # tests/gate-tests.lisp:162-183: 2-qubit QFT truth table through run-program
+    expected = [[0.5, 0.5, 0.5, 0.5], [0.5, 0.5j, -0.5, -0.5j], [0.5, -0.5, 0.5, -0.5], [0.5, -0.5j, -0.5, 0.5j]]
+    for compiled in (False, True):
+        Q.compile_before_running = compiled
+        try:
+            for t in range(4):
+                qvm = Q.make_qvm(2)
+                qvm.load_program("\n".join((["X 0"] if t & 1 else []) + (["X 1"] if t & 2 else []) + ["I 0"]))
+                qvm.run()
+                qvm.state.vec.apply_gates(CC.qft_circuit([0, 1]))
+                np.testing.assert_allclose(qvm.amplitudes, expected[t], atol=1e-14)
+            # :64-73 CNOT from CZ, :46-53 four RX(pi/2)
+            qvm = Q.run_program(2, "X 0\nH 1\nCZ 0 1\nH 1")
+            assert abs(abs(qvm.amplitudes[3]) ** 2 - 1) < 1e-13
+            qvm = Q.run_program(1, "\n".join(["RX(pi/2) 0"] * 4))
+            assert abs(abs(qvm.amplitudes[0]) ** 2 - 1) < 1e-13
+            # :28-44 qubit ordering: compiled == interpreted
+            amps = Q.run_program(4, "H 0\nH 1\nH 2\nH 3\nCNOT 2 0\nCSWAP 1 3 2").amplitudes
+            np.testing.assert_allclose(np.abs(amps) ** 2, 1 / 16, atol=1e-14)
+        finally:
+            Q.compile_before_running = False
+
+
+def test_measure_statistics_and_rules(Q, O):
+    # entangle-25's shape at 12 qubits: after MEASURE 0 the second MEASURE is deterministic
+    prog = "H 0\n" + "\n".join(f"CNOT {i} {i + 1}" for i in range(11)) + "\nDECLARE ro BIT[2]\nMEASURE 0 ro[0]\nMEASURE 10 ro[1]"
+    ones = 0
+    for seed in range(40):
+        for compiled in (False, True):
+            Q.compile_before_running = compiled
+            try:
+                qvm = Q.make_qvm(12, seed=seed).load_program(prog).run()
+            finally:
+                Q.compile_before_running = False
+            assert qvm.registers["ro"][0] == qvm.registers["ro"][1]
+            ones += int(qvm.registers["ro"][0])
+            assert abs(qvm.state.vec.norm2() - 1) < 1e-12
+    assert 15 < ones < 65
+
+
+def test_large_state_properties(Q):
+    """Full-size checks through size-independent properties (no oracle at this size): QFT|0> is uniform,
+    the norm is preserved, and the inverse circuit restores the input."""
+    n = 28
+    circ = CC.qft_circuit(range(n))
+    vec = Q.DeviceVector(1 << n)
+    vec.set_zero_state()
+    vec.apply_gates(circ, fuse=True)
+    assert abs(vec.norm2() - 1) < 1e-10
+    head = vec.download(0, 1024)
+    np.testing.assert_allclose(head, 2.0 ** (-n / 2), rtol=1e-12)
+    tail = vec.download((1 << n) - 1024, 1024)
+    np.testing.assert_allclose(tail, 2.0 ** (-n / 2), rtol=1e-12)
+    for q in (0, 13, 27):
+        assert abs(vec.prob_excited(q) - 0.5) < 1e-10
+    inverse = [(G.dagger(m), q) for m, q in reversed(circ)]
+    vec.apply_gates(inverse, fuse=True)
+    z = vec.download(0, 4)
+    assert abs(z[0] - 1) < 1e-10 and np.abs(z[1:]).max() < 1e-10
+    assert abs(vec.norm2() - 1) < 1e-10
+    vec.close()
