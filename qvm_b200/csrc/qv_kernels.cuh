@@ -28,109 +28,121 @@ __device__ __forceinline__ void qv_st_stream(qvc* p, qvc v) {
 // The tile kernel: one CTA = one tile of 2^T amplitudes staged in shared memory
 // (XOR-swizzled, see qv_swz), rounds of register-resident groups, write back.
 // 256 threads, <= 80 registers, 64 KiB of shared memory at T=12 -> 3 CTAs per SM.
-// PEERS=true: tile bits include rank bits, amplitudes come from / go to peer
-// shards over NVLink (P2P loads/stores on IPC-mapped pointers).
+//   FULL  = true : T == 12 (every state of >= 12 qubits): all loop bounds are compile-time, the
+//                  tile-local -> physical address of element tid + 256*i is
+//                  (base | gather(tid)) | hi_off[i] with hi_off precomputed by the host.
+//   PEERS = true : tile bits include rank bits, amplitudes come from / go to peer
+//                  shards over NVLink (P2P loads/stores on IPC-mapped pointers).
 // ---------------------------------------------------------------------------
 struct QvProgSmall { uint8_t bytes[QV_PROG_SMALL_BYTES]; };
 struct QvProgLarge { uint8_t bytes[QV_PROG_LARGE_BYTES]; };
 
-template <typename PROG, bool PEERS>
+template <typename PROG, bool PEERS, bool FULL>
 __global__ void __launch_bounds__(QV_THREADS, 3)
 qv_tile_kernel(const __grid_constant__ PROG prog, const __grid_constant__ QvPeers peers,
                const qvc* __restrict__ tables) {
     extern __shared__ __align__(16) uint8_t qv_smem_raw[];
     qvc* tile = reinterpret_cast<qvc*>(qv_smem_raw);
-    __shared__ uint64_t s_ghi[16];
+    __shared__ uint32_t s_ext[QV_MAX_PASS_CHUNKS];
 
     // The control program sits in the constant bank (kernel parameters): every read below is a
     // uniform constant load, matrices reach the FP64 pipe through uniform registers.
     const uint8_t* blob = prog.bytes;
     const QvPassHeader* h = reinterpret_cast<const QvPassHeader*>(blob);
-    const uint32_t T = h->T;
+    const uint32_t T = FULL ? 12u : h->T;
     const uint32_t tile_n = 1u << T;
-    const uint32_t n_tile_segs = h->n_tile_segs, n_base_segs = h->n_base_segs;
     const uint64_t fixed_bits = h->fixed_bits;
     const uint64_t n_tiles = h->n_tiles;
     const uint32_t n_local = h->n_local_bits;
     const uint64_t local_mask = (1ull << n_local) - 1ull;
     const uint32_t n_rounds = h->n_rounds;
+    const uint32_t n_chunks = h->n_chunks;
     const QvRound* rounds = reinterpret_cast<const QvRound*>(blob + h->off_rounds);
     const QvOp* ops = reinterpret_cast<const QvOp*>(blob + h->off_ops);
     const QvChunk* chunks = reinterpret_cast<const QvChunk*>(blob + h->off_chunks);
     const qvc* mats = reinterpret_cast<const qvc*>(blob + h->off_matrices);
 
     const uint32_t tid = threadIdx.x;
-    const uint32_t iters = (tile_n + QV_THREADS - 1) / QV_THREADS;   // 16 at T=12
+    const uint32_t iters = FULL ? 16u : (tile_n + QV_THREADS - 1) / QV_THREADS;
     // tile-local e = tid + 256*i: the gather is bitwise linear, so split it.
-    const uint64_t glo = qv_gather((uint64_t)tid, h->tile_segs, n_tile_segs);
-    if (tid < iters) s_ghi[tid] = qv_gather((uint64_t)tid * QV_THREADS, h->tile_segs, n_tile_segs);
-    __syncthreads();
+    const uint64_t glo = qv_gather((uint64_t)tid, h->tile_segs, h->n_tile_segs);
+    // qv_swz only mixes bits 3..5 into bits 0..2, so the slot of tid + 256*i is qv_swz(tid) + 256*i
+    qvc* const my_tile = tile + qv_swz(tid);
     qvc* const own = peers.base[PEERS ? 0 : (fixed_bits >> n_local) & (QV_MAX_PEERS - 1)];
 
     for (uint64_t t = blockIdx.x; t < n_tiles; t += gridDim.x) {
-        const uint64_t base = qv_gather(t, h->base_segs, n_base_segs) | fixed_bits;
-        const uint64_t pbase = base | glo;
+        const uint64_t base = qv_gather(t, h->base_segs, h->n_base_segs) | fixed_bits;
+        const uint64_t pbase = PEERS ? (base | glo) : ((base | glo) & local_mask);
+        if (tid < n_chunks) s_ext[tid] = (uint32_t)qv_gather(base, chunks[tid].esegs, chunks[tid].n_esegs);
 
         // ---- HBM -> shared memory, 8 independent 128-bit loads in flight per thread
-        for (uint32_t i0 = 0; i0 < iters; i0 += 8) {
-            qvc v[8];
+        if (FULL) {
 #pragma unroll
-            for (int j = 0; j < 8; j++) {
-                const uint32_t i = i0 + j;
-                const uint32_t e = tid + i * QV_THREADS;
-                if (i < iters && e < tile_n) {
-                    const uint64_t p = pbase | s_ghi[i];
-                    const qvc* src = PEERS ? peers.base[(p >> n_local) & (QV_MAX_PEERS - 1)] + (p & local_mask)
-                                           : own + (p & local_mask);
+            for (int half = 0; half < 2; half++) {
+                qvc v[8];
+#pragma unroll
+                for (int j = 0; j < 8; j++) {
+                    const uint64_t p = pbase | h->hi_off[half * 8 + j];
+                    const qvc* src = PEERS ? peers.base[(p >> n_local) & (QV_MAX_PEERS - 1)] + (p & local_mask) : own + p;
                     v[j] = qv_ld_stream(src);
                 }
-            }
 #pragma unroll
-            for (int j = 0; j < 8; j++) {
-                const uint32_t i = i0 + j;
+                for (int j = 0; j < 8; j++) my_tile[(half * 8 + j) * QV_THREADS] = v[j];
+            }
+        } else {
+            for (uint32_t i = 0; i < iters; i++) {
                 const uint32_t e = tid + i * QV_THREADS;
-                if (i < iters && e < tile_n) tile[qv_swz(e)] = v[j];
+                if (e < tile_n) {
+                    const uint64_t p = pbase | h->hi_off[i];
+                    const qvc* src = PEERS ? peers.base[(p >> n_local) & (QV_MAX_PEERS - 1)] + (p & local_mask) : own + p;
+                    my_tile[i * QV_THREADS] = qv_ld_stream(src);
+                }
             }
         }
         __syncthreads();
 
         // ---- rounds: 2^m amplitudes per thread in registers, every op of the round applied there
         for (uint32_t r = 0; r < n_rounds; r++) {
-            const QvRound* rdp = rounds + r;
-            const uint32_t m = rdp->m;
-            QvRegPos dep;
-            dep.p0 = rdp->regpos[0];
-            dep.p1 = rdp->regpos[1];
-            dep.p2 = rdp->regpos[2];
+            const QvRound& rd = rounds[r];
+            const uint32_t m = FULL ? 3u : rd.m;
             const uint32_t nslots = 1u << m;
             const uint32_t ngroups = tile_n >> m;
             for (uint32_t g = tid; g < ngroups; g += QV_THREADS) {
                 uint32_t e0 = g;
-                if (m > 0) e0 = qv_insert_zero(e0, dep.p0);
-                if (m > 1) e0 = qv_insert_zero(e0, dep.p1);
-                if (m > 2) e0 = qv_insert_zero(e0, dep.p2);
+                if (m > 0) e0 = qv_insert_zero(e0, rd.regpos[0]);
+                if (m > 1) e0 = qv_insert_zero(e0, rd.regpos[1]);
+                if (m > 2) e0 = qv_insert_zero(e0, rd.regpos[2]);
+                const uint32_t se0 = qv_swz(e0);
                 qvc a[8];
 #pragma unroll
                 for (int s = 0; s < 8; s++) {
-                    if ((uint32_t)s < nslots) a[s] = tile[qv_swz(e0 | qv_dep(s, dep.p0, dep.p1, dep.p2))];
+                    if (FULL || (uint32_t)s < nslots) a[s] = tile[se0 ^ rd.slot_xor[s]];
                     else { a[s].x = 0.0; a[s].y = 0.0; }
                 }
-                qv_apply_round(a, *rdp, ops, chunks, mats, tables, e0, dep, base);
+                qv_apply_round(a, rd, ops, chunks, mats, tables, s_ext, e0, base);
 #pragma unroll
                 for (int s = 0; s < 8; s++)
-                    if ((uint32_t)s < nslots) tile[qv_swz(e0 | qv_dep(s, dep.p0, dep.p1, dep.p2))] = a[s];
+                    if (FULL || (uint32_t)s < nslots) tile[se0 ^ rd.slot_xor[s]] = a[s];
             }
             __syncthreads();
         }
 
         // ---- shared memory -> HBM
-        for (uint32_t i = 0; i < iters; i++) {
-            const uint32_t e = tid + i * QV_THREADS;
-            if (e < tile_n) {
-                const uint64_t p = pbase | s_ghi[i];
-                qvc* dst = PEERS ? peers.base[(p >> n_local) & (QV_MAX_PEERS - 1)] + (p & local_mask)
-                                 : own + (p & local_mask);
-                qv_st_stream(dst, tile[qv_swz(e)]);
+        if (FULL) {
+#pragma unroll
+            for (int i = 0; i < 16; i++) {
+                const uint64_t p = pbase | h->hi_off[i];
+                qvc* dst = PEERS ? peers.base[(p >> n_local) & (QV_MAX_PEERS - 1)] + (p & local_mask) : own + p;
+                qv_st_stream(dst, my_tile[i * QV_THREADS]);
+            }
+        } else {
+            for (uint32_t i = 0; i < iters; i++) {
+                const uint32_t e = tid + i * QV_THREADS;
+                if (e < tile_n) {
+                    const uint64_t p = pbase | h->hi_off[i];
+                    qvc* dst = PEERS ? peers.base[(p >> n_local) & (QV_MAX_PEERS - 1)] + (p & local_mask) : own + p;
+                    qv_st_stream(dst, my_tile[i * QV_THREADS]);
+                }
             }
         }
         __syncthreads();
@@ -186,7 +198,7 @@ qv_big_kernel(qvc* __restrict__ psi, QvBigGate g, const qvc* __restrict__ mat, u
                     const uint64_t lo = base & ((1ull << sorted[j]) - 1ull);
                     base = ((base >> sorted[j]) << (sorted[j] + 1)) | lo;
                 }
-                if ((base & g.ctrl_mask) == g.ctrl_val) {
+                if (((base | g.fixed_bits) & g.ctrl_mask) == g.ctrl_val) {
                     const qvc* row = mat + (size_t)r * d;
                     const qvc* col = in + ((idx >> k) << k);
                     qvc acc;

@@ -1,7 +1,7 @@
 // qv_ops.h -- register-level op application shared by the CUDA tile kernel
-// (qv_kernels.cu) and the TEST-ONLY CPU emulator (tests/support/qv_emulator.cpp).
+// (qv_kernels.cuh) and the TEST-ONLY CPU emulator (tests/support/qv_emulator.cpp).
 // Everything here works on a GROUP: 2^m amplitudes held in a[0..7], slot r being
-// the amplitude at tile-local index e0 | dep[r].
+// the amplitude at tile-local index e0 | rd.slot_dep[r].
 #pragma once
 #include "qv_program.h"
 
@@ -17,7 +17,9 @@ struct alignas(16) qvc {
 
 // Shared-memory swizzle: XOR the 16-byte column inside a 128-byte row with the
 // row number so that groups whose register bits are the low bits (stride 128 B
-// between lanes) still hit 8 distinct columns per quarter-warp.
+// between lanes) still hit 8 distinct columns per quarter-warp.  It is XOR-linear:
+// qv_swz(a ^ b) == qv_swz(a) ^ qv_swz(b), which the kernel uses to turn per-slot
+// address math into one XOR with a host-precomputed constant.
 QV_HD uint32_t qv_swz(uint32_t e) { return e ^ ((e >> 3) & 7u); }
 
 QV_HD uint64_t qv_gather(uint64_t x, const QvSeg* segs, uint32_t n) {
@@ -55,18 +57,8 @@ QV_HD qvc qv_cmadd(qvc acc, qvc m, qvc a) {
     return r;
 }
 
-// tile-local offset of register slot s for register-bit positions p0 < p1 < p2
-QV_HD uint32_t qv_dep(int s, uint32_t p0, uint32_t p1, uint32_t p2) {
-    return ((s & 1) ? (1u << p0) : 0u) | ((s & 2) ? (1u << p1) : 0u) | ((s & 4) ? (1u << p2) : 0u);
-}
-
-struct QvRegPos {
-    uint32_t p0, p1, p2;
-};
-
-template <int RB>
-QV_HD void qv_dense1(qvc a[8], const qvc* M, uint32_t flags, uint32_t e0, const QvRegPos dep,
-                     uint32_t cm, uint32_t cv) {
+template <int RB, bool REAL, bool CTRL>
+QV_HD void qv_dense1(qvc a[8], const qvc* M, const QvRound& rd, uint32_t e0, uint32_t cm, uint32_t cv) {
     const qvc m00 = M[0], m01 = M[1], m10 = M[2], m11 = M[3];
 #pragma unroll
     for (int r = 0; r < 8; r++) {
@@ -74,7 +66,7 @@ QV_HD void qv_dense1(qvc a[8], const qvc* M, uint32_t flags, uint32_t e0, const 
         const int r1 = r | (1 << RB);
         const qvc a0 = a[r], a1 = a[r1];
         qvc n0, n1;
-        if (flags & QV_F_REAL) {
+        if (REAL) {
             n0.x = m00.x * a0.x + m01.x * a1.x;
             n0.y = m00.x * a0.y + m01.x * a1.y;
             n1.x = m10.x * a0.x + m11.x * a1.x;
@@ -84,7 +76,7 @@ QV_HD void qv_dense1(qvc a[8], const qvc* M, uint32_t flags, uint32_t e0, const 
             n1 = qv_cmadd(qv_cmul(m10, a0), m11, a1);
         }
         bool ok = true;
-        if (flags & QV_F_CTRL_LOCAL) ok = (((e0 | qv_dep(r, dep.p0, dep.p1, dep.p2)) & cm) == cv);
+        if (CTRL) ok = (((e0 | rd.slot_dep[r]) & cm) == cv);
         if (ok) {
             a[r] = n0;
             a[r1] = n1;
@@ -92,9 +84,8 @@ QV_HD void qv_dense1(qvc a[8], const qvc* M, uint32_t flags, uint32_t e0, const 
     }
 }
 
-template <int RB0, int RB1>
-QV_HD void qv_dense2(qvc a[8], const qvc* M, uint32_t flags, uint32_t e0, const QvRegPos dep,
-                     uint32_t cm, uint32_t cv) {
+template <int RB0, int RB1, bool REAL, bool CTRL>
+QV_HD void qv_dense2(qvc a[8], const qvc* M, const QvRound& rd, uint32_t e0, uint32_t cm, uint32_t cv) {
 #pragma unroll
     for (int r = 0; r < 8; r++) {
         if (r & ((1 << RB0) | (1 << RB1))) continue;
@@ -104,7 +95,7 @@ QV_HD void qv_dense2(qvc a[8], const qvc* M, uint32_t flags, uint32_t e0, const 
 #pragma unroll
         for (int i = 0; i < 4; i++) {
             const qvc* row = M + 4 * i;
-            if (flags & QV_F_REAL) {
+            if (REAL) {
                 o[i].x = ((row[0].x * v0.x + row[1].x * v1.x) + row[2].x * v2.x) + row[3].x * v3.x;
                 o[i].y = ((row[0].x * v0.y + row[1].x * v1.y) + row[2].x * v2.y) + row[3].x * v3.y;
             } else {
@@ -116,7 +107,7 @@ QV_HD void qv_dense2(qvc a[8], const qvc* M, uint32_t flags, uint32_t e0, const 
             }
         }
         bool ok = true;
-        if (flags & QV_F_CTRL_LOCAL) ok = (((e0 | qv_dep(r, dep.p0, dep.p1, dep.p2)) & cm) == cv);
+        if (CTRL) ok = (((e0 | rd.slot_dep[r]) & cm) == cv);
         if (ok) {
             a[i0] = o[0];
             a[i1] = o[1];
@@ -126,29 +117,58 @@ QV_HD void qv_dense2(qvc a[8], const qvc* M, uint32_t flags, uint32_t e0, const 
     }
 }
 
+template <int RB, bool REAL>
+QV_HD void qv_dense1_dispatch(qvc a[8], const qvc* M, const QvRound& rd, const QvOp& op, uint32_t e0) {
+    if (op.flags & QV_F_CTRL_LOCAL) qv_dense1<RB, REAL, true>(a, M, rd, e0, op.cm_local, op.cv_local);
+    else qv_dense1<RB, REAL, false>(a, M, rd, e0, 0, 0);
+}
+
+template <int RB0, int RB1>
+QV_HD void qv_dense2_dispatch(qvc a[8], const qvc* M, const QvRound& rd, const QvOp& op, uint32_t e0) {
+    const bool ctrl = (op.flags & QV_F_CTRL_LOCAL) != 0;
+    if (op.flags & QV_F_REAL) {
+        if (ctrl) qv_dense2<RB0, RB1, true, true>(a, M, rd, e0, op.cm_local, op.cv_local);
+        else qv_dense2<RB0, RB1, true, false>(a, M, rd, e0, 0, 0);
+    } else {
+        if (ctrl) qv_dense2<RB0, RB1, false, true>(a, M, rd, e0, op.cm_local, op.cv_local);
+        else qv_dense2<RB0, RB1, false, false>(a, M, rd, e0, 0, 0);
+    }
+}
+
+// One register bit feeds the chunk: two table entries serve the whole group.
+template <int RB>
+QV_HD void qv_diag_1bit(qvc a[8], qvc t0, qvc t1) {
+#pragma unroll
+    for (int r = 0; r < 8; r++) a[r] = qv_cmul(a[r], (r & (1 << RB)) ? t1 : t0);
+}
+
 // Merged diagonal: every amplitude is multiplied by the product of its chunk
-// table entries.  Chunks that do not read a register bit give one factor for
-// the whole group, folded into `common` (one complex multiply per group instead
-// of one per amplitude).
-QV_HD void qv_diag(qvc a[8], const QvOp& op, const QvChunk* chunks, const qvc* tables, uint32_t e0,
-                   const QvRegPos dep, uint64_t base) {
+// table entries.  chunk_ext[c] is the part of chunk c's table index that comes
+// from the bits outside the tile (constant per tile, computed once per tile).
+QV_HD void qv_diag(qvc a[8], const QvOp& op, const QvChunk* chunks, const qvc* tables, const uint32_t* chunk_ext,
+                   uint32_t e0) {
     qvc common;
     common.x = 1.0;
     common.y = 0.0;
     bool have_common = false;
     for (uint32_t c = 0; c < op.n_chunks; c++) {
-        const QvChunk& ch = chunks[op.data_off + c];
-        const uint32_t g0 = (uint32_t)qv_gather(base, ch.esegs, ch.n_esegs) | qv_gather32(e0, ch.lsegs, ch.n_lsegs);
+        const uint32_t ci = op.data_off + c;
+        const QvChunk& ch = chunks[ci];
+        const uint32_t g0 = chunk_ext[ci] | qv_gather32(e0, ch.lsegs, ch.n_lsegs);
         const qvc* tab = tables + ch.table_off;
-        if (ch.reg_mask == 0) {
+        const uint32_t rm = ch.reg_mask;
+        if (rm == 0) {
+            // no register bit: one factor for the whole group
             common = have_common ? qv_cmul(common, tab[g0]) : tab[g0];
             have_common = true;
+        } else if ((rm & (rm - 1)) == 0) {
+            const qvc t0 = tab[g0];
+            if (rm == 1) qv_diag_1bit<0>(a, t0, tab[g0 | ch.slot_off[1]]);
+            else if (rm == 2) qv_diag_1bit<1>(a, t0, tab[g0 | ch.slot_off[2]]);
+            else qv_diag_1bit<2>(a, t0, tab[g0 | ch.slot_off[4]]);
         } else {
 #pragma unroll
-            for (int r = 0; r < 8; r++) {
-                const uint32_t g = g0 | qv_gather32(qv_dep(r, dep.p0, dep.p1, dep.p2), ch.lsegs, ch.n_lsegs);
-                a[r] = qv_cmul(a[r], tab[g]);
-            }
+            for (int r = 0; r < 8; r++) a[r] = qv_cmul(a[r], tab[g0 | ch.slot_off[r]]);
         }
     }
     if (have_common) {
@@ -159,28 +179,36 @@ QV_HD void qv_diag(qvc a[8], const QvOp& op, const QvChunk* chunks, const qvc* t
 
 // Apply every op of a round to one register group.
 QV_HD void qv_apply_round(qvc a[8], const QvRound& rd, const QvOp* ops, const QvChunk* chunks,
-                          const qvc* mats, const qvc* tables, uint32_t e0, const QvRegPos dep,
+                          const qvc* mats, const qvc* tables, const uint32_t* chunk_ext, uint32_t e0,
                           uint64_t base) {
     for (uint32_t i = 0; i < rd.n_ops; i++) {
         const QvOp& op = ops[rd.first_op + i];
         if ((op.flags & QV_F_CTRL_EXT) && ((base & op.cm_ext) != op.cv_ext)) continue;
         if (op.type == QV_OP_DENSE1) {
             const qvc* M = mats + op.data_off;
-            switch (op.rb0) {
-                case 0: qv_dense1<0>(a, M, op.flags, e0, dep, op.cm_local, op.cv_local); break;
-                case 1: qv_dense1<1>(a, M, op.flags, e0, dep, op.cm_local, op.cv_local); break;
-                default: qv_dense1<2>(a, M, op.flags, e0, dep, op.cm_local, op.cv_local); break;
+            if (op.flags & QV_F_REAL) {
+                switch (op.rb0) {
+                    case 0: qv_dense1_dispatch<0, true>(a, M, rd, op, e0); break;
+                    case 1: qv_dense1_dispatch<1, true>(a, M, rd, op, e0); break;
+                    default: qv_dense1_dispatch<2, true>(a, M, rd, op, e0); break;
+                }
+            } else {
+                switch (op.rb0) {
+                    case 0: qv_dense1_dispatch<0, false>(a, M, rd, op, e0); break;
+                    case 1: qv_dense1_dispatch<1, false>(a, M, rd, op, e0); break;
+                    default: qv_dense1_dispatch<2, false>(a, M, rd, op, e0); break;
+                }
             }
         } else if (op.type == QV_OP_DENSE2) {
             const qvc* M = mats + op.data_off;
             const uint32_t sel = op.rb0 + op.rb1;   // (0,1)->1 (0,2)->2 (1,2)->3
             switch (sel) {
-                case 1: qv_dense2<0, 1>(a, M, op.flags, e0, dep, op.cm_local, op.cv_local); break;
-                case 2: qv_dense2<0, 2>(a, M, op.flags, e0, dep, op.cm_local, op.cv_local); break;
-                default: qv_dense2<1, 2>(a, M, op.flags, e0, dep, op.cm_local, op.cv_local); break;
+                case 1: qv_dense2_dispatch<0, 1>(a, M, rd, op, e0); break;
+                case 2: qv_dense2_dispatch<0, 2>(a, M, rd, op, e0); break;
+                default: qv_dense2_dispatch<1, 2>(a, M, rd, op, e0); break;
             }
         } else {
-            qv_diag(a, op, chunks, tables, e0, dep, base);
+            qv_diag(a, op, chunks, tables, chunk_ext, e0);
         }
     }
 }

@@ -24,6 +24,7 @@
 #define QV_MAX_CHUNK_BITS 8      // diagonal factor tables have <= 256 entries
 #define QV_THREADS 256
 #define QV_MAX_PEERS 8
+#define QV_MAX_PASS_CHUNKS 256   // per-tile chunk offsets are staged in shared memory
 // The control part of a pass (header, rounds, ops, chunk descriptors, matrices) is handed to the
 // kernel as a __grid_constant__ parameter: it lives in the constant bank, so ptxas reads matrices
 // through uniform registers instead of spending vector registers on them.  Two size classes.
@@ -53,8 +54,9 @@ struct QvChunk {
     uint8_t n_lsegs, n_esegs;       // fields gathered from the tile-local index / the tile base
     uint8_t reg_mask;               // which register bits of the op's round feed this chunk
     uint8_t pad;
-    QvSeg lsegs[QV_CHUNK_SEGS];
+    QvSeg lsegs[QV_CHUNK_SEGS];     // only the NON-register local bits (register bits go through slot_off)
     QvSeg esegs[QV_CHUNK_SEGS];
+    uint32_t slot_off[8];           // table-index contribution of register slot r (host-precomputed)
 };
 
 struct QvOp {
@@ -74,6 +76,9 @@ struct QvRound {
     uint32_t regpos[QV_REG_BITS];   // tile-local bit positions, ascending
     uint32_t first_op, n_ops;
     uint32_t pad[2];
+    uint32_t slot_dep[8];           // tile-local index offset of register slot r
+    uint32_t slot_xor[8];           // qv_swz(slot_dep[r]): the swizzle is XOR-linear, so the shared-memory
+                                    // slot of (e0 | dep) is qv_swz(e0) ^ slot_xor[r]
 };
 
 struct QvPassHeader {
@@ -94,6 +99,7 @@ struct QvPassHeader {
     uint32_t blob_bytes;
     uint32_t uses_peers;            // tile bits include a physical bit >= n_local_bits
     uint32_t pad;
+    uint64_t hi_off[16];            // physical-index bits of tile-local index 256*i (host-precomputed gather)
 };
 
 // A k>=3 dense gate runs as its own pass through the generic kernel.
@@ -102,4 +108,5 @@ struct QvBigGate {
     uint32_t pad;
     uint32_t pos[16];               // physical bit of matrix index bit j
     uint64_t ctrl_mask, ctrl_val;   // physical control bits (identity when not matching)
+    uint64_t fixed_bits;            // rank bits of this shard (for controls on global qubits)
 };

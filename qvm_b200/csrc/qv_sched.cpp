@@ -1,4 +1,15 @@
 // qv_sched.cpp -- see qv_sched.h.
+//
+// Vocabulary
+//   logical qubit : what the gate list names.
+//   wire          : one bit-stream of the amplitude index.  Absorbed SWAP gates only exchange which
+//                   wire a logical qubit rides on (wire_of), no data moves.
+//   physical bit  : the position of a wire in the amplitude index (w2p).  It changes only when a
+//                   REMAP pass physically swaps a global (rank-selecting) bit with a local bit --
+//                   dqvm's "record the permutation instead of undoing it"
+//                   (dqvm/src/apply-distributed-gate.lisp:38-42), here batched and deferred until a
+//                   gate really needs the qubit to be local.
+//   atom          : one controlled dense block or one diagonal of a gate, in wire space.
 #include "qv_sched.h"
 
 #include <algorithm>
@@ -11,20 +22,15 @@ namespace {
 
 struct Atom {
     enum Kind { DIAG, DENSE, BIG } kind = DIAG;
-    std::vector<int> tpos;      // DENSE/BIG: physical target bit of matrix index bit j (DENSE: ascending)
+    std::vector<int> tw;        // DENSE/BIG: wire of matrix index bit j
     std::vector<cd> mat;        // DENSE/BIG: 2^kt x 2^kt row-major; DIAG: 2^k diagonal entries
-    std::vector<int> dpos;      // DIAG: physical bit of entry index bit j
-    uint64_t cmask = 0, cval = 0;
-    uint64_t mix = 0;           // physical bits the atom mixes (its targets)
-    uint64_t touch = 0;         // every physical bit the atom reads
+    std::vector<int> dw;        // DIAG: wire of entry index bit j
+    uint64_t cmask = 0, cval = 0;   // control wires / required values
+    uint64_t mix = 0;           // wires the atom mixes (its targets)
+    uint64_t touch = 0;         // every wire the atom reads
 };
 
 inline int popc(uint64_t x) { return __builtin_popcountll(x); }
-
-inline bool commute(const Atom& a, const Atom& b) {
-    // Shared bits must be non-mixing (control / diagonal) in both atoms.
-    return (a.mix & b.touch) == 0 && (b.mix & a.touch) == 0;
-}
 
 bool is_exact_swap(const Gate& g) {
     if (g.qubits.size() != 2) return false;
@@ -49,7 +55,9 @@ uint32_t deposit_bits(uint32_t s, uint32_t mask) {
     return r;
 }
 
-void analyze(const Gate& g, const std::vector<int>& l2p, std::vector<Atom>& out) {
+// Split a gate into atoms.  A qubit is NON-MIXING when the matrix is block diagonal with respect to
+// its bit (controls, diagonal gates): such a qubit never has to be inside a tile.
+void analyze(const Gate& g, const std::vector<int>& wire_of, std::vector<Atom>& out) {
     const int k = (int)g.qubits.size();
     if (k < 1 || k > 16) throw std::runtime_error("gate arity out of range (1..16)");
     const uint32_t d = 1u << k;
@@ -61,9 +69,9 @@ void analyze(const Gate& g, const std::vector<int>& l2p, std::vector<Atom>& out)
     for (uint32_t r = 0; r < d; r++)
         for (uint32_t c = 0; c < d; c++)
             if (g.mat[(size_t)r * d + c] != cd(0.0, 0.0)) mixbits |= (r ^ c);
-    auto phys = [&](int j) { return l2p[g.qubits[j]]; };
+    auto wire = [&](int j) { return wire_of[g.qubits[j]]; };
     uint64_t touch = 0;
-    for (int j = 0; j < k; j++) touch |= 1ull << phys(j);
+    for (int j = 0; j < k; j++) touch |= 1ull << wire(j);
 
     if (mixbits == 0 && k <= QV_MAX_CHUNK_BITS) {
         Atom a;
@@ -75,7 +83,7 @@ void analyze(const Gate& g, const std::vector<int>& l2p, std::vector<Atom>& out)
             a.mat[r] = g.mat[(size_t)r * d + r];
             if (a.mat[r] != cd(1.0, 0.0)) ident = false;
         }
-        for (int j = 0; j < k; j++) a.dpos.push_back(phys(j));
+        for (int j = 0; j < k; j++) a.dw.push_back(wire(j));
         if (!ident) out.push_back(std::move(a));
         return;
     }
@@ -83,9 +91,8 @@ void analyze(const Gate& g, const std::vector<int>& l2p, std::vector<Atom>& out)
     const uint32_t nonmix = (d - 1) & ~mixbits;
     const int km = popc(mixbits);
     const uint32_t dm = 1u << km;
-    // enumerate the values of the non-mixing bits
     uint32_t v = 0;
-    for (;;) {
+    for (;;) {   // every value of the non-mixing bits selects one block
         std::vector<cd> sub((size_t)dm * dm);
         bool ident = true;
         for (uint32_t r = 0; r < dm; r++)
@@ -99,36 +106,24 @@ void analyze(const Gate& g, const std::vector<int>& l2p, std::vector<Atom>& out)
             Atom a;
             a.kind = (km <= 2) ? Atom::DENSE : Atom::BIG;
             a.touch = touch;
-            std::vector<int> tp;
             for (int j = 0; j < k; j++)
-                if (mixbits >> j & 1) tp.push_back(phys(j));
+                if (mixbits >> j & 1) a.tw.push_back(wire(j));
             for (int j = 0; j < k; j++)
                 if (nonmix >> j & 1) {
-                    a.cmask |= 1ull << phys(j);
-                    if (v >> j & 1) a.cval |= 1ull << phys(j);
+                    a.cmask |= 1ull << wire(j);
+                    if (v >> j & 1) a.cval |= 1ull << wire(j);
                 }
-            if (a.kind == Atom::DENSE && km == 2 && tp[0] > tp[1]) {
-                // make matrix bit 0 the lower physical bit
-                std::swap(tp[0], tp[1]);
-                static const int sw[4] = {0, 2, 1, 3};
-                std::vector<cd> m2(16);
-                for (int r = 0; r < 4; r++)
-                    for (int c = 0; c < 4; c++) m2[sw[r] * 4 + sw[c]] = sub[r * 4 + c];
-                sub.swap(m2);
-            }
-            a.tpos = tp;
             a.mat = std::move(sub);
-            for (int p : a.tpos) a.mix |= 1ull << p;
+            for (int w : a.tw) a.mix |= 1ull << w;
             out.push_back(std::move(a));
         }
         if (v == nonmix) break;
-        v = (v - nonmix) & nonmix;   // next subset of nonmix
+        v = (v - nonmix) & nonmix;
     }
 }
 
 // ---------------------------------------------------------------- segments
 std::vector<QvSeg> make_segs(const std::vector<int>& srcpos, const std::vector<int>& dstpos) {
-    // bit srcpos[i] of the source goes to bit dstpos[i]; merge runs.
     std::vector<QvSeg> segs;
     for (size_t i = 0; i < srcpos.size(); i++) {
         if (!segs.empty()) {
@@ -147,7 +142,7 @@ std::vector<QvSeg> make_segs(const std::vector<int>& srcpos, const std::vector<i
     return segs;
 }
 
-// ---------------------------------------------------------------- diagonal chunks
+// ---------------------------------------------------------------- diagonal chunks (physical space)
 struct Chunk {
     std::vector<int> bits;      // sorted physical positions; table index bit i <-> bits[i]
     std::vector<cd> table;
@@ -158,27 +153,11 @@ struct DiagFactor {
     std::vector<cd> diag;
 };
 
-int count_runs(const std::vector<int>& v) {
-    int runs = 0;
-    for (size_t i = 0; i < v.size(); i++)
-        if (i == 0 || v[i] != v[i - 1] + 1) runs++;
-    return runs;
-}
-
 struct TileMap {
     int T = 0;
     std::vector<int> tilebits;          // sorted physical bits inside the tile
     std::vector<int> local_of;          // physical bit -> tile-local position or -1
 };
-
-bool chunk_segs_ok(const std::vector<int>& bits, const TileMap& tm) {
-    std::vector<int> loc, ext;
-    for (int b : bits) {
-        if (tm.local_of[b] >= 0) loc.push_back(tm.local_of[b]);
-        else ext.push_back(b);
-    }
-    return count_runs(loc) <= QV_CHUNK_SEGS && count_runs(ext) <= QV_CHUNK_SEGS;
-}
 
 void chunk_multiply(Chunk& c, const DiagFactor& f) {
     const size_t n = c.table.size();
@@ -209,7 +188,7 @@ void chunk_extend(Chunk& c, const std::vector<int>& newbits) {
     c.table.swap(nt);
 }
 
-std::vector<Chunk> build_chunks(const std::vector<DiagFactor>& factors, const TileMap& tm) {
+std::vector<Chunk> build_chunks(const std::vector<DiagFactor>& factors) {
     std::vector<Chunk> chunks;
     for (const DiagFactor& f : factors) {
         std::vector<int> fb = f.pos;
@@ -219,10 +198,8 @@ std::vector<Chunk> build_chunks(const std::vector<DiagFactor>& factors, const Ti
         std::vector<int> best_union;
         for (size_t ci = 0; ci < chunks.size(); ci++) {
             std::vector<int> u;
-            std::set_union(chunks[ci].bits.begin(), chunks[ci].bits.end(), fb.begin(), fb.end(),
-                           std::back_inserter(u));
+            std::set_union(chunks[ci].bits.begin(), chunks[ci].bits.end(), fb.begin(), fb.end(), std::back_inserter(u));
             if (u.size() > QV_MAX_CHUNK_BITS) continue;
-            if (u.size() != chunks[ci].bits.size() && !chunk_segs_ok(u, tm)) continue;
             if (u.size() < best_size) {
                 best_size = u.size();
                 best = (int)ci;
@@ -246,9 +223,9 @@ std::vector<Chunk> build_chunks(const std::vector<DiagFactor>& factors, const Ti
 // ---------------------------------------------------------------- pass builder
 struct RoundOp {
     bool is_diag = false;
-    const Atom* dense = nullptr;            // DENSE atom
-    std::vector<DiagFactor> factors;        // merged DIAG atoms
-    uint64_t mix = 0, touch = 0;
+    const Atom* dense = nullptr;
+    std::vector<DiagFactor> factors;
+    uint64_t mix = 0, touch = 0;        // wire space
 };
 
 struct BlobWriter {
@@ -259,38 +236,59 @@ struct BlobWriter {
     std::vector<cd> tables;
 };
 
+struct Layout {
+    const std::vector<int>* w2p;        // wire -> physical bit
+    int phys(int w) const { return (*w2p)[w]; }
+};
+
 void emit_round(BlobWriter& w, const std::vector<RoundOp>& rops, const std::vector<int>& regpos_local,
-                const TileMap& tm) {
+                const TileMap& tm, const Layout& lay) {
     QvRound rd{};
     rd.m = (uint32_t)regpos_local.size();
     for (size_t i = 0; i < regpos_local.size(); i++) rd.regpos[i] = (uint32_t)regpos_local[i];
+    for (uint32_t sl = 0; sl < 8; sl++) {
+        uint32_t dep = 0;
+        for (size_t i = 0; i < regpos_local.size(); i++)
+            if (sl >> i & 1) dep |= 1u << regpos_local[i];
+        rd.slot_dep[sl] = dep;
+        rd.slot_xor[sl] = dep ^ ((dep >> 3) & 7u);     // qv_swz
+    }
     rd.first_op = (uint32_t)w.ops.size();
-    uint64_t tile_mask = 0;
-    for (int b : tm.tilebits) tile_mask |= 1ull << b;
     for (const RoundOp& ro : rops) {
         QvOp op{};
         if (!ro.is_diag) {
             const Atom& a = *ro.dense;
-            op.type = a.tpos.size() == 1 ? QV_OP_DENSE1 : QV_OP_DENSE2;
-            auto rb_of = [&](int physbit) {
-                const int lp = tm.local_of[physbit];
+            auto rb_of = [&](int wire) {
+                const int lp = tm.local_of[lay.phys(wire)];
                 for (size_t i = 0; i < regpos_local.size(); i++)
                     if (regpos_local[i] == lp) return (int)i;
-                throw std::runtime_error("scheduler bug: target bit not a register bit");
+                throw std::runtime_error("scheduler bug: target bit is not a register bit");
             };
-            op.rb0 = (uint8_t)rb_of(a.tpos[0]);
-            if (a.tpos.size() == 2) {
-                op.rb1 = (uint8_t)rb_of(a.tpos[1]);
-                if (op.rb0 >= op.rb1) throw std::runtime_error("scheduler bug: register bits not ascending");
+            std::vector<cd> mat = a.mat;
+            if (a.tw.size() == 1) {
+                op.type = QV_OP_DENSE1;
+                op.rb0 = (uint8_t)rb_of(a.tw[0]);
+            } else {
+                op.type = QV_OP_DENSE2;
+                int r0 = rb_of(a.tw[0]), r1 = rb_of(a.tw[1]);
+                if (r0 > r1) {   // matrix index bit 0 must be the lower register bit
+                    std::swap(r0, r1);
+                    static const int sw[4] = {0, 2, 1, 3};
+                    for (int r = 0; r < 4; r++)
+                        for (int c = 0; c < 4; c++) mat[sw[r] * 4 + sw[c]] = a.mat[r * 4 + c];
+                }
+                op.rb0 = (uint8_t)r0;
+                op.rb1 = (uint8_t)r1;
             }
             bool real = true;
-            for (const cd& e : a.mat)
+            for (const cd& e : mat)
                 if (e.imag() != 0.0) real = false;
             if (real) op.flags |= QV_F_REAL;
-            for (int b = 0; b < 64; b++) {
-                if (!(a.cmask >> b & 1)) continue;
-                const bool one = a.cval >> b & 1;
-                if (tile_mask >> b & 1) {
+            for (int wq = 0; wq < 64; wq++) {
+                if (!(a.cmask >> wq & 1)) continue;
+                const bool one = a.cval >> wq & 1;
+                const int b = lay.phys(wq);
+                if (tm.local_of[b] >= 0) {
                     op.flags |= QV_F_CTRL_LOCAL;
                     op.cm_local |= 1u << tm.local_of[b];
                     if (one) op.cv_local |= 1u << tm.local_of[b];
@@ -301,10 +299,10 @@ void emit_round(BlobWriter& w, const std::vector<RoundOp>& rops, const std::vect
                 }
             }
             op.data_off = (uint32_t)w.mats.size();
-            w.mats.insert(w.mats.end(), a.mat.begin(), a.mat.end());
+            w.mats.insert(w.mats.end(), mat.begin(), mat.end());
         } else {
             op.type = QV_OP_DIAG;
-            std::vector<Chunk> chunks = build_chunks(ro.factors, tm);
+            std::vector<Chunk> chunks = build_chunks(ro.factors);
             op.data_off = (uint32_t)w.chunks.size();
             op.n_chunks = (uint32_t)chunks.size();
             for (const Chunk& c : chunks) {
@@ -315,10 +313,17 @@ void emit_round(BlobWriter& w, const std::vector<RoundOp>& rops, const std::vect
                 for (size_t i = 0; i < c.bits.size(); i++) {
                     const int b = c.bits[i];
                     if (tm.local_of[b] >= 0) {
+                        bool is_reg = false;
+                        for (size_t r = 0; r < regpos_local.size(); r++)
+                            if (regpos_local[r] == tm.local_of[b]) {
+                                qc.reg_mask |= (uint8_t)(1u << r);
+                                for (uint32_t sl = 0; sl < 8; sl++)
+                                    if (sl >> r & 1) qc.slot_off[sl] |= 1u << i;
+                                is_reg = true;
+                            }
+                        if (is_reg) continue;    // register bits reach the table index through slot_off
                         lsrc.push_back(tm.local_of[b]);
                         ldst.push_back((int)i);
-                        for (size_t r = 0; r < regpos_local.size(); r++)
-                            if (regpos_local[r] == tm.local_of[b]) qc.reg_mask |= (uint8_t)(1u << r);
                     } else {
                         esrc.push_back(b);
                         edst.push_back((int)i);
@@ -340,20 +345,21 @@ void emit_round(BlobWriter& w, const std::vector<RoundOp>& rops, const std::vect
     w.rounds.push_back(rd);
 }
 
-// Split the ordered atoms of one pass into register rounds.
-void build_rounds(BlobWriter& w, const std::vector<const Atom*>& atoms, const TileMap& tm) {
+// Split the ordered atoms of one pass into register rounds (same greedy + commutation look-ahead
+// as the pass level, one level down: <= QV_REG_BITS target bits per round).
+void build_rounds(BlobWriter& w, const std::vector<const Atom*>& atoms, const TileMap& tm, const Layout& lay) {
     const int m_max = std::min(QV_REG_BITS, tm.T);
     std::vector<const Atom*> pending = atoms;
     while (!pending.empty()) {
         std::vector<const Atom*> deferred;
         uint64_t dmix = 0, dtouch = 0;
-        uint64_t regbits = 0;   // physical bits that must be register bits
+        uint64_t regwires = 0;
         std::vector<RoundOp> rops;
         for (const Atom* a : pending) {
             bool blocked = (a->mix & dtouch) != 0 || (dmix & a->touch) != 0;
             if (!blocked && a->kind == Atom::DENSE) {
-                const uint64_t need = regbits | a->mix;
-                if (popc(need) <= m_max) regbits = need;
+                const uint64_t need = regwires | a->mix;
+                if (popc(need) <= m_max) regwires = need;
                 else blocked = true;
             }
             if (blocked) {
@@ -369,9 +375,11 @@ void build_rounds(BlobWriter& w, const std::vector<const Atom*>& atoms, const Ti
                 ro.touch = a->touch;
                 rops.push_back(std::move(ro));
             } else {
-                // hoist the diagonal backwards over commuting dense ops and merge it
-                // into the nearest earlier diagonal group it can reach.
-                DiagFactor f{a->dpos, a->mat};
+                // hoist the diagonal backwards over commuting dense ops and merge it into the
+                // nearest earlier diagonal group it can reach.
+                DiagFactor f;
+                for (int wq : a->dw) f.pos.push_back(lay.phys(wq));
+                f.diag = a->mat;
                 int j = (int)rops.size() - 1;
                 bool merged = false;
                 while (j >= 0) {
@@ -393,28 +401,29 @@ void build_rounds(BlobWriter& w, const std::vector<const Atom*>& atoms, const Ti
                 }
             }
         }
-        // register bit positions: required ones, padded with unused tile-local
-        // positions (highest first) up to m_max.
         std::vector<int> regpos;
-        for (int b = 0; b < 64; b++)
-            if (regbits >> b & 1) regpos.push_back(tm.local_of[b]);
+        for (int wq = 0; wq < 64; wq++)
+            if (regwires >> wq & 1) regpos.push_back(tm.local_of[lay.phys(wq)]);
         for (int lp = tm.T - 1; lp >= 0 && (int)regpos.size() < m_max; lp--)
             if (std::find(regpos.begin(), regpos.end(), lp) == regpos.end()) regpos.push_back(lp);
         std::sort(regpos.begin(), regpos.end());
-        emit_round(w, rops, regpos, tm);
+        emit_round(w, rops, regpos, tm, lay);
         pending.swap(deferred);
     }
 }
 
-Step build_tile_step(const std::vector<const Atom*>& atoms, uint64_t tile_targets, int n_bits,
-                     const CompileOptions& opt) {
-    const int n_local = opt.n_local_bits > 0 ? opt.n_local_bits : n_bits;
+struct Geometry {
+    int n_bits, n_local, T, lmin, rank;
+};
+
+// tile_targets: physical bits that must be inside the tile.
+Step build_tile_step(const std::vector<const Atom*>& atoms, uint64_t tile_targets, const Geometry& geo,
+                     const Layout& lay) {
     TileMap tm;
-    tm.T = std::min(opt.tile_bits, n_local);
-    const int lmin = (tm.T < n_local) ? std::max(0, std::min(opt.min_low_bits, tm.T - 2)) : tm.T;
+    tm.T = geo.T;
     uint64_t tb = tile_targets;
-    for (int b = 0; b < lmin; b++) tb |= 1ull << b;
-    for (int b = 0; b < n_local && popc(tb) < tm.T; b++) tb |= 1ull << b;
+    for (int b = 0; b < geo.lmin; b++) tb |= 1ull << b;
+    for (int b = 0; b < geo.n_local && popc(tb) < tm.T; b++) tb |= 1ull << b;
     if (popc(tb) != tm.T) throw std::runtime_error("scheduler bug: tile bit count");
     tm.local_of.assign(64, -1);
     for (int b = 0; b < 64; b++)
@@ -422,8 +431,12 @@ Step build_tile_step(const std::vector<const Atom*>& atoms, uint64_t tile_target
             tm.local_of[b] = (int)tm.tilebits.size();
             tm.tilebits.push_back(b);
         }
+    const uint64_t local_mask = (1ull << geo.n_local) - 1ull;
+    const uint64_t tile_global = tb & ~local_mask;          // rank bits that vary inside the tile
+    const int s = popc(tile_global);
+
     BlobWriter w;
-    build_rounds(w, atoms, tm);
+    build_rounds(w, atoms, tm, lay);
 
     QvPassHeader h{};
     h.T = (uint32_t)tm.T;
@@ -433,26 +446,52 @@ Step build_tile_step(const std::vector<const Atom*>& atoms, uint64_t tile_target
             src[i] = i;
             dst[i] = tm.tilebits[i];
         }
-        std::vector<QvSeg> s = make_segs(src, dst);
-        if (s.size() > QV_MAX_SEGS) throw std::runtime_error("scheduler bug: too many tile segments");
-        h.n_tile_segs = (uint32_t)s.size();
-        std::copy(s.begin(), s.end(), h.tile_segs);
+        std::vector<QvSeg> sg = make_segs(src, dst);
+        if (sg.size() > QV_MAX_SEGS) throw std::runtime_error("scheduler bug: too many tile segments");
+        h.n_tile_segs = (uint32_t)sg.size();
+        std::copy(sg.begin(), sg.end(), h.tile_segs);
+    }
+    // Non-tile local bits enumerate the tiles.  In a peer pass the 2^s ranks that share the tiles
+    // split them: the top s non-tile local bits are pinned to this rank's value on the tile's rank bits.
+    std::vector<int> nontile;
+    for (int b = 0; b < geo.n_local; b++)
+        if (!(tb >> b & 1)) nontile.push_back(b);
+    if ((int)nontile.size() < s) throw std::runtime_error("scheduler bug: shard too small for a peer pass");
+    uint64_t fixed = 0;
+    for (int b = geo.n_local; b < geo.n_bits; b++)
+        if (!(tb >> b & 1) && (geo.rank >> (b - geo.n_local) & 1)) fixed |= 1ull << b;
+    {
+        int j = 0;
+        for (int b = geo.n_local; b < geo.n_bits; b++)
+            if (tb >> b & 1) {
+                const int pinned = nontile[nontile.size() - s + j];
+                if (geo.rank >> (b - geo.n_local) & 1) fixed |= 1ull << pinned;
+                j++;
+            }
+        nontile.resize(nontile.size() - s);
     }
     {
         std::vector<int> src, dst;
-        for (int b = 0; b < n_local; b++)
-            if (!(tb >> b & 1)) {
-                src.push_back((int)src.size());
-                dst.push_back(b);
-            }
-        std::vector<QvSeg> s = make_segs(src, dst);
-        if (s.size() > QV_MAX_SEGS) throw std::runtime_error("scheduler bug: too many base segments");
-        h.n_base_segs = (uint32_t)s.size();
-        std::copy(s.begin(), s.end(), h.base_segs);
+        for (size_t i = 0; i < nontile.size(); i++) {
+            src.push_back((int)i);
+            dst.push_back(nontile[i]);
+        }
+        std::vector<QvSeg> sg = make_segs(src, dst);
+        if (sg.size() > QV_MAX_SEGS) throw std::runtime_error("scheduler bug: too many base segments");
+        h.n_base_segs = (uint32_t)sg.size();
+        std::copy(sg.begin(), sg.end(), h.base_segs);
     }
-    h.fixed_bits = (uint64_t)opt.rank << n_local;
-    h.n_tiles = 1ull << (n_local - tm.T);
-    h.n_local_bits = (uint32_t)n_local;
+    for (int i = 0; i < 16; i++) {
+        uint64_t off = 0;
+        const uint32_t e = (uint32_t)i * QV_THREADS;
+        for (int t = 0; t < tm.T; t++)
+            if (e >> t & 1) off |= 1ull << tm.tilebits[t];
+        h.hi_off[i] = off;
+    }
+    h.fixed_bits = fixed;
+    h.n_tiles = 1ull << nontile.size();
+    h.n_local_bits = (uint32_t)geo.n_local;
+    h.uses_peers = s > 0 ? 1u : 0u;
     h.n_rounds = (uint32_t)w.rounds.size();
     h.n_ops = (uint32_t)w.ops.size();
     h.n_chunks = (uint32_t)w.chunks.size();
@@ -469,9 +508,11 @@ Step build_tile_step(const std::vector<const Atom*>& atoms, uint64_t tile_target
     h.n_table_entries = (uint32_t)w.tables.size();
     h.blob_bytes = (uint32_t)off;
     if (off > QV_PROG_LARGE_BYTES) throw std::runtime_error("scheduler bug: pass control program too large");
+    if (w.chunks.size() > QV_MAX_PASS_CHUNKS) throw std::runtime_error("scheduler bug: too many diagonal chunks in a pass");
 
     Step st;
     st.kind = Step::TILE;
+    st.uses_peers = s > 0;
     st.blob.assign(off, 0);
     std::memcpy(st.blob.data(), &h, sizeof(h));
     if (!w.rounds.empty()) std::memcpy(st.blob.data() + h.off_rounds, w.rounds.data(), w.rounds.size() * sizeof(QvRound));
@@ -483,13 +524,17 @@ Step build_tile_step(const std::vector<const Atom*>& atoms, uint64_t tile_target
     return st;
 }
 
-Step build_big_step(const Atom& a) {
+Step build_big_step(const Atom& a, const Geometry& geo, const Layout& lay) {
     Step st;
     st.kind = Step::BIG;
-    st.big.k = (uint32_t)a.tpos.size();
-    for (size_t j = 0; j < a.tpos.size(); j++) st.big.pos[j] = (uint32_t)a.tpos[j];
-    st.big.ctrl_mask = a.cmask;
-    st.big.ctrl_val = a.cval;
+    st.big.k = (uint32_t)a.tw.size();
+    for (size_t j = 0; j < a.tw.size(); j++) st.big.pos[j] = (uint32_t)lay.phys(a.tw[j]);
+    for (int wq = 0; wq < 64; wq++)
+        if (a.cmask >> wq & 1) {
+            st.big.ctrl_mask |= 1ull << lay.phys(wq);
+            if (a.cval >> wq & 1) st.big.ctrl_val |= 1ull << lay.phys(wq);
+        }
+    st.big.fixed_bits = (uint64_t)geo.rank << geo.n_local;
     st.bigmat = a.mat;
     st.n_gates = 1;
     return st;
@@ -502,91 +547,175 @@ Tape compile(const std::vector<Gate>& gates, int n_bits, const CompileOptions& o
     if (n_bits < 1 || n_bits > 40) throw std::runtime_error("qubit count out of range");
     Tape tape;
     tape.n_bits = n_bits;
-    tape.l2p = l2p_in;
-    if (tape.l2p.empty()) {
-        tape.l2p.resize(n_bits);
-        for (int i = 0; i < n_bits; i++) tape.l2p[i] = i;
+    std::vector<int> w2p = l2p_in;          // wire q starts as logical qubit q
+    if (w2p.empty()) {
+        w2p.resize(n_bits);
+        for (int i = 0; i < n_bits; i++) w2p[i] = i;
     }
-    if ((int)tape.l2p.size() != n_bits) throw std::runtime_error("l2p has the wrong length");
-    const int n_local = opt.n_local_bits > 0 ? opt.n_local_bits : n_bits;
-    const int T = std::min(opt.tile_bits, n_local);
-    if (T < 1 || T > QV_MAX_TILE_BITS || (T < n_local && T < 2)) throw std::runtime_error("tile_bits out of range");
-    // keep room for a 2-target gate above the always-resident low bits
-    const int lmin = (T < n_local) ? std::max(0, std::min(opt.min_low_bits, T - 2)) : T;
-    const uint64_t lowmask = (1ull << lmin) - 1;
-    const int cap_high = T - lmin;
+    if ((int)w2p.size() != n_bits) throw std::runtime_error("l2p has the wrong length");
+    std::vector<int> wire_of(n_bits);
+    for (int i = 0; i < n_bits; i++) wire_of[i] = i;
 
-    // 1. analyse gates into atoms; group boundaries matter only when !fuse.
+    Geometry geo;
+    geo.n_bits = n_bits;
+    geo.n_local = opt.n_local_bits > 0 ? opt.n_local_bits : n_bits;
+    geo.rank = opt.rank;
+    geo.T = std::min(opt.tile_bits, geo.n_local);
+    if (geo.n_local > n_bits) throw std::runtime_error("n_local_bits exceeds the qubit count");
+    const int g_bits = n_bits - geo.n_local;
+    if (geo.T < 1 || geo.T > QV_MAX_TILE_BITS || (geo.T < geo.n_local && geo.T < 2))
+        throw std::runtime_error("tile_bits out of range");
+    // keep room for a 2-target gate above the always-resident low bits
+    geo.lmin = (geo.T < geo.n_local) ? std::max(0, std::min(opt.min_low_bits, geo.T - 2)) : geo.T;
+    if (g_bits > 0 && geo.T - geo.lmin < 2)
+        throw std::runtime_error("shard too small for the requested number of ranks");
+    const uint64_t lowmask = (1ull << geo.lmin) - 1;
+    const uint64_t local_mask = (1ull << geo.n_local) - 1ull;
+    const int cap_high = geo.T - geo.lmin;
+    Layout lay{&w2p};
+
+    // 1. analyse gates into atoms (wire space)
     std::vector<Atom> atoms;
-    std::vector<int> gate_of;   // atom -> gate index
+    std::vector<int> gate_of;
     for (size_t gi = 0; gi < gates.size(); gi++) {
         const Gate& g = gates[gi];
         for (int q : g.qubits)
             if (q < 0 || q >= n_bits) throw std::runtime_error("gate qubit out of range");
         if (opt.absorb_swaps && is_exact_swap(g)) {
-            std::swap(tape.l2p[g.qubits[0]], tape.l2p[g.qubits[1]]);
+            std::swap(wire_of[g.qubits[0]], wire_of[g.qubits[1]]);
             continue;
         }
         const size_t before = atoms.size();
-        analyze(g, tape.l2p, atoms);
+        analyze(g, wire_of, atoms);
         for (size_t i = before; i < atoms.size(); i++) gate_of.push_back((int)gi);
     }
     tape.n_gates = (int)gates.size();
     tape.n_atoms = (int)atoms.size();
-    for (const Atom& a : atoms)
-        if (a.kind != Atom::BIG)
-            for (int b = 0; b < 64; b++)
-                if ((a.mix >> b & 1) && b >= n_local)
-                    throw std::runtime_error("gate mixes a physical bit that is not local to this device");
 
-    auto fits = [&](uint64_t need) { return popc(need & ~lowmask) <= cap_high; };
+    auto phys_mask = [&](uint64_t wires) {
+        uint64_t m = 0;
+        for (int wq = 0; wq < n_bits; wq++)
+            if (wires >> wq & 1) m |= 1ull << w2p[wq];
+        return m;
+    };
+    auto fits = [&](uint64_t need_phys) {
+        return (need_phys & ~local_mask) == 0 && popc(need_phys & ~lowmask) <= cap_high;
+    };
+
+    // The SWAP matrix used by remap passes.
+    Atom swap_proto;
+    swap_proto.kind = Atom::DENSE;
+    swap_proto.mat.assign(16, cd(0.0, 0.0));
+    swap_proto.mat[0] = swap_proto.mat[6] = swap_proto.mat[9] = swap_proto.mat[15] = cd(1.0, 0.0);
+    std::vector<Atom> remap_atoms;     // storage that outlives the step builders
+
+    // Bring the wires in `need` (currently on rank bits) onto local bits: one peer pass of physical
+    // SWAPs between each needed global bit and a victim local bit (the local wire whose next use as
+    // a gate target is farthest away), then relabel.
+    auto remap = [&](uint64_t need_wires, const std::vector<const Atom*>& pending) {
+        std::vector<int> globals;
+        for (int wq = 0; wq < n_bits; wq++)
+            if ((need_wires >> wq & 1) && w2p[wq] >= geo.n_local) globals.push_back(wq);
+        if (globals.empty()) throw std::runtime_error("scheduler bug: remap without a global wire");
+        // next use (as a mixing target) of every wire
+        std::vector<size_t> next_use(n_bits, pending.size() + 1);
+        for (size_t i = 0; i < pending.size(); i++)
+            for (int wq = 0; wq < n_bits; wq++)
+                if ((pending[i]->mix >> wq & 1) && next_use[wq] > i) next_use[wq] = i;
+        std::vector<int> cand;
+        for (int wq = 0; wq < n_bits; wq++)
+            if (w2p[wq] < geo.n_local && w2p[wq] >= geo.lmin && !(need_wires >> wq & 1)) cand.push_back(wq);
+        std::stable_sort(cand.begin(), cand.end(), [&](int a, int b) {
+            if (next_use[a] != next_use[b]) return next_use[a] > next_use[b];
+            return w2p[a] > w2p[b];     // prefer high local bits: longer contiguous runs stay put
+        });
+        if (cand.size() < globals.size()) throw std::runtime_error("scheduler: no local bit available for a remap");
+        // one peer pass exchanges as many (global, victim) pairs as the tile has room for
+        const size_t per_pass = (size_t)std::max(1, cap_high / 2);
+        for (size_t first = 0; first < globals.size(); first += per_pass) {
+            const size_t last = std::min(globals.size(), first + per_pass);
+            remap_atoms.clear();
+            remap_atoms.reserve(last - first);
+            uint64_t targets = 0;
+            for (size_t i = first; i < last; i++) {
+                Atom a = swap_proto;
+                a.tw = {cand[i], globals[i]};
+                a.mix = a.touch = (1ull << cand[i]) | (1ull << globals[i]);
+                targets |= (1ull << w2p[cand[i]]) | (1ull << w2p[globals[i]]);
+                remap_atoms.push_back(std::move(a));
+            }
+            std::vector<const Atom*> ptrs;
+            for (const Atom& a : remap_atoms) ptrs.push_back(&a);
+            Step st = build_tile_step(ptrs, targets, geo, lay);
+            st.n_gates = 0;
+            st.is_remap = true;
+            tape.steps.push_back(std::move(st));
+            for (size_t i = first; i < last; i++) std::swap(w2p[cand[i]], w2p[globals[i]]);
+        }
+    };
+
+    std::vector<const Atom*> pending;
+    for (const Atom& a : atoms) pending.push_back(&a);
 
     if (!opt.fuse) {
+        // every gate is its own pass (its controlled blocks share it when they fit)
         size_t i = 0;
         while (i < atoms.size()) {
             size_t j = i;
             while (j < atoms.size() && gate_of[j] == gate_of[i]) j++;
-            // atoms of one gate: tile passes for DIAG/DENSE (one pass if they fit), BIG on their own
+            uint64_t need = 0;
+            for (size_t a = i; a < j; a++) need |= atoms[a].mix;
+            if (phys_mask(need) & ~local_mask) {
+                std::vector<const Atom*> rest(pending.begin() + i, pending.end());
+                remap(need, rest);
+            }
             std::vector<const Atom*> cur;
             uint64_t targets = 0;
             for (size_t a = i; a < j; a++) {
                 if (atoms[a].kind == Atom::BIG) {
                     if (!cur.empty()) {
-                        tape.steps.push_back(build_tile_step(cur, targets, n_bits, opt));
+                        tape.steps.push_back(build_tile_step(cur, targets, geo, lay));
                         cur.clear();
                         targets = 0;
                     }
-                    tape.steps.push_back(build_big_step(atoms[a]));
+                    tape.steps.push_back(build_big_step(atoms[a], geo, lay));
                 } else {
-                    if (!fits(targets | atoms[a].mix)) {
-                        tape.steps.push_back(build_tile_step(cur, targets, n_bits, opt));
+                    const uint64_t pm = phys_mask(atoms[a].mix);
+                    if (!cur.empty() && !fits(targets | pm)) {
+                        tape.steps.push_back(build_tile_step(cur, targets, geo, lay));
                         cur.clear();
                         targets = 0;
                     }
-                    targets |= atoms[a].mix;
+                    targets |= pm;
                     cur.push_back(&atoms[a]);
                 }
             }
-            if (!cur.empty()) tape.steps.push_back(build_tile_step(cur, targets, n_bits, opt));
+            if (!cur.empty()) tape.steps.push_back(build_tile_step(cur, targets, geo, lay));
             i = j;
         }
+        tape.l2p.resize(n_bits);
+        for (int q = 0; q < n_bits; q++) tape.l2p[q] = w2p[wire_of[q]];
         return tape;
     }
 
     // 2. greedy pass formation with commutation look-ahead.
-    std::vector<const Atom*> pending;
-    for (const Atom& a : atoms) pending.push_back(&a);
     while (!pending.empty()) {
         if (pending.front()->kind == Atom::BIG) {
-            tape.steps.push_back(build_big_step(*pending.front()));
+            if (phys_mask(pending.front()->mix) & ~local_mask) {
+                remap(pending.front()->mix, pending);
+                continue;
+            }
+            tape.steps.push_back(build_big_step(*pending.front(), geo, lay));
             pending.erase(pending.begin());
             continue;
         }
         std::vector<const Atom*> in_pass, deferred;
         uint64_t dmix = 0, dtouch = 0, targets = 0;
         size_t est_bytes = sizeof(QvPassHeader);
+        size_t n_diag = 0;
         for (const Atom* a : pending) {
             bool blocked = (a->mix & dtouch) != 0 || (dmix & a->touch) != 0;
+            if (!blocked && a->kind == Atom::DIAG && n_diag + 1 > QV_MAX_PASS_CHUNKS) blocked = true;
             // conservative size of the atom in the control program (round + op + chunk + matrix)
             const size_t need_bytes = sizeof(QvRound) + sizeof(QvOp) +
                                       (a->kind == Atom::DENSE ? a->mat.size() * sizeof(cd) : sizeof(QvChunk));
@@ -594,7 +723,8 @@ Tape compile(const std::vector<Gate>& gates, int n_bits, const CompileOptions& o
             if (!blocked) {
                 if (a->kind == Atom::BIG) blocked = true;
                 else if (a->kind == Atom::DENSE) {
-                    if (fits(targets | a->mix)) targets |= a->mix;
+                    const uint64_t pm = phys_mask(a->mix);
+                    if (fits(targets | pm)) targets |= pm;
                     else blocked = true;
                 }
             }
@@ -605,12 +735,32 @@ Tape compile(const std::vector<Gate>& gates, int n_bits, const CompileOptions& o
             } else {
                 in_pass.push_back(a);
                 est_bytes += need_bytes;
+                if (a->kind == Atom::DIAG) n_diag++;
             }
         }
-        if (in_pass.empty()) throw std::runtime_error("scheduler bug: no atom fits an empty pass");
-        tape.steps.push_back(build_tile_step(in_pass, targets, n_bits, opt));
+        if (in_pass.empty()) {
+            // the front atom needs wires that sit on rank bits: bring them (and the other global
+            // targets of the atoms queued right behind it, while there is room) home first.
+            uint64_t need = pending.front()->mix;
+            if (!(phys_mask(need) & ~local_mask)) throw std::runtime_error("scheduler bug: no atom fits an empty pass");
+            for (const Atom* a : pending) {
+                const uint64_t gl = a->mix & ~need;
+                uint64_t extra = 0;
+                for (int wq = 0; wq < n_bits; wq++)
+                    if ((gl >> wq & 1) && w2p[wq] >= geo.n_local) extra |= 1ull << wq;
+                int n_glob = 0;
+                for (int wq = 0; wq < n_bits; wq++)
+                    if (((need | extra) >> wq & 1) && w2p[wq] >= geo.n_local) n_glob++;
+                if (n_glob <= g_bits) need |= extra;
+            }
+            remap(need, pending);
+            continue;
+        }
+        tape.steps.push_back(build_tile_step(in_pass, targets, geo, lay));
         pending.swap(deferred);
     }
+    tape.l2p.resize(n_bits);
+    for (int q = 0; q < n_bits; q++) tape.l2p[q] = w2p[wire_of[q]];
     return tape;
 }
 
@@ -626,12 +776,16 @@ std::string describe(const Tape& t) {
         }
         QvPassHeader h;
         std::memcpy(&h, s.blob.data(), sizeof(h));
-        os << "  [" << i << "] TILE T=" << h.T << " atoms=" << s.n_gates << " rounds=" << h.n_rounds
-           << " ops=" << h.n_ops << " chunks=" << h.n_chunks << " bytes=" << h.blob_bytes << " tables=" << h.n_table_entries << " tilebits=";
+        os << "  [" << i << "] " << (s.is_remap ? "REMAP" : (s.uses_peers ? "PEER" : "TILE")) << " T=" << h.T
+           << " atoms=" << s.n_gates << " rounds=" << h.n_rounds << " ops=" << h.n_ops << " chunks=" << h.n_chunks
+           << " bytes=" << h.blob_bytes << " tables=" << h.n_table_entries << " tilebits=";
         for (uint32_t k = 0; k < h.n_tile_segs; k++)
             os << (int)h.tile_segs[k].dst << "+" << (int)h.tile_segs[k].len << (k + 1 < h.n_tile_segs ? "," : "");
         os << "\n";
     }
+    os << "  l2p:";
+    for (int p : t.l2p) os << " " << p;
+    os << "\n";
     return os.str();
 }
 

@@ -41,6 +41,8 @@ struct Step {
     QvBigGate big{};             // BIG
     std::vector<cd> bigmat;      // BIG: row-major 2^k x 2^k
     int n_gates = 0;             // logical gates (atoms) folded into this step
+    bool uses_peers = false;     // TILE: the tile spans rank bits -> peer shards are read/written (needs barriers)
+    bool is_remap = false;       // TILE: a global<->local qubit exchange inserted by the scheduler
 };
 
 struct Tape {

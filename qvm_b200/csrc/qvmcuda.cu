@@ -104,29 +104,36 @@ int tile_grid(const qvmcuda_state* s, uint64_t n_tiles) {
     return (int)(n_tiles < cap ? n_tiles : cap);
 }
 
-template <typename PROG, bool PEERS>
+template <typename PROG, bool PEERS, bool FULL>
 int launch_tile_t(qvmcuda_state* s, const qv::Step& st, const QvPassHeader& h, const uint8_t* d_tables) {
     static std::atomic<bool> attr_set{false};
     if (!attr_set.exchange(true)) {
-        CK(cudaFuncSetAttribute(qv_tile_kernel<PROG, PEERS>, cudaFuncAttributeMaxDynamicSharedMemorySize, 65536));
-        CK(cudaFuncSetAttribute(qv_tile_kernel<PROG, PEERS>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+        CK(cudaFuncSetAttribute(qv_tile_kernel<PROG, PEERS, FULL>, cudaFuncAttributeMaxDynamicSharedMemorySize, 65536));
+        CK(cudaFuncSetAttribute(qv_tile_kernel<PROG, PEERS, FULL>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
     }
     static thread_local PROG prog;   // 28 KiB: keep it off the stack
     std::memcpy(prog.bytes, st.blob.data(), st.blob.size());
     const size_t smem = (size_t)sizeof(qvc) << h.T;
-    qv_tile_kernel<PROG, PEERS><<<tile_grid(s, h.n_tiles), QV_THREADS, smem, s->stream>>>(prog, s->peers, (const qvc*)d_tables);
+    qv_tile_kernel<PROG, PEERS, FULL><<<tile_grid(s, h.n_tiles), QV_THREADS, smem, s->stream>>>(prog, s->peers, (const qvc*)d_tables);
     g_launches++;
     CK(cudaGetLastError());
     return 0;
+}
+
+template <typename PROG>
+int launch_tile_p(qvmcuda_state* s, const qv::Step& st, const QvPassHeader& h, const uint8_t* d_tables) {
+    const bool full = h.T == QV_MAX_TILE_BITS;
+    if (h.uses_peers) return full ? launch_tile_t<PROG, true, true>(s, st, h, d_tables) : launch_tile_t<PROG, true, false>(s, st, h, d_tables);
+    return full ? launch_tile_t<PROG, false, true>(s, st, h, d_tables) : launch_tile_t<PROG, false, false>(s, st, h, d_tables);
 }
 
 int launch_tile(qvmcuda_state* s, const qv::Step& st, const uint8_t* d_tables) {
     QvPassHeader h;
     std::memcpy(&h, st.blob.data(), sizeof(h));
     if (st.blob.size() > QV_PROG_LARGE_BYTES) return fail("pass control program too large");
-    const bool small = st.blob.size() <= QV_PROG_SMALL_BYTES;
-    if (h.uses_peers) return small ? launch_tile_t<QvProgSmall, true>(s, st, h, d_tables) : launch_tile_t<QvProgLarge, true>(s, st, h, d_tables);
-    return small ? launch_tile_t<QvProgSmall, false>(s, st, h, d_tables) : launch_tile_t<QvProgLarge, false>(s, st, h, d_tables);
+    if (h.uses_peers && s->world < 2) return fail("peer pass on a state without attached peers");
+    return st.blob.size() <= QV_PROG_SMALL_BYTES ? launch_tile_p<QvProgSmall>(s, st, h, d_tables)
+                                                 : launch_tile_p<QvProgLarge>(s, st, h, d_tables);
 }
 
 int launch_big(qvmcuda_state* s, const qv::Step& st, const uint8_t* d_mat) {

@@ -126,3 +126,28 @@ def random_circuit(n, n_gates, rng, max_dense=3):
             q = rng.choice(n, k, replace=False)
             circ.append((np.diag(d[: 1 << k]), tuple(int(x) for x in q)))
     return circ
+
+
+def run_emulator_sharded(psi, n, world, circ, fuse=True, tile_bits=12, absorb_swaps=False):
+    """Emulates `world` ranks (shards back to back in psi) running the sharded schedule."""
+    ks, qf, mf = flatten_circuit(circ)
+    desc = C.create_string_buffer(1 << 16)
+    l2p = np.arange(n, dtype=np.int32)
+    p = lambda a: a.ctypes.data_as(C.c_void_p)
+    emu = emulator()
+    emu.qvtest_run_sharded.restype = C.c_int
+    rc = emu.qvtest_run_sharded(p(psi), n, world, len(circ), p(ks), p(qf), p(mf), int(fuse), tile_bits,
+                                int(absorb_swaps), p(l2p), desc, len(desc))
+    if rc < 0:
+        raise RuntimeError(desc.value.decode())
+    return rc // 1000, rc % 1000, desc.value.decode(), l2p
+
+
+def unpermute(psi_phys, l2p):
+    """psi_phys is indexed by physical bits; logical qubit q lives at physical bit l2p[q]."""
+    n = len(l2p)
+    idx = np.arange(psi_phys.size)
+    phys = np.zeros_like(idx)
+    for q in range(n):
+        phys |= ((idx >> q) & 1) << int(l2p[q])
+    return psi_phys[phys]

@@ -15,7 +15,8 @@
 
 namespace {
 
-void run_tile_step(qvc* psi, const qv::Step& st) {
+// peers[r] = base pointer of rank r's shard (peers[0] for a single device)
+void run_tile_step(qvc* const* peers, const qv::Step& st) {
     const uint8_t* blob = st.blob.data();
     QvPassHeader h;
     std::memcpy(&h, blob, sizeof(h));
@@ -27,36 +28,39 @@ void run_tile_step(qvc* psi, const qv::Step& st) {
     const uint32_t tile_n = 1u << h.T;
     const uint64_t local_mask = (1ull << h.n_local_bits) - 1ull;
     std::vector<qvc> smem(tile_n);
+    std::vector<uint32_t> ext(h.n_chunks ? h.n_chunks : 1);
+    auto addr = [&](uint64_t p) { return peers[p >> h.n_local_bits] + (p & local_mask); };
     for (uint64_t tile = 0; tile < h.n_tiles; tile++) {
         const uint64_t base = qv_gather(tile, h.base_segs, h.n_base_segs) | h.fixed_bits;
+        for (uint32_t c = 0; c < h.n_chunks; c++) ext[c] = (uint32_t)qv_gather(base, chunks[c].esegs, chunks[c].n_esegs);
         for (uint32_t e = 0; e < tile_n; e++) {
-            const uint64_t p = base | qv_gather(e, h.tile_segs, h.n_tile_segs);
-            smem[qv_swz(e)] = psi[p & local_mask];
+            const uint64_t p = base | qv_gather(e & (QV_THREADS - 1), h.tile_segs, h.n_tile_segs) | h.hi_off[e / QV_THREADS];
+            smem[qv_swz(e)] = *addr(p);
         }
         for (uint32_t r = 0; r < h.n_rounds; r++) {
             const QvRound& rd = rounds[r];
-            QvRegPos dep{rd.regpos[0], rd.regpos[1], rd.regpos[2]};
             const uint32_t ngroups = tile_n >> rd.m;
             for (uint32_t g = 0; g < ngroups; g++) {
                 uint32_t e0 = g;
                 for (uint32_t j = 0; j < rd.m; j++) e0 = qv_insert_zero(e0, rd.regpos[j]);
+                const uint32_t se0 = qv_swz(e0);
                 qvc a[8];
                 for (uint32_t s = 0; s < 8; s++) {
-                    if (s < (1u << rd.m)) a[s] = smem[qv_swz(e0 | qv_dep(s, dep.p0, dep.p1, dep.p2))];
+                    if (s < (1u << rd.m)) a[s] = smem[se0 ^ rd.slot_xor[s]];
                     else { a[s].x = 0.0; a[s].y = 0.0; }
                 }
-                qv_apply_round(a, rd, ops, chunks, mats, tables, e0, dep, base);
-                for (uint32_t s = 0; s < (1u << rd.m); s++) smem[qv_swz(e0 | qv_dep(s, dep.p0, dep.p1, dep.p2))] = a[s];
+                qv_apply_round(a, rd, ops, chunks, mats, tables, ext.data(), e0, base);
+                for (uint32_t s = 0; s < (1u << rd.m); s++) smem[se0 ^ rd.slot_xor[s]] = a[s];
             }
         }
         for (uint32_t e = 0; e < tile_n; e++) {
-            const uint64_t p = base | qv_gather(e, h.tile_segs, h.n_tile_segs);
-            psi[p & local_mask] = smem[qv_swz(e)];
+            const uint64_t p = base | qv_gather(e & (QV_THREADS - 1), h.tile_segs, h.n_tile_segs) | h.hi_off[e / QV_THREADS];
+            *addr(p) = smem[qv_swz(e)];
         }
     }
 }
 
-void run_big_step(qvc* psi, int n_bits, const qv::Step& st) {
+void run_big_step(qvc* psi, int n_bits, const qv::Step& st) {   // psi = this rank's shard, n_bits = its log2 size
     const uint32_t k = st.big.k;
     const uint64_t d = 1ull << k;
     uint64_t tmask = 0;
@@ -64,7 +68,7 @@ void run_big_step(qvc* psi, int n_bits, const qv::Step& st) {
     std::vector<qvc> in(d), out(d);
     for (uint64_t base = 0; base < (1ull << n_bits); base++) {
         if (base & tmask) continue;
-        if ((base & st.big.ctrl_mask) != st.big.ctrl_val) continue;
+        if (((base | st.big.fixed_bits) & st.big.ctrl_mask) != st.big.ctrl_val) continue;
         for (uint64_t c = 0; c < d; c++) {
             uint64_t a = base;
             for (uint32_t j = 0; j < k; j++)
@@ -113,7 +117,8 @@ extern "C" int qvtest_run(double* psi, int n_bits, int n_gates, const int* ks, c
         if (l2p_inout) l2p.assign(l2p_inout, l2p_inout + n_bits);
         qv::Tape tape = qv::compile(gates, n_bits, opt, l2p);
         for (const qv::Step& st : tape.steps) {
-            if (st.kind == qv::Step::TILE) run_tile_step((qvc*)psi, st);
+            qvc* peers[1] = {(qvc*)psi};
+            if (st.kind == qv::Step::TILE) run_tile_step(peers, st);
             else run_big_step((qvc*)psi, n_bits, st);
         }
         if (l2p_inout) std::memcpy(l2p_inout, tape.l2p.data(), sizeof(int) * n_bits);
@@ -123,6 +128,70 @@ extern "C" int qvtest_run(double* psi, int n_bits, int n_gates, const int* ks, c
             desc[desc_len - 1] = 0;
         }
         return (int)tape.steps.size();
+    } catch (const std::exception& e) {
+        if (desc && desc_len > 0) {
+            std::strncpy(desc, e.what(), desc_len - 1);
+            desc[desc_len - 1] = 0;
+        }
+        return -1;
+    }
+}
+
+// Emulates `world` ranks in one process: psi holds the shards back to back (rank r at r << n_local).
+// Every rank compiles its own tape (the schedules must agree step for step); step i of all ranks
+// runs before step i+1 of any rank, which is what the barriers around peer passes guarantee on GPUs.
+extern "C" int qvtest_run_sharded(double* psi, int n_bits, int world, int n_gates, const int* ks,
+                                  const int* qubits_flat, const double* mats_flat, int fuse, int tile_bits,
+                                  int absorb_swaps, int* l2p_inout, char* desc, int desc_len) {
+    try {
+        std::vector<qv::Gate> gates(n_gates);
+        size_t qo = 0, mo = 0;
+        for (int g = 0; g < n_gates; g++) {
+            const int k = ks[g];
+            gates[g].qubits.assign(qubits_flat + qo, qubits_flat + qo + k);
+            qo += k;
+            const size_t d = (size_t)1 << k;
+            gates[g].mat.resize(d * d);
+            for (size_t i = 0; i < d * d; i++) gates[g].mat[i] = qv::cd(mats_flat[mo + 2 * i], mats_flat[mo + 2 * i + 1]);
+            mo += 2 * d * d;
+        }
+        int gb = 0;
+        while ((1 << gb) < world) gb++;
+        const int n_local = n_bits - gb;
+        std::vector<int> l2p;
+        if (l2p_inout) l2p.assign(l2p_inout, l2p_inout + n_bits);
+        std::vector<qv::Tape> tapes(world);
+        for (int r = 0; r < world; r++) {
+            qv::CompileOptions opt;
+            opt.fuse = fuse != 0;
+            opt.tile_bits = tile_bits;
+            opt.absorb_swaps = absorb_swaps != 0;
+            opt.n_local_bits = n_local;
+            opt.rank = r;
+            tapes[r] = qv::compile(gates, n_bits, opt, l2p);
+            if (tapes[r].steps.size() != tapes[0].steps.size() || tapes[r].l2p != tapes[0].l2p)
+                throw std::runtime_error("ranks disagree on the schedule");
+        }
+        std::vector<qvc*> peers(world);
+        for (int r = 0; r < world; r++) peers[r] = (qvc*)psi + ((size_t)r << n_local);
+        int peer_steps = 0;
+        for (size_t i = 0; i < tapes[0].steps.size(); i++) {
+            for (int r = 0; r < world; r++) {
+                const qv::Step& st = tapes[r].steps[i];
+                if (st.kind != tapes[0].steps[i].kind || st.uses_peers != tapes[0].steps[i].uses_peers)
+                    throw std::runtime_error("ranks disagree on a step");
+                if (st.kind == qv::Step::TILE) run_tile_step(peers.data(), st);
+                else run_big_step(peers[r], n_local, st);
+            }
+            if (tapes[0].steps[i].uses_peers) peer_steps++;
+        }
+        if (l2p_inout) std::memcpy(l2p_inout, tapes[0].l2p.data(), sizeof(int) * n_bits);
+        if (desc && desc_len > 0) {
+            std::string s = qv::describe(tapes[0]);
+            std::strncpy(desc, s.c_str(), desc_len - 1);
+            desc[desc_len - 1] = 0;
+        }
+        return (int)tapes[0].steps.size() * 1000 + peer_steps;
     } catch (const std::exception& e) {
         if (desc && desc_len > 0) {
             std::strncpy(desc, e.what(), desc_len - 1);

@@ -1,0 +1,63 @@
+"""Host logic of the multi-GPU path: the sharded schedules (remap passes, peer tiles, rank-dependent
+diagonals/controls) interpreted on the CPU for 2/4/8 emulated ranks must reproduce the oracle.
+Mirrors dqvm's own strategy of testing the address algebra without MPI ranks
+(dqvm/tests/distributed-qvm-tests.lisp:52-98, dqvm/tests/program-tests.lisp:61-113)."""
+import numpy as np
+import pytest
+
+from helpers import assert_close, rand_state, random_circuit, run_emulator_sharded, run_oracle, unpermute
+from qvm_b200 import circuits as CC
+
+
+@pytest.mark.parametrize("world", [2, 4, 8])
+@pytest.mark.parametrize("fuse", [True, False])
+def test_sharded_qft(world, fuse):
+    n, tile_bits = 13, 7
+    circ = CC.qft_circuit(range(n))
+    a = rand_state(n)
+    ref = run_oracle(a.copy(), circ)
+    steps, peer_steps, desc, l2p = run_emulator_sharded(a, n, world, circ, fuse=fuse, tile_bits=tile_bits)
+    assert peer_steps >= 1, desc
+    assert_close(unpermute(a, l2p), ref)
+
+
+@pytest.mark.parametrize("seed", range(8))
+def test_sharded_random_circuits(seed):
+    rng = np.random.default_rng(900 + seed)
+    world = int(rng.choice([2, 4, 8]))
+    n = int(rng.integers(12, 15))
+    circ = random_circuit(n, 50, rng, max_dense=4)
+    a = rand_state(n, seed)
+    ref = run_oracle(a.copy(), circ)
+    steps, peer_steps, desc, l2p = run_emulator_sharded(a, n, world, circ, fuse=True, tile_bits=7)
+    assert_close(unpermute(a, l2p), ref)
+
+
+def test_index_tracer_through_remaps():
+    """dqvm's debug wavefunction psi_i = i (dqvm/tests/program-tests.lisp:14-19): permutation-only circuits
+    move integer labels exactly, so any address-algebra slip shows up as a wrong integer."""
+    from qvm_b200 import gates as G
+    n, world = 12, 4
+    rng = np.random.default_rng(3)
+    circ = []
+    for _ in range(40):
+        a, b, c = (int(x) for x in rng.choice(n, 3, replace=False))
+        circ.append([(G.gate_matrix("SWAP"), (a, b)), (G.gate_matrix("CNOT"), (a, b)), (G.gate_matrix("CCNOT"), (a, b, c)),
+                     (G.gate_matrix("X"), (a,))][int(rng.integers(0, 4))])
+    psi = np.arange(1 << n).astype(np.complex128)
+    ref = run_oracle(psi.copy(), circ)
+    _, _, _, l2p = run_emulator_sharded(psi, n, world, circ, fuse=True, tile_bits=6)
+    assert np.array_equal(unpermute(psi, l2p), ref)
+
+
+def test_diagonal_gates_on_global_qubits_need_no_exchange():
+    from qvm_b200 import gates as G
+    n, world = 12, 8
+    circ = [(G.gate_matrix("H"), (q,)) for q in range(9)]
+    circ += [(G.gate_matrix("CZ"), (11, 3)), (G.gate_matrix("CPHASE", [0.3]), (10, 11)), (G.gate_matrix("RZ", [0.7]), (9,)),
+             (G.gate_matrix("CNOT"), (10, 2)), (G.gate_matrix("T"), (11,))]
+    a = rand_state(n)
+    ref = run_oracle(a.copy(), circ)
+    steps, peer_steps, desc, l2p = run_emulator_sharded(a, n, world, circ, fuse=True, tile_bits=6)
+    assert peer_steps == 0, desc
+    assert_close(unpermute(a, l2p), ref)
