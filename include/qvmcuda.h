@@ -126,6 +126,22 @@ int qvmcuda_density_diag_probs(qvmcuda_state *s, int n_qubits, double *out);
  *      read/write peer shards over NVLink. */
 int qvmcuda_shard_export(qvmcuda_state *s, uint8_t handle[64]);
 int qvmcuda_shard_attach(qvmcuda_state *s, int rank, int world, const uint8_t *handles /* world*64 */);
+/* Schedule a gate run against the shard's current qubit layout (gate qubits are LOGICAL, 0 <= q <
+ * log2(shard length) + log2(world); every rank must pass the same gate list).  The tape is run step by
+ * step: a step whose flags have QVMCUDA_STEP_PEER set reads/writes peer shards over NVLink, so the host
+ * must synchronise and barrier all ranks before and after it (dqvm's MPI_Waitall + barrier,
+ * dqvm/src/apply-distributed-gate.lisp:24-86); other steps touch only the local shard.  Steps are
+ * asynchronous on the handle's stream.  qvmcuda_tape_commit adopts the layout the tape leaves behind. */
+#define QVMCUDA_STEP_PEER  1u
+#define QVMCUDA_STEP_REMAP 2u
+int qvmcuda_shard_compile(qvmcuda_state *s, int n_gates, const int32_t *ks, const int32_t *qubits,
+                          const double *matrices, uint32_t flags, qvmcuda_tape **out);
+int qvmcuda_tape_num_steps(qvmcuda_tape *t, int *n_steps);
+int qvmcuda_tape_step_flags(qvmcuda_tape *t, int step, uint32_t *flags);
+int qvmcuda_tape_run_step(qvmcuda_state *s, qvmcuda_tape *t, int step);
+int qvmcuda_tape_commit(qvmcuda_state *s, qvmcuda_tape *t);
+/* current logical -> physical qubit map (n entries; physical bits >= log2(shard length) select the rank) */
+int qvmcuda_state_layout(qvmcuda_state *s, int32_t *l2p, int n);
 
 #ifdef __cplusplus
 }

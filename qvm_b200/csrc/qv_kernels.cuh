@@ -24,6 +24,17 @@ __device__ __forceinline__ void qv_st_stream(qvc* p, qvc v) {
     asm volatile("st.global.L1::no_allocate.v2.f64 [%0], {%1, %2};" ::"l"(p), "d"(v.x), "d"(v.y) : "memory");
 }
 
+// Asynchronous 16-byte global -> shared copy (LDGSTS): no register staging, so a thread keeps all 16 of
+// its tile loads in flight at once (64 KiB per CTA) and the swizzled shared-memory slot is free to choose.
+__device__ __forceinline__ void qv_cp_async16(qvc* smem_dst, const qvc* gsrc) {
+    const uint32_t d = (uint32_t)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void qv_cp_async_wait_all() {
+    asm volatile("cp.async.commit_group;" ::: "memory");
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+}
+
 // ---------------------------------------------------------------------------
 // The tile kernel: one CTA = one tile of 2^T amplitudes staged in shared memory
 // (XOR-swizzled, see qv_swz), rounds of register-resident groups, write back.
@@ -75,19 +86,13 @@ qv_tile_kernel(const __grid_constant__ PROG prog, const __grid_constant__ QvPeer
         const uint64_t pbase = PEERS ? (base | glo) : ((base | glo) & local_mask);
         if (tid < n_chunks) s_ext[tid] = (uint32_t)qv_gather(base, chunks[tid].esegs, chunks[tid].n_esegs);
 
-        // ---- HBM -> shared memory, 8 independent 128-bit loads in flight per thread
+        // ---- HBM -> shared memory: 16 asynchronous 16-byte copies in flight per thread
         if (FULL) {
 #pragma unroll
-            for (int half = 0; half < 2; half++) {
-                qvc v[8];
-#pragma unroll
-                for (int j = 0; j < 8; j++) {
-                    const uint64_t p = pbase | h->hi_off[half * 8 + j];
-                    const qvc* src = PEERS ? peers.base[(p >> n_local) & (QV_MAX_PEERS - 1)] + (p & local_mask) : own + p;
-                    v[j] = qv_ld_stream(src);
-                }
-#pragma unroll
-                for (int j = 0; j < 8; j++) my_tile[(half * 8 + j) * QV_THREADS] = v[j];
+            for (int i = 0; i < 16; i++) {
+                const uint64_t p = pbase | h->hi_off[i];
+                const qvc* src = PEERS ? peers.base[(p >> n_local) & (QV_MAX_PEERS - 1)] + (p & local_mask) : own + p;
+                qv_cp_async16(my_tile + i * QV_THREADS, src);
             }
         } else {
             for (uint32_t i = 0; i < iters; i++) {
@@ -95,10 +100,11 @@ qv_tile_kernel(const __grid_constant__ PROG prog, const __grid_constant__ QvPeer
                 if (e < tile_n) {
                     const uint64_t p = pbase | h->hi_off[i];
                     const qvc* src = PEERS ? peers.base[(p >> n_local) & (QV_MAX_PEERS - 1)] + (p & local_mask) : own + p;
-                    my_tile[i * QV_THREADS] = qv_ld_stream(src);
+                    qv_cp_async16(my_tile + i * QV_THREADS, src);
                 }
             }
         }
+        qv_cp_async_wait_all();
         __syncthreads();
 
         // ---- rounds: 2^m amplitudes per thread in registers, every op of the round applied there

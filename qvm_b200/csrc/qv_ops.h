@@ -135,6 +135,22 @@ QV_HD void qv_dense2_dispatch(qvc a[8], const qvc* M, const QvRound& rd, const Q
     }
 }
 
+// The chunk is gated by register bit RB: every table entry with that bit clear is exactly 1, so only
+// the slots with the bit set are touched (controlled-phase ladders: half the multiplies and lookups).
+template <int RB>
+QV_HD void qv_diag_gated(qvc a[8], const qvc* tab, uint32_t g0, const QvChunk& ch) {
+    if ((ch.reg_mask & (ch.reg_mask - 1)) == 0) {
+        const qvc t1 = tab[g0 | ch.slot_off[1 << RB]];
+#pragma unroll
+        for (int r = 0; r < 8; r++)
+            if (r & (1 << RB)) a[r] = qv_cmul(a[r], t1);
+    } else {
+#pragma unroll
+        for (int r = 0; r < 8; r++)
+            if (r & (1 << RB)) a[r] = qv_cmul(a[r], tab[g0 | ch.slot_off[r]]);
+    }
+}
+
 // One register bit feeds the chunk: two table entries serve the whole group.
 template <int RB>
 QV_HD void qv_diag_1bit(qvc a[8], qvc t0, qvc t1) {
@@ -161,6 +177,10 @@ QV_HD void qv_diag(qvc a[8], const QvOp& op, const QvChunk* chunks, const qvc* t
             // no register bit: one factor for the whole group
             common = have_common ? qv_cmul(common, tab[g0]) : tab[g0];
             have_common = true;
+        } else if (ch.gate_rb) {
+            if (ch.gate_rb == 1) qv_diag_gated<0>(a, tab, g0, ch);
+            else if (ch.gate_rb == 2) qv_diag_gated<1>(a, tab, g0, ch);
+            else qv_diag_gated<2>(a, tab, g0, ch);
         } else if ((rm & (rm - 1)) == 0) {
             const qvc t0 = tab[g0];
             if (rm == 1) qv_diag_1bit<0>(a, t0, tab[g0 | ch.slot_off[1]]);

@@ -53,7 +53,7 @@ struct QvChunk {
     uint32_t table_off;             // offset in complex entries into the pass's table pool
     uint8_t n_lsegs, n_esegs;       // fields gathered from the tile-local index / the tile base
     uint8_t reg_mask;               // which register bits of the op's round feed this chunk
-    uint8_t pad;
+    uint8_t gate_rb;                // 1 + register bit r such that every entry with that bit clear is exactly 1; 0 = none
     QvSeg lsegs[QV_CHUNK_SEGS];     // only the NON-register local bits (register bits go through slot_off)
     QvSeg esegs[QV_CHUNK_SEGS];
     uint32_t slot_off[8];           // table-index contribution of register slot r (host-precomputed)

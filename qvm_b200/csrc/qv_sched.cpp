@@ -329,6 +329,17 @@ void emit_round(BlobWriter& w, const std::vector<RoundOp>& rops, const std::vect
                         edst.push_back((int)i);
                     }
                 }
+                // gated chunk: some register bit whose clear half of the table is exactly 1
+                for (size_t r = 0; r < regpos_local.size() && !qc.gate_rb; r++) {
+                    if (!(qc.reg_mask >> r & 1)) continue;
+                    size_t ibit = 0;
+                    for (size_t i = 0; i < c.bits.size(); i++)
+                        if (tm.local_of[c.bits[i]] == regpos_local[r]) ibit = i;
+                    bool all_one = true;
+                    for (size_t t = 0; t < c.table.size() && all_one; t++)
+                        if (!(t >> ibit & 1) && c.table[t] != cd(1.0, 0.0)) all_one = false;
+                    if (all_one) qc.gate_rb = (uint8_t)(r + 1);
+                }
                 std::vector<QvSeg> ls = make_segs(lsrc, ldst), es = make_segs(esrc, edst);
                 if (ls.size() > QV_CHUNK_SEGS || es.size() > QV_CHUNK_SEGS)
                     throw std::runtime_error("scheduler bug: chunk needs too many segments");
@@ -507,8 +518,8 @@ Step build_tile_step(const std::vector<const Atom*>& atoms, uint64_t tile_target
     off = align16(off + w.mats.size() * sizeof(cd));
     h.n_table_entries = (uint32_t)w.tables.size();
     h.blob_bytes = (uint32_t)off;
-    if (off > QV_PROG_LARGE_BYTES) throw std::runtime_error("scheduler bug: pass control program too large");
-    if (w.chunks.size() > QV_MAX_PASS_CHUNKS) throw std::runtime_error("scheduler bug: too many diagonal chunks in a pass");
+    if (off > QV_PROG_LARGE_BYTES) throw std::length_error("pass control program too large");
+    if (w.chunks.size() > QV_MAX_PASS_CHUNKS) throw std::length_error("too many diagonal chunks in a pass");
 
     Step st;
     st.kind = Step::TILE;
@@ -715,11 +726,12 @@ Tape compile(const std::vector<Gate>& gates, int n_bits, const CompileOptions& o
         size_t n_diag = 0;
         for (const Atom* a : pending) {
             bool blocked = (a->mix & dtouch) != 0 || (dmix & a->touch) != 0;
-            if (!blocked && a->kind == Atom::DIAG && n_diag + 1 > QV_MAX_PASS_CHUNKS) blocked = true;
+            if (!blocked && a->kind == Atom::DIAG && n_diag + 1 > 4096) blocked = true;
             // conservative size of the atom in the control program (round + op + chunk + matrix)
-            const size_t need_bytes = sizeof(QvRound) + sizeof(QvOp) +
-                                      (a->kind == Atom::DENSE ? a->mat.size() * sizeof(cd) : sizeof(QvChunk));
-            if (!blocked && est_bytes + need_bytes > QV_PROG_LARGE_BYTES - 1024) blocked = true;
+            // rough size of the atom in the control program; diagonals merge into shared chunks, so they
+            // are cheap -- the real size is checked when the pass is built (see the retry below)
+            const size_t need_bytes = a->kind == Atom::DENSE ? sizeof(QvOp) + a->mat.size() * sizeof(cd) + 32 : 16;
+            if (!blocked && est_bytes + need_bytes > QV_PROG_LARGE_BYTES - 2048) blocked = true;
             if (!blocked) {
                 if (a->kind == Atom::BIG) blocked = true;
                 else if (a->kind == Atom::DENSE) {
@@ -756,7 +768,23 @@ Tape compile(const std::vector<Gate>& gates, int n_bits, const CompileOptions& o
             remap(need, pending);
             continue;
         }
-        tape.steps.push_back(build_tile_step(in_pass, targets, geo, lay));
+        // Build the pass; if its control program or chunk count overflows, keep the first half of the
+        // atoms and send the rest back (original order restored: pointers into `atoms` are ordered).
+        for (;;) {
+            try {
+                tape.steps.push_back(build_tile_step(in_pass, targets, geo, lay));
+                break;
+            } catch (const std::length_error&) {
+                if (in_pass.size() < 2) throw std::runtime_error("scheduler: a single atom overflows a pass");
+                const size_t keep = in_pass.size() / 2;
+                deferred.insert(deferred.end(), in_pass.begin() + keep, in_pass.end());
+                std::sort(deferred.begin(), deferred.end());
+                in_pass.resize(keep);
+                targets = 0;
+                for (const Atom* a : in_pass)
+                    if (a->kind == Atom::DENSE) targets |= phys_mask(a->mix);
+            }
+        }
         pending.swap(deferred);
     }
     tape.l2p.resize(n_bits);

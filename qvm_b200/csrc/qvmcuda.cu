@@ -78,6 +78,7 @@ struct qvmcuda_tape {
     std::map<int, uint8_t*> d_blobs;      // device -> one buffer holding every step's blob / matrix
     std::vector<size_t> offsets;          // per step offset into the buffer
     size_t total_bytes = 0;
+    int n_local = 0, rank = 0, world = 1; // geometry the tape was compiled for
 };
 
 namespace {
@@ -223,6 +224,7 @@ int run_gates_locked(qvmcuda_state* s, const std::vector<qv::Gate>& gates, uint3
 // Undo absorbed swaps so that physical bit q holds logical qubit q again.
 int canonicalize_locked(qvmcuda_state* s) {
     if (l2p_is_identity(s->l2p)) return 0;
+    if (s->world > 1) return 0;   // shards keep their layout; the host maps indices through qvmcuda_state_layout
     std::vector<int> l2p = s->l2p;
     std::vector<qv::Gate> swaps;
     static const double sw[16] = {1, 0, 0, 0, 0, 0, 1, 0, 0, 1, 0, 0, 0, 0, 0, 1};
@@ -259,6 +261,18 @@ int reduce_locked(qvmcuda_state* s, uint64_t count, int mode, uint32_t q, uint64
     CK(cudaMemcpyAsync(out, s->d_partial + kReduceBlocks, sizeof(double), cudaMemcpyDeviceToHost, s->stream));
     CK(cudaStreamSynchronize(s->stream));
     return 0;
+}
+
+// Probability that physical bit `pbit` equals `value`, restricted to this shard (the host adds the
+// shards' partial results).  A rank bit is constant over the shard.
+int prob_bit_locked(qvmcuda_state* s, int pbit, int value, double* p) {
+    if (pbit < s->n_bits) return reduce_locked(s, s->n_amps / 2, value ? 1 : 3, (uint32_t)pbit, 0, p);
+    const int mine = (s->rank >> (pbit - s->n_bits)) & 1;
+    if (mine != value) {
+        *p = 0.0;
+        return 0;
+    }
+    return reduce_locked(s, s->n_amps, 0, 0, 0, p);
 }
 
 int elementwise_locked(qvmcuda_state* s, int mode, uint32_t q, uint32_t q2, uint32_t keep, double f) {
@@ -446,6 +460,7 @@ int qvmcuda_tape_compile(int n_qubits, int n_gates, const int32_t* ks, const int
     if (int rc = gates_from_flat(n_gates, ks, qubits, matrices, gates)) return rc;
     qvmcuda_tape* t = new qvmcuda_tape();
     t->flags = flags;
+    t->n_local = n_qubits;
     try {
         t->tape = qv::compile(gates, n_qubits, make_options(nullptr, flags));
     } catch (const std::exception& e) {
@@ -454,6 +469,90 @@ int qvmcuda_tape_compile(int n_qubits, int n_gates, const int32_t* ks, const int
     }
     layout_tape(t);
     *out = t;
+    return 0;
+}
+
+static int tape_device_buffer(qvmcuda_state* s, qvmcuda_tape* t, uint8_t** out) {
+    uint8_t*& d_buf = t->d_blobs[s->device];
+    if (!d_buf) {
+        std::vector<uint8_t> host(t->total_bytes ? t->total_bytes : 256, 0);
+        for (size_t i = 0; i < t->tape.steps.size(); i++) {
+            const qv::Step& st = t->tape.steps[i];
+            const std::vector<qv::cd>& src = st.kind == qv::Step::TILE ? st.tables : st.bigmat;
+            if (!src.empty()) std::memcpy(host.data() + t->offsets[i], src.data(), src.size() * sizeof(qv::cd));
+        }
+        CK(cudaMalloc((void**)&d_buf, host.size()));
+        CK(cudaMemcpy(d_buf, host.data(), host.size(), cudaMemcpyHostToDevice));
+    }
+    *out = d_buf;
+    return 0;
+}
+
+int qvmcuda_shard_compile(qvmcuda_state* s, int n_gates, const int32_t* ks, const int32_t* qubits,
+                          const double* matrices, uint32_t flags, qvmcuda_tape** out) {
+    if (!s || !out) return fail("null argument");
+    *out = nullptr;
+    std::vector<qv::Gate> gates;
+    if (int rc = gates_from_flat(n_gates, ks, qubits, matrices, gates)) return rc;
+    std::lock_guard<std::mutex> lk(s->mu);
+    qvmcuda_tape* t = new qvmcuda_tape();
+    t->flags = flags;
+    t->n_local = s->n_bits;
+    t->rank = s->rank;
+    t->world = s->world;
+    try {
+        const int total_bits = s->n_bits + log2_exact((uint64_t)s->world);
+        t->tape = qv::compile(gates, total_bits, make_options(s, flags), s->l2p);
+    } catch (const std::exception& e) {
+        delete t;
+        return fail(std::string("schedule: ") + e.what());
+    }
+    layout_tape(t);
+    *out = t;
+    return 0;
+}
+
+int qvmcuda_tape_num_steps(qvmcuda_tape* t, int* n_steps) {
+    if (!t || !n_steps) return fail("null argument");
+    *n_steps = (int)t->tape.steps.size();
+    return 0;
+}
+
+int qvmcuda_tape_step_flags(qvmcuda_tape* t, int step, uint32_t* flags) {
+    if (!t || !flags) return fail("null argument");
+    if (step < 0 || step >= (int)t->tape.steps.size()) return fail("step out of range");
+    const qv::Step& st = t->tape.steps[step];
+    *flags = (st.uses_peers ? QVMCUDA_STEP_PEER : 0u) | (st.is_remap ? QVMCUDA_STEP_REMAP : 0u);
+    return 0;
+}
+
+int qvmcuda_tape_run_step(qvmcuda_state* s, qvmcuda_tape* t, int step) {
+    if (!s || !t) return fail("null argument");
+    std::lock_guard<std::mutex> lk(s->mu);
+    std::lock_guard<std::mutex> lt(t->mu);
+    if (step < 0 || step >= (int)t->tape.steps.size()) return fail("step out of range");
+    if (t->n_local != s->n_bits || t->rank != s->rank || t->world != s->world)
+        return fail("tape was compiled for a different shard geometry");
+    DeviceGuard dg(s->device);
+    uint8_t* d_buf = nullptr;
+    if (int rc = tape_device_buffer(s, t, &d_buf)) return rc;
+    const qv::Step& st = t->tape.steps[step];
+    return st.kind == qv::Step::TILE ? launch_tile(s, st, d_buf + t->offsets[step]) : launch_big(s, st, d_buf + t->offsets[step]);
+}
+
+int qvmcuda_tape_commit(qvmcuda_state* s, qvmcuda_tape* t) {
+    if (!s || !t) return fail("null argument");
+    std::lock_guard<std::mutex> lk(s->mu);
+    if (t->tape.l2p.size() != s->l2p.size()) return fail("tape layout does not match the state");
+    s->l2p = t->tape.l2p;
+    return 0;
+}
+
+int qvmcuda_state_layout(qvmcuda_state* s, int32_t* l2p, int n) {
+    if (!s || !l2p) return fail("null argument");
+    std::lock_guard<std::mutex> lk(s->mu);
+    if (n != (int)s->l2p.size()) return fail("layout length mismatch");
+    for (int i = 0; i < n; i++) l2p[i] = s->l2p[i];
     return 0;
 }
 
@@ -470,18 +569,8 @@ int qvmcuda_tape_run(qvmcuda_state* s, qvmcuda_tape* t) {
         s->l2p = t->tape.l2p;
         return 0;
     }
-    uint8_t*& d_buf = t->d_blobs[s->device];
-    if (!d_buf) {
-        std::vector<uint8_t> host(t->total_bytes, 0);
-        for (size_t i = 0; i < t->tape.steps.size(); i++) {
-            const qv::Step& st = t->tape.steps[i];
-            const std::vector<qv::cd>& src = st.kind == qv::Step::TILE ? st.tables : st.bigmat;
-            if (!src.empty()) std::memcpy(host.data() + t->offsets[i], src.data(), src.size() * sizeof(qv::cd));
-        }
-        host.resize(t->total_bytes ? t->total_bytes : 256, 0);
-        CK(cudaMalloc((void**)&d_buf, host.size()));
-        CK(cudaMemcpy(d_buf, host.data(), host.size(), cudaMemcpyHostToDevice));
-    }
+    uint8_t* d_buf = nullptr;
+    if (int rc = tape_device_buffer(s, t, &d_buf)) return rc;
     if (int rc = run_steps(s, t->tape, t->offsets, d_buf)) return rc;
     s->l2p = t->tape.l2p;
     return 0;
@@ -519,17 +608,17 @@ int qvmcuda_tape_destroy(qvmcuda_tape* t) {
 int qvmcuda_prob_excited(qvmcuda_state* s, int qubit, double* p) {
     if (!s || !p) return fail("null argument");
     std::lock_guard<std::mutex> lk(s->mu);
-    if (qubit < 0 || qubit >= s->n_bits) return fail("qubit out of range");
+    if (qubit < 0 || qubit >= (int)s->l2p.size()) return fail("qubit out of range");
     DeviceGuard dg(s->device);
-    return reduce_locked(s, s->n_amps / 2, 1, (uint32_t)s->l2p[qubit], 0, p);
+    return prob_bit_locked(s, s->l2p[qubit], 1, p);
 }
 
 int qvmcuda_prob_ground(qvmcuda_state* s, int qubit, double* p) {
     if (!s || !p) return fail("null argument");
     std::lock_guard<std::mutex> lk(s->mu);
-    if (qubit < 0 || qubit >= s->n_bits) return fail("qubit out of range");
+    if (qubit < 0 || qubit >= (int)s->l2p.size()) return fail("qubit out of range");
     DeviceGuard dg(s->device);
-    return reduce_locked(s, s->n_amps / 2, 3, (uint32_t)s->l2p[qubit], 0, p);
+    return prob_bit_locked(s, s->l2p[qubit], 0, p);
 }
 
 int qvmcuda_norm2(qvmcuda_state* s, double* out) {
@@ -555,9 +644,17 @@ int qvmcuda_normalize(qvmcuda_state* s) {
 int qvmcuda_collapse(qvmcuda_state* s, int qubit, int keep_bit, double inv_norm) {
     if (!s) return fail("null argument");
     std::lock_guard<std::mutex> lk(s->mu);
-    if (qubit < 0 || qubit >= s->n_bits) return fail("qubit out of range");
+    if (qubit < 0 || qubit >= (int)s->l2p.size()) return fail("qubit out of range");
     DeviceGuard dg(s->device);
-    return elementwise_locked(s, 1, (uint32_t)s->l2p[qubit], 0, keep_bit ? 1u : 0u, inv_norm);
+    const int pbit = s->l2p[qubit];
+    if (pbit >= s->n_bits) {
+        // the qubit selects the rank: the whole shard is either kept (scaled) or annihilated
+        const int mine = (s->rank >> (pbit - s->n_bits)) & 1;
+        if (mine == (keep_bit ? 1 : 0)) return elementwise_locked(s, 0, 0, 0, 0, inv_norm);
+        CK(cudaMemsetAsync(s->d_amps, 0, s->n_amps * sizeof(qvc), s->stream));
+        return 0;
+    }
+    return elementwise_locked(s, 1, (uint32_t)pbit, 0, keep_bit ? 1u : 0u, inv_norm);
 }
 
 int qvmcuda_sample(qvmcuda_state* s, const double* uniforms, uint64_t n_shots, uint64_t* out, int strict) {

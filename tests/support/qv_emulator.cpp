@@ -200,3 +200,64 @@ extern "C" int qvtest_run_sharded(double* psi, int n_bits, int world, int n_gate
         return -1;
     }
 }
+
+// ---- step-wise sharded emulation for the gloo world-size-2 tests: each PROCESS owns one rank's tape and
+// runs its own steps on shards that live in POSIX shared memory (standing in for NVLink peer access).
+struct EmuTape {
+    qv::Tape tape;
+    int n_local = 0;
+};
+
+extern "C" void* qvtest_shard_compile(int n_bits, int world, int rank, int n_gates, const int* ks, const int* qubits_flat,
+                                      const double* mats_flat, int fuse, int tile_bits, int absorb_swaps,
+                                      const int* l2p_in, char* err, int errlen) {
+    try {
+        std::vector<qv::Gate> gates(n_gates);
+        size_t qo = 0, mo = 0;
+        for (int g = 0; g < n_gates; g++) {
+            const int k = ks[g];
+            gates[g].qubits.assign(qubits_flat + qo, qubits_flat + qo + k);
+            qo += k;
+            const size_t d = (size_t)1 << k;
+            gates[g].mat.resize(d * d);
+            for (size_t i = 0; i < d * d; i++) gates[g].mat[i] = qv::cd(mats_flat[mo + 2 * i], mats_flat[mo + 2 * i + 1]);
+            mo += 2 * d * d;
+        }
+        int gb = 0;
+        while ((1 << gb) < world) gb++;
+        qv::CompileOptions opt;
+        opt.fuse = fuse != 0;
+        opt.tile_bits = tile_bits;
+        opt.absorb_swaps = absorb_swaps != 0;
+        opt.n_local_bits = n_bits - gb;
+        opt.rank = rank;
+        std::vector<int> l2p(l2p_in, l2p_in + n_bits);
+        EmuTape* t = new EmuTape();
+        t->n_local = n_bits - gb;
+        t->tape = qv::compile(gates, n_bits, opt, l2p);
+        return t;
+    } catch (const std::exception& e) {
+        if (err && errlen > 0) {
+            std::strncpy(err, e.what(), errlen - 1);
+            err[errlen - 1] = 0;
+        }
+        return nullptr;
+    }
+}
+extern "C" int qvtest_shard_num_steps(void* t) { return (int)((EmuTape*)t)->tape.steps.size(); }
+extern "C" int qvtest_shard_step_flags(void* t, int i) {
+    const qv::Step& st = ((EmuTape*)t)->tape.steps[i];
+    return (st.uses_peers ? 1 : 0) | (st.is_remap ? 2 : 0);
+}
+extern "C" int qvtest_shard_run_step(void* t, int i, double** peers, int rank) {
+    EmuTape* et = (EmuTape*)t;
+    const qv::Step& st = et->tape.steps[i];
+    if (st.kind == qv::Step::TILE) run_tile_step((qvc* const*)peers, st);
+    else run_big_step((qvc*)peers[rank], et->n_local, st);
+    return 0;
+}
+extern "C" void qvtest_shard_l2p(void* t, int* out) {
+    EmuTape* et = (EmuTape*)t;
+    for (size_t i = 0; i < et->tape.l2p.size(); i++) out[i] = et->tape.l2p[i];
+}
+extern "C" void qvtest_shard_free(void* t) { delete (EmuTape*)t; }

@@ -1,0 +1,87 @@
+"""The N > 1 path on CPU: two processes, torch.distributed `gloo`, ShardedState driving the TEST-ONLY
+emulator engine (shards in POSIX shared memory).  Checks the protocol the GPUs follow: identical
+schedules on every rank, barriers around peer passes, scalar reductions, sharded sampling/measurement."""
+import os
+import socket
+import sys
+import traceback
+
+import numpy as np
+import pytest
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, q):
+    try:
+        sys.path.insert(0, HERE)
+        sys.path.insert(0, os.path.dirname(HERE))
+        sys.path.insert(0, os.path.join(HERE, "support"))
+        import torch.distributed as dist
+        dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world)
+        import helpers
+        from emu_engine import EmuShardEngine
+        from oracle import oracle as O
+        from qvm_b200 import circuits as CC
+        from qvm_b200 import gates as G
+        from qvm_b200.dist import ShardedState
+
+        n = 11
+        n_local = n - (world.bit_length() - 1)
+        st = ShardedState(n, dist, engine_factory=lambda: EmuShardEngine(n_local, rank, world, dist, tag=port))
+        psi = helpers.rand_state(n, 21)
+        st.scatter_logical(psi)
+        rng = np.random.default_rng(5)
+        circ = CC.qft_circuit(range(n)) + helpers.random_circuit(n, 40, rng, max_dense=3)
+        st.apply_gates(circ, fuse=True)
+        ref = helpers.run_oracle(psi.copy(), circ)
+        got = st.gather_logical()
+        helpers.assert_close(got, ref)
+        assert st.peer_steps >= 1
+        assert abs(st.norm2() - 1) < 1e-12
+        for qb in range(n):
+            assert abs(st.prob_excited(qb) - O.prob_excited(ref, qb)) < 1e-12
+        # sampling: every rank returns the same logical indices, distributed like |psi|^2
+        u = np.random.default_rng(7).random(4000)
+        idx = st.sample(u, strict=False)
+        probs = np.abs(ref) ** 2
+        hist = np.bincount(idx.astype(np.int64), minlength=1 << n) / u.size
+        assert np.abs(hist - probs).sum() < 0.9          # coarse: 2048 bins, 4000 shots
+        assert probs[idx.astype(np.int64)].min() > 0
+        # measurement of a qubit that currently selects the rank and of a local one
+        lay = st.layout()
+        for qb in (int(np.argmax(lay)), int(np.argmin(lay))):
+            p1 = O.prob_excited(ref, qb)
+            bit = st.measure(qb, 0.37)
+            assert bit == (1 if 0.37 <= p1 else 0)
+            O.force_measurement(ref, qb, bit, p1)
+            helpers.assert_close(st.gather_logical(), ref)
+        st.close()
+        dist.destroy_process_group()
+        q.put((rank, "ok"))
+    except Exception:
+        q.put((rank, traceback.format_exc()))
+
+
+@pytest.mark.timeout(300)
+def test_two_rank_gloo_sharded_state():
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    results = [q.get(timeout=240) for _ in procs]
+    for p in procs:
+        p.join(timeout=30)
+    for rank, msg in results:
+        assert msg == "ok", f"rank {rank}: {msg}"

@@ -1,0 +1,96 @@
+"""Multi-GPU parity (-m gpu, needs >= 2 GPUs on the box): two ranks over NCCL, each owning one shard;
+the tile kernel reaches the peer shard over NVLink (CUDA IPC).  Compared with the oracle on rank 0."""
+import os
+import socket
+import sys
+import traceback
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, q):
+    try:
+        sys.path.insert(0, HERE)
+        sys.path.insert(0, os.path.dirname(HERE))
+        import torch
+        import torch.distributed as dist
+        torch.cuda.set_device(rank)
+        dist.init_process_group("nccl", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world,
+                                device_id=torch.device("cuda", rank))
+        import helpers
+        from oracle import oracle as O
+        from qvm_b200 import circuits as CC
+        from qvm_b200.dist import ShardedState
+
+        n = 19 + (world.bit_length() - 1)
+        st = ShardedState(n, dist, device=rank)
+        psi = helpers.rand_state(n, 21)
+        st.scatter_logical(psi)
+        rng = np.random.default_rng(5)
+        circ = CC.qft_circuit(range(n)) + helpers.random_circuit(n, 60, rng, max_dense=3) + CC.random_layer_circuit(n, 2, 1)
+        for fuse in (True, False):
+            st.set_zero_state()
+            st.scatter_logical(psi)
+            st.apply_gates(circ, fuse=fuse)
+            got = st.gather_logical()
+            if rank == 0:
+                ref = helpers.run_oracle(psi.copy(), circ)
+                helpers.assert_close(got, ref)
+        assert st.peer_steps >= 1
+        assert abs(st.norm2() - 1) < 1e-12
+        ref = helpers.run_oracle(psi.copy(), circ)
+        for qb in (0, 7, n - 2, n - 1):
+            assert abs(st.prob_excited(qb) - O.prob_excited(ref, qb)) < 1e-12
+        u = np.random.default_rng(7).random(20000)
+        idx = st.sample(u, strict=False).astype(np.int64)
+        probs = np.abs(ref) ** 2
+        assert probs[idx].min() > 0
+        # coarse distribution check on the top 3 logical qubits
+        for qb in (n - 1, n - 2, 0):
+            frac = ((idx >> qb) & 1).mean()
+            assert abs(frac - O.prob_excited(ref, qb)) < 0.02
+        lay = st.layout()
+        for qb in (int(np.argmax(lay)), int(np.argmin(lay))):
+            p1 = O.prob_excited(ref, qb)
+            bit = st.measure(qb, 0.37)
+            assert bit == (1 if 0.37 <= p1 else 0)
+            O.force_measurement(ref, qb, bit, p1)
+            got = st.gather_logical()
+            if rank == 0:
+                helpers.assert_close(got, ref)
+        st.close()
+        dist.destroy_process_group()
+        q.put((rank, "ok"))
+    except Exception:
+        q.put((rank, traceback.format_exc()))
+
+
+@pytest.mark.parametrize("world", [2, 4, 8])
+def test_sharded_state_over_nvlink(world):
+    import torch
+    if torch.cuda.device_count() < world:
+        pytest.skip(f"needs {world} GPUs")
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    results = [q.get(timeout=600) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+    for rank, msg in results:
+        assert msg == "ok", f"rank {rank}: {msg}"
