@@ -1,0 +1,66 @@
+;;;; measurement.lisp -- the measurement protocol on device states (src/measurement.lisp:7-225).
+;;;; The random draws stay in Lisp (mt19937, src/measurement.lisp:99,136): the library only ever
+;;;; receives uniforms.
+
+(in-package #:qvm-cuda)
+
+(defmethod qvm::get-excited-state-probability ((state device-pure-state) qubit)
+  (flush-gate-tape state)
+  (call-returning-double #'prob-excited (device-handle state) qubit))
+
+(defmethod qvm::get-excited-state-probability ((state device-density-matrix-state) qubit)
+  (call-returning-double #'density-prob-excited (device-handle state) (qvm::num-qubits state) qubit))
+
+(defmethod qvm::force-measurement (measured-value qubit (state device-pure-state) excited-probability)
+  ;; src/measurement.lisp:10-41
+  (flush-gate-tape state)
+  (let ((inv-norm (if (= 1 measured-value)
+                      (/ (sqrt excited-probability))
+                      (/ (sqrt (- (qvm:flonum 1) excited-probability))))))
+    (collapse (device-handle state) qubit measured-value inv-norm)
+    (setf (device-newer-p state) t)
+    state))
+
+(defmethod qvm::force-measurement (measured-value qubit (state device-density-matrix-state)
+                                   excited-probability)
+  ;; src/measurement.lisp:43-68: rescale by 1/p, not 1/sqrt(p)
+  (let ((inv-norm (if (= 1 measured-value)
+                      (/ excited-probability)
+                      (/ (- (qvm:flonum 1) excited-probability)))))
+    (density-collapse (device-handle state) (qvm::num-qubits state) qubit measured-value inv-norm)
+    (setf (device-newer-p state) t)
+    state))
+
+(defmethod qvm::measure-all-state ((state device-pure-state) (qvm qvm::base-qvm))
+  ;; src/measurement.lisp:128-143: one uniform, smallest b with C(b) > p, psi <- |b>
+  (flush-gate-tape state)
+  (let ((basis-state
+          (cffi:with-foreign-objects ((u :double) (out :uint64))
+            (setf (cffi:mem-ref u :double) (qvm:flonum (random 1.0d0)))
+            (sample (device-handle state) u 1 out 1)
+            (cffi:mem-ref out :uint64))))
+    (set-basis-state (device-handle state) basis-state)
+    (setf (device-newer-p state) t
+          (host-newer-p state) nil)
+    (values qvm (loop :for i :below (qvm:number-of-qubits qvm)
+                      :collect (ldb (byte 1 i) basis-state)))))
+
+(defmethod qvm::apply-measure-discard-to-state (qvm (state device-density-matrix-state)
+                                                (instr quil:measure-discard))
+  ;; src/measurement.lisp:111-120
+  (density-measure-discard (device-handle state) (qvm::num-qubits state)
+                           (quil:qubit-index (quil:measurement-qubit instr)))
+  (setf (device-newer-p state) t)
+  qvm)
+
+(defun sample-wavefunction-multiple-times/cuda (state num-samples)
+  "SAMPLE-WAVEFUNCTION-MULTIPLE-TIMES (src/measurement.lisp:246-288) on a device state: NUM-SAMPLES
+uniforms are drawn here, the prefix structure and the searches run on the GPU."
+  (flush-gate-tape state)
+  (let ((samples (make-array num-samples :element-type '(unsigned-byte 64) :initial-element 0)))
+    (cffi:with-foreign-objects ((u :double num-samples) (out :uint64 num-samples))
+      (dotimes (i num-samples)
+        (setf (cffi:mem-aref u :double i) (random 1.0d0)))
+      (sample (device-handle state) u num-samples out 0)
+      (dotimes (i num-samples samples)
+        (setf (aref samples i) (cffi:mem-aref out :uint64 i))))))
