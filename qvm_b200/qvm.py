@@ -200,6 +200,31 @@ class DensityMatrixState:
         """DENSITY-MATRIX-STATE-MEASUREMENT-PROBABILITIES :268-286."""
         return self.vec.density_diag_probs(self.num_qubits)
 
+    def apply_ops(self, ops, fuse: bool = True) -> None:
+        """A run of unitaries / Kraus channels in ONE library call (fused passes over vec(rho))."""
+        self.vec.apply_gates(density_gate_list(self.num_qubits, ops), fuse=fuse)
+
+
+def density_gate_list(n: int, ops):
+    """Translate density-matrix operations into gates on the 2n index bits of vec(rho).
+
+    ops = [(U or [K_0, K_1, ...], qubits in Quil order)].  A unitary becomes conj(U) on the column bits
+    (qubits) and U on the row bits (qubits + n), exactly the two applications of src/apply-gate.lisp:56-65.
+    A Kraus list becomes ONE superoperator sum_j K_j (x) conj(K_j) on (row bits, column bits) instead of the
+    reference's copy / apply / add / restore loop (src/apply-gate.lisp:79-99)."""
+    out = []
+    for gate, qubits in ops:
+        qubits = tuple(int(q) for q in qubits)
+        ghosts = tuple(q + n for q in qubits)
+        if isinstance(gate, (list, tuple)) and len(gate) > 1:
+            sop = sum(np.kron(np.asarray(k, dtype=np.complex128), np.conj(np.asarray(k, dtype=np.complex128))) for k in gate)
+            out.append((np.ascontiguousarray(sop), ghosts + qubits))
+        else:
+            u = np.asarray(gate[0] if isinstance(gate, (list, tuple)) else gate, dtype=np.complex128)
+            out.append((np.ascontiguousarray(np.conj(u)), qubits))
+            out.append((np.ascontiguousarray(u), ghosts))
+    return out
+
 
 def apply_gate_to_state(gate, state, qubits: Sequence[int]) -> None:
     """APPLY-GATE-TO-STATE (src/apply-gate.lisp:106-212).  GATE is a matrix, or a list of Kraus

@@ -151,3 +151,18 @@ def unpermute(psi_phys, l2p):
     for q in range(n):
         phys |= ((idx >> q) & 1) << int(l2p[q])
     return psi_phys[phys]
+
+
+def load_bench_circuit(name):
+    """Benchmark inputs of the reference (bench/*.quil), from the committed fixture
+    tests/golden/bench_circuits.json -> ([(matrix, qubits)], measures, n_qubits)."""
+    import json
+    from qvm_b200 import gates as G
+    data = json.load(open(os.path.join(ROOT, "tests", "golden", "bench_circuits.json")))[name]
+    circ, measures = [], []
+    for ins in data["instructions"]:
+        if ins[0] == "G":
+            circ.append((G.gate_matrix(ins[1], ins[2]), tuple(ins[3])))
+        else:
+            measures.append((ins[1], tuple(ins[2]) if ins[2] else None))
+    return circ, measures, data["n_qubits"]

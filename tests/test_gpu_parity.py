@@ -327,3 +327,30 @@ def test_large_state_properties(Q):
     assert abs(z[0] - 1) < 1e-10 and np.abs(z[1:]).max() < 1e-10
     assert abs(vec.norm2() - 1) < 1e-10
     vec.close()
+
+
+def test_density_noisy_qaoa_fused_vs_oracle(Q, O):
+    """Config 4 at small size: QAOA line graph + depolarizing after every gate, one fused library call."""
+    n = 5
+    circ = CC.qaoa_maxcut_circuit(n, CC.line_graph(n))
+    dep = G.depolarizing_kraus_map(0.01)
+    ops = []
+    for m, q in circ:
+        ops.append((m, q))
+        for qq in q:
+            ops.append((dep, (qq,)))
+    rho = O.zero_density(n)
+    for gate, q in ops:
+        if isinstance(gate, list):
+            O.density_apply_kraus(rho, n, gate, q)
+        else:
+            O.density_apply_unitary(rho, n, gate, q)
+    st = Q.DensityMatrixState(n)
+    st.apply_ops(ops, fuse=True)
+    assert_close(st.state_elements(), rho)
+    assert abs(st.measurement_probabilities().sum() - 1) < 1e-12
+    # 2q channel given as kraus-kron product (16 operators): one 4-index-bit superoperator
+    kk = G.kraus_kron(dep, dep)
+    O.density_apply_kraus(rho, n, kk, (3, 1))
+    st.apply_ops([(kk, (3, 1))])
+    assert_close(st.state_elements(), rho)
