@@ -266,6 +266,8 @@ def main():
     ap.add_argument("--cpu-budget", type=float, default=15.0)
     ap.add_argument("--ref-gates-per-step", type=int, default=4)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--workload", default="qft", choices=["qft", "random"], help="N>1 only: circuit family")
+    ap.add_argument("--layers", type=int, default=4, help="layers of the random workload")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

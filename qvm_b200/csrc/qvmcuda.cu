@@ -1,6 +1,8 @@
 // qvmcuda.cu -- C ABI of libqvmcuda (see include/qvmcuda.h for the contract and
 // the reference interfaces each entry point stands behind).
 #include <atomic>
+#include <chrono>
+#include <cstdlib>
 #include <cstdio>
 #include <cstring>
 #include <map>
@@ -69,6 +71,11 @@ struct qvmcuda_state {
     int rank = 0, world = 1;
     QvPeers peers{};
     std::vector<void*> opened;     // IPC-opened peer pointers
+    // immediate-mode program upload
+    uint8_t* d_scratch = nullptr;
+    uint8_t* h_scratch = nullptr;  // pinned
+    size_t scratch_cap = 0;
+    cudaEvent_t upload_done = nullptr;
 };
 
 struct qvmcuda_tape {
@@ -190,6 +197,15 @@ qv::CompileOptions make_options(const qvmcuda_state* s, uint32_t flags) {
 
 // compile + upload + run in immediate mode (state mutex held)
 int run_gates_locked(qvmcuda_state* s, const std::vector<qv::Gate>& gates, uint32_t flags) {
+    static const bool trace = getenv("QVMCUDA_TRACE") != nullptr;
+    const auto t_begin = std::chrono::steady_clock::now();
+    struct Tracer {
+        bool on; std::chrono::steady_clock::time_point t0; size_t n;
+        ~Tracer() {
+            if (on) fprintf(stderr, "[qvmcuda] apply_gates: %zu gates, host time %.3f ms\n", n,
+                            std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count());
+        }
+    } tracer{trace, t_begin, gates.size()};
     qvmcuda_tape t;
     try {
         const int total_bits = s->n_bits + log2_exact((uint64_t)s->world);
@@ -198,24 +214,39 @@ int run_gates_locked(qvmcuda_state* s, const std::vector<qv::Gate>& gates, uint3
         return fail(std::string("schedule: ") + e.what());
     }
     layout_tape(&t);
+    if (trace) fprintf(stderr, "[qvmcuda] schedule: %zu steps in %.3f ms\n", t.tape.steps.size(),
+                       std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_begin).count());
     if (t.tape.steps.empty()) {
         s->l2p = t.tape.l2p;
         return 0;
     }
-    std::vector<uint8_t> host(t.total_bytes, 0);
+    // Program data (diagonal tables / big matrices) go through a persistent pinned staging buffer and a
+    // persistent device scratch buffer: no allocation on the gate path.  The staging buffer is reused only
+    // after the previous upload has completed (event), the device buffer is protected by stream order.
+    const size_t need = t.total_bytes ? t.total_bytes : 256;
+    if (need > s->scratch_cap) {
+        CK(cudaStreamSynchronize(s->stream));
+        if (s->d_scratch) cudaFree(s->d_scratch);
+        if (s->h_scratch) cudaFreeHost(s->h_scratch);
+        s->d_scratch = nullptr;
+        s->h_scratch = nullptr;
+        s->scratch_cap = 0;
+        const size_t cap = std::max<size_t>(need * 2, 1 << 20);
+        CK(cudaMalloc((void**)&s->d_scratch, cap));
+        CK(cudaMallocHost((void**)&s->h_scratch, cap));
+        if (!s->upload_done) CK(cudaEventCreateWithFlags(&s->upload_done, cudaEventDisableTiming));
+        s->scratch_cap = cap;
+    } else {
+        CK(cudaEventSynchronize(s->upload_done));
+    }
     for (size_t i = 0; i < t.tape.steps.size(); i++) {
         const qv::Step& st = t.tape.steps[i];
         const std::vector<qv::cd>& src = st.kind == qv::Step::TILE ? st.tables : st.bigmat;
-        if (!src.empty()) std::memcpy(host.data() + t.offsets[i], src.data(), src.size() * sizeof(qv::cd));
+        if (!src.empty()) std::memcpy(s->h_scratch + t.offsets[i], src.data(), src.size() * sizeof(qv::cd));
     }
-    uint8_t* d_buf = nullptr;
-    const size_t alloc_bytes = t.total_bytes ? t.total_bytes : 256;
-    host.resize(alloc_bytes, 0);
-    CK(cudaMallocAsync((void**)&d_buf, alloc_bytes, s->stream));
-    CK(cudaMemcpyAsync(d_buf, host.data(), alloc_bytes, cudaMemcpyHostToDevice, s->stream));
-    // pageable source: the copy has been staged when the call returns, `host` may go away
-    int rc = run_steps(s, t.tape, t.offsets, d_buf);
-    cudaFreeAsync(d_buf, s->stream);
+    CK(cudaMemcpyAsync(s->d_scratch, s->h_scratch, need, cudaMemcpyHostToDevice, s->stream));
+    CK(cudaEventRecord(s->upload_done, s->stream));
+    int rc = run_steps(s, t.tape, t.offsets, s->d_scratch);
     if (rc) return rc;
     s->l2p = t.tape.l2p;
     return 0;
@@ -352,6 +383,9 @@ int qvmcuda_state_destroy(qvmcuda_state* s) {
         for (void* p : s->opened) cudaIpcCloseMemHandle(p);
         cudaFree(s->d_amps);
         cudaFree(s->d_partial);
+        if (s->d_scratch) cudaFree(s->d_scratch);
+        if (s->h_scratch) cudaFreeHost(s->h_scratch);
+        if (s->upload_done) cudaEventDestroy(s->upload_done);
         if (s->own_stream && s->stream) cudaStreamDestroy(s->stream);
         s->d_amps = nullptr;
     }

@@ -133,13 +133,22 @@ class ShardedState:
 
     def apply_gates(self, gates, fuse: bool = True, absorb_swaps: bool = False):
         tape = self.engine.compile(gates, fuse=fuse, absorb_swaps=absorb_swaps)
+        trace = os.environ.get("QVM_DIST_TRACE") and self.rank == 0
         try:
             n = self.engine.num_steps(tape)
             for i in range(n):
-                peer = self.engine.step_flags(tape, i) & STEP_PEER
+                flags = self.engine.step_flags(tape, i)
+                peer = flags & STEP_PEER
                 if peer:
                     self._barrier()       # every shard must be complete before anyone reads it remotely
+                if trace:
+                    self.engine.synchronize()
+                    t0 = time.perf_counter()
                 self.engine.run_step(tape, i)
+                if trace:
+                    self.engine.synchronize()
+                    print(f"[dist] step {i}: {'REMAP' if flags & STEP_REMAP else 'PEER' if peer else 'LOCAL'} "
+                          f"{1e3 * (time.perf_counter() - t0):.2f} ms", flush=True)
                 if peer:
                     self._barrier()       # remote writes must have landed before local work resumes
                     self.peer_steps += 1
@@ -234,7 +243,12 @@ def bench_sharded(args, rank: int, world: int, local_rank: int):
     g = _log2(world)
     n = args.qubits + g
     st = ShardedState(n, dist, device=local_rank)
-    gates = circuits.qft_circuit(range(n))
+    if getattr(args, "workload", "qft") == "random":
+        gates = circuits.random_layer_circuit(n, args.layers, seed=0)
+        wl = f"random 1q(RZ.RY.RZ)/CZ circuit, {args.layers} layers, {n} qubits (SURVEY 8d C5)"
+    else:
+        gates = circuits.qft_circuit(range(n))
+        wl = f"qft-{n}"
 
     def step():
         st.apply_gates(gates, fuse=True, absorb_swaps=False)
@@ -267,7 +281,7 @@ def bench_sharded(args, rank: int, world: int, local_rank: int):
             "metric": "gates/s", "value": value, "unit": "gates/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": f"qft-{n} sharded over {world} GPUs ({args.qubits} local qubits = {16 << args.qubits} B per GPU), gate fusion on",
+            "config": {"workload": f"{wl} sharded over {world} GPUs ({args.qubits} local qubits = {16 << args.qubits} B per GPU), gate fusion on",
                        "value_definition": f"gates/s x 2^(n-{args.qubits}): amplitude updates per second / 2^{args.qubits}; equals plain gates/s at N=1",
                        "raw_gates_per_s": len(gates) * args.steps / dt,
                        "hbm_passes_per_step": (st.steps - s0) / args.steps, "peer_passes_per_step": peer_per_step,
