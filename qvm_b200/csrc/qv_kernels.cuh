@@ -55,6 +55,7 @@ qv_tile_kernel(const __grid_constant__ PROG prog, const __grid_constant__ QvPeer
     extern __shared__ __align__(16) uint8_t qv_smem_raw[];
     qvc* tile = reinterpret_cast<qvc*>(qv_smem_raw);
     __shared__ uint32_t s_ext[QV_MAX_PASS_CHUNKS];
+    __shared__ qvc s_slice[QV_SLICE_ENTRIES];
 
     // The control program sits in the constant bank (kernel parameters): every read below is a
     // uniform constant load, matrices reach the FP64 pipe through uniform registers.
@@ -71,6 +72,7 @@ qv_tile_kernel(const __grid_constant__ PROG prog, const __grid_constant__ QvPeer
     const QvRound* rounds = reinterpret_cast<const QvRound*>(blob + h->off_rounds);
     const QvOp* ops = reinterpret_cast<const QvOp*>(blob + h->off_ops);
     const QvChunk* chunks = reinterpret_cast<const QvChunk*>(blob + h->off_chunks);
+    const QvSource* sources = reinterpret_cast<const QvSource*>(blob + h->off_sources);
     const qvc* mats = reinterpret_cast<const qvc*>(blob + h->off_matrices);
 
     const uint32_t tid = threadIdx.x;
@@ -85,6 +87,16 @@ qv_tile_kernel(const __grid_constant__ PROG prog, const __grid_constant__ QvPeer
         const uint64_t base = qv_gather(t, h->base_segs, h->n_base_segs) | fixed_bits;
         const uint64_t pbase = PEERS ? (base | glo) : ((base | glo) & local_mask);
         if (tid < n_chunks) s_ext[tid] = (uint32_t)qv_gather(base, chunks[tid].esegs, chunks[tid].n_esegs);
+        // per-tile diagonal slices: warp w builds the slices of chunks w, w+8, ... (their external bits are
+        // constant over the tile, so all sources over the same local bits collapse into one small table)
+        for (uint32_t c = tid >> 5; c < n_chunks; c += QV_THREADS / 32) {
+            const QvChunk& ch = chunks[c];
+            if (ch.kind) {
+                const uint32_t cnt = 1u << ch.nl;
+                for (uint32_t x = tid & 31; x < cnt; x += 32)
+                    s_slice[ch.table_off + x] = qv_slice_entry(ch, sources, tables, base, x);
+            }
+        }
 
         // ---- HBM -> shared memory: 16 asynchronous 16-byte copies in flight per thread
         if (FULL) {
@@ -125,7 +137,7 @@ qv_tile_kernel(const __grid_constant__ PROG prog, const __grid_constant__ QvPeer
                     if (FULL || (uint32_t)s < nslots) a[s] = tile[se0 ^ rd.slot_xor[s]];
                     else { a[s].x = 0.0; a[s].y = 0.0; }
                 }
-                qv_apply_round(a, rd, ops, chunks, mats, tables, s_ext, e0, base);
+                qv_apply_round(a, rd, ops, chunks, mats, tables, s_ext, s_slice, e0, base);
 #pragma unroll
                 for (int s = 0; s < 8; s++)
                     if (FULL || (uint32_t)s < nslots) tile[se0 ^ rd.slot_xor[s]] = a[s];

@@ -135,10 +135,12 @@ QV_HD void qv_dense2_dispatch(qvc a[8], const qvc* M, const QvRound& rd, const Q
     }
 }
 
-// The chunk is gated by register bit RB: every table entry with that bit clear is exactly 1, so only
-// the slots with the bit set are touched (controlled-phase ladders: half the multiplies and lookups).
-template <int RB>
-QV_HD void qv_diag_gated(qvc a[8], const qvc* tab, uint32_t g0, const QvChunk& ch) {
+// Table lookups of one chunk for the 8 slots of a group.  TAB is either a global-memory table or a
+// shared-memory slice (separate instantiations keep the address spaces explicit for the compiler).
+//   gated by register bit RB: every entry with that bit clear is exactly 1, so only the slots with the
+//   bit set are touched (controlled-phase ladders: half the multiplies and lookups).
+template <int RB, typename TAB>
+QV_HD void qv_diag_gated(qvc a[8], TAB tab, uint32_t g0, const QvChunk& ch) {
     if ((ch.reg_mask & (ch.reg_mask - 1)) == 0) {
         const qvc t1 = tab[g0 | ch.slot_off[1 << RB]];
 #pragma unroll
@@ -158,11 +160,34 @@ QV_HD void qv_diag_1bit(qvc a[8], qvc t0, qvc t1) {
     for (int r = 0; r < 8; r++) a[r] = qv_cmul(a[r], (r & (1 << RB)) ? t1 : t0);
 }
 
-// Merged diagonal: every amplitude is multiplied by the product of its chunk
-// table entries.  chunk_ext[c] is the part of chunk c's table index that comes
-// from the bits outside the tile (constant per tile, computed once per tile).
+template <typename TAB>
+QV_HD void qv_diag_chunk(qvc a[8], TAB tab, uint32_t g0, const QvChunk& ch, qvc& common, bool& have_common) {
+    const uint32_t rm = ch.reg_mask;
+    if (rm == 0) {
+        // no register bit: one factor for the whole group
+        common = have_common ? qv_cmul(common, tab[g0]) : tab[g0];
+        have_common = true;
+    } else if (ch.gate_rb) {
+        if (ch.gate_rb == 1) qv_diag_gated<0>(a, tab, g0, ch);
+        else if (ch.gate_rb == 2) qv_diag_gated<1>(a, tab, g0, ch);
+        else qv_diag_gated<2>(a, tab, g0, ch);
+    } else if ((rm & (rm - 1)) == 0) {
+        const qvc t0 = tab[g0];
+        if (rm == 1) qv_diag_1bit<0>(a, t0, tab[g0 | ch.slot_off[1]]);
+        else if (rm == 2) qv_diag_1bit<1>(a, t0, tab[g0 | ch.slot_off[2]]);
+        else qv_diag_1bit<2>(a, t0, tab[g0 | ch.slot_off[4]]);
+    } else {
+#pragma unroll
+        for (int r = 0; r < 8; r++) a[r] = qv_cmul(a[r], tab[g0 | ch.slot_off[r]]);
+    }
+}
+
+// Merged diagonal: every amplitude is multiplied by the product of its chunk table entries.
+//   chunk_ext[c] : the part of a GLOBAL chunk's table index that comes from the bits outside the tile
+//                  (constant per tile, computed once per tile);
+//   slices       : the per-tile slice area (SLICE chunks), built once per tile by qv_build_slices.
 QV_HD void qv_diag(qvc a[8], const QvOp& op, const QvChunk* chunks, const qvc* tables, const uint32_t* chunk_ext,
-                   uint32_t e0) {
+                   const qvc* slices, uint32_t e0) {
     qvc common;
     common.x = 1.0;
     common.y = 0.0;
@@ -170,26 +195,9 @@ QV_HD void qv_diag(qvc a[8], const QvOp& op, const QvChunk* chunks, const qvc* t
     for (uint32_t c = 0; c < op.n_chunks; c++) {
         const uint32_t ci = op.data_off + c;
         const QvChunk& ch = chunks[ci];
-        const uint32_t g0 = chunk_ext[ci] | qv_gather32(e0, ch.lsegs, ch.n_lsegs);
-        const qvc* tab = tables + ch.table_off;
-        const uint32_t rm = ch.reg_mask;
-        if (rm == 0) {
-            // no register bit: one factor for the whole group
-            common = have_common ? qv_cmul(common, tab[g0]) : tab[g0];
-            have_common = true;
-        } else if (ch.gate_rb) {
-            if (ch.gate_rb == 1) qv_diag_gated<0>(a, tab, g0, ch);
-            else if (ch.gate_rb == 2) qv_diag_gated<1>(a, tab, g0, ch);
-            else qv_diag_gated<2>(a, tab, g0, ch);
-        } else if ((rm & (rm - 1)) == 0) {
-            const qvc t0 = tab[g0];
-            if (rm == 1) qv_diag_1bit<0>(a, t0, tab[g0 | ch.slot_off[1]]);
-            else if (rm == 2) qv_diag_1bit<1>(a, t0, tab[g0 | ch.slot_off[2]]);
-            else qv_diag_1bit<2>(a, t0, tab[g0 | ch.slot_off[4]]);
-        } else {
-#pragma unroll
-            for (int r = 0; r < 8; r++) a[r] = qv_cmul(a[r], tab[g0 | ch.slot_off[r]]);
-        }
+        const uint32_t gl = qv_gather32(e0, ch.lsegs, ch.n_lsegs);
+        if (ch.kind) qv_diag_chunk(a, slices + ch.table_off, gl, ch, common, have_common);
+        else qv_diag_chunk(a, tables + ch.table_off, chunk_ext[ci] | gl, ch, common, have_common);
     }
     if (have_common) {
 #pragma unroll
@@ -197,10 +205,24 @@ QV_HD void qv_diag(qvc a[8], const QvOp& op, const QvChunk* chunks, const qvc* t
     }
 }
 
+// Entry x of SLICE chunk ch for the tile whose base index is `base`: the product of its sources.
+QV_HD qvc qv_slice_entry(const QvChunk& ch, const QvSource* sources, const qvc* tables, uint64_t base, uint32_t x) {
+    qvc prod;
+    prod.x = 1.0;
+    prod.y = 0.0;
+    for (uint32_t s = 0; s < ch.n_src; s++) {
+        const QvSource& src = sources[ch.first_src + s];
+        const uint32_t ext = (uint32_t)qv_gather(base, src.esegs, src.n_esegs);
+        const qvc t = tables[src.table_off + ((ext << ch.nl) | x)];
+        prod = s ? qv_cmul(prod, t) : t;
+    }
+    return prod;
+}
+
 // Apply every op of a round to one register group.
 QV_HD void qv_apply_round(qvc a[8], const QvRound& rd, const QvOp* ops, const QvChunk* chunks,
-                          const qvc* mats, const qvc* tables, const uint32_t* chunk_ext, uint32_t e0,
-                          uint64_t base) {
+                          const qvc* mats, const qvc* tables, const uint32_t* chunk_ext, const qvc* slices,
+                          uint32_t e0, uint64_t base) {
     for (uint32_t i = 0; i < rd.n_ops; i++) {
         const QvOp& op = ops[rd.first_op + i];
         if ((op.flags & QV_F_CTRL_EXT) && ((base & op.cm_ext) != op.cv_ext)) continue;
@@ -228,7 +250,7 @@ QV_HD void qv_apply_round(qvc a[8], const QvRound& rd, const QvOp* ops, const Qv
                 default: qv_dense2_dispatch<1, 2>(a, M, rd, op, e0); break;
             }
         } else {
-            qv_diag(a, op, chunks, tables, chunk_ext, e0);
+            qv_diag(a, op, chunks, tables, chunk_ext, slices, e0);
         }
     }
 }

@@ -25,6 +25,7 @@
 #define QV_THREADS 256
 #define QV_MAX_PEERS 8
 #define QV_MAX_PASS_CHUNKS 256   // per-tile chunk offsets are staged in shared memory
+#define QV_SLICE_ENTRIES 544     // per-tile diagonal slices staged in shared memory (8.5 KiB; 3 CTAs/SM still fit)
 // The control part of a pass (header, rounds, ops, chunk descriptors, matrices) is handed to the
 // kernel as a __grid_constant__ parameter: it lives in the constant bank, so ptxas reads matrices
 // through uniform registers instead of spending vector registers on them.  Two size classes.
@@ -48,7 +49,18 @@ struct QvSeg {
     uint8_t src, len, dst, pad;
 };
 
-// One factor of a merged diagonal: phase = table[gather_local(e) | gather_ext(base)]
+// One source table of a SLICE chunk: index = (gather_ext(base) << nl) | local_index.
+struct QvSource {
+    uint32_t table_off;             // offset in complex entries into the pass's table pool
+    uint8_t n_esegs, pad[3];
+    QvSeg esegs[QV_CHUNK_SEGS];
+};
+
+// One factor of a merged diagonal.
+//   kind 0 (GLOBAL): phase = table[gather_local(e) | gather_ext(base)], table in global memory.
+//   kind 1 (SLICE) : all source tables over the same tile-local bits are multiplied together ONCE PER
+//                    TILE (their external bits are constant there) into a 2^nl-entry slice in shared
+//                    memory; phase = slice[gather_local(e)].
 struct QvChunk {
     uint32_t table_off;             // offset in complex entries into the pass's table pool
     uint8_t n_lsegs, n_esegs;       // fields gathered from the tile-local index / the tile base
@@ -57,6 +69,9 @@ struct QvChunk {
     QvSeg lsegs[QV_CHUNK_SEGS];     // only the NON-register local bits (register bits go through slot_off)
     QvSeg esegs[QV_CHUNK_SEGS];
     uint32_t slot_off[8];           // table-index contribution of register slot r (host-precomputed)
+    uint16_t kind;                  // 0 = GLOBAL, 1 = SLICE (table_off then counts entries into the slice area)
+    uint16_t nl;                    // SLICE: log2(entries)
+    uint16_t first_src, n_src;      // SLICE: its sources
 };
 
 struct QvOp {
@@ -95,7 +110,7 @@ struct QvPassHeader {
     uint32_t n_chunks;
     // byte offsets from the start of the control blob (the diagonal tables travel separately,
     // in global memory)
-    uint32_t off_rounds, off_ops, off_chunks, off_matrices, n_table_entries;
+    uint32_t off_rounds, off_ops, off_chunks, off_sources, off_matrices, n_table_entries, n_sources, n_slice_entries;
     uint32_t blob_bytes;
     uint32_t uses_peers;            // tile bits include a physical bit >= n_local_bits
     uint32_t pad;

@@ -13,6 +13,8 @@
 #include "qv_sched.h"
 
 #include <algorithm>
+#include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <sstream>
 #include <stdexcept>
@@ -188,15 +190,45 @@ void chunk_extend(Chunk& c, const std::vector<int>& newbits) {
     c.table.swap(nt);
 }
 
-std::vector<Chunk> build_chunks(const std::vector<DiagFactor>& factors) {
+// Physical bits b of a factor such that every entry with bit b clear is exactly 1 (controlled phases:
+// CPHASE/CZ are gated by both of their qubits, T / PHASE by their only qubit, RZ by none).
+uint64_t gating_bits(const DiagFactor& f) {
+    uint64_t g = 0;
+    for (size_t j = 0; j < f.pos.size(); j++) {
+        bool all_one = true;
+        for (size_t t = 0; t < f.diag.size() && all_one; t++)
+            if (!(t >> j & 1) && f.diag[t] != cd(1.0, 0.0)) all_one = false;
+        if (all_one) g |= 1ull << f.pos[j];
+    }
+    return g;
+}
+
+// Merge the factors of one diagonal group into chunk tables of <= QV_MAX_CHUNK_BITS bits.  Factors that
+// are gated by the same REGISTER bit of the round (reg_phys) are kept together, so that the whole chunk
+// stays gated by it and the kernel only touches the slots where that bit is set.
+std::vector<Chunk> build_chunks(const std::vector<DiagFactor>& factors, uint64_t reg_phys) {
     std::vector<Chunk> chunks;
-    for (const DiagFactor& f : factors) {
+    std::vector<int> chunk_gate;      // physical gate bit of the chunk or -1
+    std::vector<uint64_t> gates(factors.size());
+    int cnt[64] = {0};
+    for (size_t i = 0; i < factors.size(); i++) {
+        gates[i] = gating_bits(factors[i]) & reg_phys;
+        for (int b = 0; b < 64; b++)
+            if (gates[i] >> b & 1) cnt[b]++;
+    }
+    for (size_t fi = 0; fi < factors.size(); fi++) {
+        const DiagFactor& f = factors[fi];
         std::vector<int> fb = f.pos;
         std::sort(fb.begin(), fb.end());
+        // preferred gate: the candidate register bit shared by most factors of the group
+        int want_gate = -1;
+        for (int b = 0; b < 64; b++)
+            if ((gates[fi] >> b & 1) && (want_gate < 0 || cnt[b] > cnt[want_gate])) want_gate = b;
         int best = -1;
         size_t best_size = 1000;
         std::vector<int> best_union;
         for (size_t ci = 0; ci < chunks.size(); ci++) {
+            if (chunk_gate[ci] != want_gate) continue;
             std::vector<int> u;
             std::set_union(chunks[ci].bits.begin(), chunks[ci].bits.end(), fb.begin(), fb.end(), std::back_inserter(u));
             if (u.size() > QV_MAX_CHUNK_BITS) continue;
@@ -211,6 +243,7 @@ std::vector<Chunk> build_chunks(const std::vector<DiagFactor>& factors) {
             c.bits = fb;
             c.table.assign((size_t)1 << fb.size(), cd(1.0, 0.0));
             chunks.push_back(std::move(c));
+            chunk_gate.push_back(want_gate);
             best = (int)chunks.size() - 1;
         } else if (best_union.size() != chunks[best].bits.size()) {
             chunk_extend(chunks[best], best_union);
@@ -232,8 +265,10 @@ struct BlobWriter {
     std::vector<QvRound> rounds;
     std::vector<QvOp> ops;
     std::vector<QvChunk> chunks;
+    std::vector<QvSource> sources;
     std::vector<cd> mats;
     std::vector<cd> tables;
+    size_t slice_entries = 0;
 };
 
 struct Layout {
@@ -302,13 +337,53 @@ void emit_round(BlobWriter& w, const std::vector<RoundOp>& rops, const std::vect
             w.mats.insert(w.mats.end(), mat.begin(), mat.end());
         } else {
             op.type = QV_OP_DIAG;
-            std::vector<Chunk> chunks = build_chunks(ro.factors);
+            uint64_t reg_phys = 0;
+            for (int lp : regpos_local) reg_phys |= 1ull << tm.tilebits[lp];
             op.data_off = (uint32_t)w.chunks.size();
-            op.n_chunks = (uint32_t)chunks.size();
-            for (const Chunk& c : chunks) {
+
+            // How the tile-local bits `lbits` (index bit i <-> lbits[i]) reach a table / slice index:
+            // register bits through slot_off, the others through lsegs.
+            auto map_local = [&](QvChunk& qc, const std::vector<int>& lbits) {
+                std::vector<int> lsrc, ldst;
+                for (size_t i = 0; i < lbits.size(); i++) {
+                    const int lp = tm.local_of[lbits[i]];
+                    bool is_reg = false;
+                    for (size_t r = 0; r < regpos_local.size(); r++)
+                        if (regpos_local[r] == lp) {
+                            qc.reg_mask |= (uint8_t)(1u << r);
+                            for (uint32_t sl = 0; sl < 8; sl++)
+                                if (sl >> r & 1) qc.slot_off[sl] |= 1u << i;
+                            is_reg = true;
+                        }
+                    if (is_reg) continue;
+                    lsrc.push_back(lp);
+                    ldst.push_back((int)i);
+                }
+                std::vector<QvSeg> ls = make_segs(lsrc, ldst);
+                if (ls.size() > QV_CHUNK_SEGS) throw std::runtime_error("scheduler bug: chunk needs too many segments");
+                qc.n_lsegs = (uint8_t)ls.size();
+                std::copy(ls.begin(), ls.end(), qc.lsegs);
+            };
+            // A chunk is gated by register bit r when every table entry with that bit clear is exactly 1.
+            auto detect_gate = [&](QvChunk& qc, const std::vector<const Chunk*>& tabs) {
+                for (size_t r = 0; r < regpos_local.size() && !qc.gate_rb; r++) {
+                    if (!(qc.reg_mask >> r & 1)) continue;
+                    bool all_one = true;
+                    for (const Chunk* c : tabs) {
+                        size_t ibit = 0;
+                        for (size_t i = 0; i < c->bits.size(); i++)
+                            if (tm.local_of[c->bits[i]] == regpos_local[r]) ibit = i;
+                        for (size_t t = 0; t < c->table.size() && all_one; t++)
+                            if (!(t >> ibit & 1) && c->table[t] != cd(1.0, 0.0)) all_one = false;
+                    }
+                    if (all_one) qc.gate_rb = (uint8_t)(r + 1);
+                }
+            };
+            auto emit_global = [&](const Chunk& c) {
                 QvChunk qc{};
                 qc.table_off = (uint32_t)w.tables.size();
                 w.tables.insert(w.tables.end(), c.table.begin(), c.table.end());
+                // table index bit i <-> c.bits[i] (ascending physical); local and external bits interleave
                 std::vector<int> lsrc, ldst, esrc, edst;
                 for (size_t i = 0; i < c.bits.size(); i++) {
                     const int b = c.bits[i];
@@ -321,7 +396,7 @@ void emit_round(BlobWriter& w, const std::vector<RoundOp>& rops, const std::vect
                                     if (sl >> r & 1) qc.slot_off[sl] |= 1u << i;
                                 is_reg = true;
                             }
-                        if (is_reg) continue;    // register bits reach the table index through slot_off
+                        if (is_reg) continue;
                         lsrc.push_back(tm.local_of[b]);
                         ldst.push_back((int)i);
                     } else {
@@ -329,17 +404,7 @@ void emit_round(BlobWriter& w, const std::vector<RoundOp>& rops, const std::vect
                         edst.push_back((int)i);
                     }
                 }
-                // gated chunk: some register bit whose clear half of the table is exactly 1
-                for (size_t r = 0; r < regpos_local.size() && !qc.gate_rb; r++) {
-                    if (!(qc.reg_mask >> r & 1)) continue;
-                    size_t ibit = 0;
-                    for (size_t i = 0; i < c.bits.size(); i++)
-                        if (tm.local_of[c.bits[i]] == regpos_local[r]) ibit = i;
-                    bool all_one = true;
-                    for (size_t t = 0; t < c.table.size() && all_one; t++)
-                        if (!(t >> ibit & 1) && c.table[t] != cd(1.0, 0.0)) all_one = false;
-                    if (all_one) qc.gate_rb = (uint8_t)(r + 1);
-                }
+                detect_gate(qc, {&c});
                 std::vector<QvSeg> ls = make_segs(lsrc, ldst), es = make_segs(esrc, edst);
                 if (ls.size() > QV_CHUNK_SEGS || es.size() > QV_CHUNK_SEGS)
                     throw std::runtime_error("scheduler bug: chunk needs too many segments");
@@ -348,6 +413,118 @@ void emit_round(BlobWriter& w, const std::vector<RoundOp>& rops, const std::vect
                 std::copy(ls.begin(), ls.end(), qc.lsegs);
                 std::copy(es.begin(), es.end(), qc.esegs);
                 w.chunks.push_back(qc);
+            };
+            // SLICE chunk over the local bits `lbits` whose sources are `srcs` (bits = lbits then external bits)
+            auto emit_slice = [&](const std::vector<int>& lbits, const std::vector<Chunk>& srcs) {
+                QvChunk qc{};
+                qc.kind = 1;
+                qc.nl = (uint16_t)lbits.size();
+                qc.table_off = (uint32_t)w.slice_entries;
+                w.slice_entries += (size_t)1 << lbits.size();
+                qc.first_src = (uint16_t)w.sources.size();
+                qc.n_src = (uint16_t)srcs.size();
+                map_local(qc, lbits);
+                std::vector<const Chunk*> tabs;
+                for (const Chunk& c : srcs) {
+                    tabs.push_back(&c);
+                    QvSource src{};
+                    src.table_off = (uint32_t)w.tables.size();
+                    w.tables.insert(w.tables.end(), c.table.begin(), c.table.end());
+                    std::vector<int> esrc, edst;
+                    for (size_t i = lbits.size(); i < c.bits.size(); i++) {
+                        esrc.push_back(c.bits[i]);
+                        edst.push_back((int)(i - lbits.size()));
+                    }
+                    std::vector<QvSeg> es = make_segs(esrc, edst);
+                    if (es.size() > QV_CHUNK_SEGS) throw std::runtime_error("scheduler bug: source needs too many segments");
+                    src.n_esegs = (uint8_t)es.size();
+                    std::copy(es.begin(), es.end(), src.esegs);
+                    w.sources.push_back(src);
+                }
+                detect_gate(qc, tabs);
+                w.chunks.push_back(qc);
+            };
+
+            // 1. split the factors: purely tile-local ones, ones with external bits and few local bits
+            //    (grouped by their exact local bit set), and the rest.
+            std::vector<DiagFactor> local_pool, global_pool;
+            std::vector<std::pair<std::vector<int>, std::vector<DiagFactor>>> ext_groups;
+            for (const DiagFactor& f : ro.factors) {
+                std::vector<int> L, E;
+                for (int b : f.pos) (tm.local_of[b] >= 0 ? L : E).push_back(b);
+                std::sort(L.begin(), L.end());
+                if (E.empty()) local_pool.push_back(f);
+                else if (L.size() <= 3) {
+                    size_t gi = 0;
+                    while (gi < ext_groups.size() && ext_groups[gi].first != L) gi++;
+                    if (gi == ext_groups.size()) ext_groups.push_back({L, {}});
+                    ext_groups[gi].second.push_back(f);
+                } else global_pool.push_back(f);
+            }
+            // 2. external groups -> one SLICE each: all their tables collapse per tile into 2^|L| entries
+            for (auto& grp : ext_groups) {
+                const std::vector<int>& L = grp.first;
+                if (w.slice_entries + ((size_t)1 << L.size()) > QV_SLICE_ENTRIES ||
+                    w.sources.size() + grp.second.size() > 60000) {
+                    global_pool.insert(global_pool.end(), grp.second.begin(), grp.second.end());
+                    continue;
+                }
+                const size_t cap_ext = 10 - L.size();
+                std::vector<Chunk> srcs;
+                std::vector<std::vector<int>> src_ext;
+                for (const DiagFactor& f : grp.second) {
+                    std::vector<int> fe;
+                    for (int b : f.pos)
+                        if (tm.local_of[b] < 0) fe.push_back(b);
+                    std::sort(fe.begin(), fe.end());
+                    int best = -1;
+                    size_t best_size = 1000;
+                    std::vector<int> best_union;
+                    for (size_t si = 0; si < srcs.size(); si++) {
+                        std::vector<int> u;
+                        std::set_union(src_ext[si].begin(), src_ext[si].end(), fe.begin(), fe.end(), std::back_inserter(u));
+                        if (u.size() > cap_ext) continue;
+                        if (u.size() < best_size) {
+                            best_size = u.size();
+                            best = (int)si;
+                            best_union.swap(u);
+                        }
+                    }
+                    if (best < 0) {
+                        Chunk c;
+                        c.bits = L;
+                        c.bits.insert(c.bits.end(), fe.begin(), fe.end());
+                        c.table.assign((size_t)1 << c.bits.size(), cd(1.0, 0.0));
+                        srcs.push_back(std::move(c));
+                        src_ext.push_back(fe);
+                        best = (int)srcs.size() - 1;
+                    } else if (best_union.size() != src_ext[best].size()) {
+                        std::vector<int> nb = L;
+                        nb.insert(nb.end(), best_union.begin(), best_union.end());
+                        chunk_extend(srcs[best], nb);
+                        src_ext[best] = best_union;
+                    }
+                    chunk_multiply(srcs[best], f);
+                }
+                emit_slice(L, srcs);
+            }
+            // 3. tile-local factors -> chunks of <= 8 bits; small ones are staged as slices (shared-memory
+            //    lookups), big ones stay in global memory (L1-resident) so the slice area is kept for the
+            //    external groups, where the per-tile collapse saves whole lookups
+            for (const Chunk& c : build_chunks(local_pool, reg_phys)) {
+                if (c.table.size() <= 16 && w.slice_entries + c.table.size() <= QV_SLICE_ENTRIES) emit_slice(c.bits, {c});
+                else emit_global(c);
+            }
+            // 4. everything else: tables in global memory, indexed by local and external bits
+            for (const Chunk& c : build_chunks(global_pool, reg_phys)) emit_global(c);
+            op.n_chunks = (uint32_t)w.chunks.size() - op.data_off;
+            if (getenv("QV_SCHED_DEBUG")) {
+                fprintf(stderr, "  DIAG op: %zu factors (%zu local, %zu ext groups, %zu global) -> %u chunks:", ro.factors.size(),
+                        local_pool.size(), ext_groups.size(), global_pool.size(), op.n_chunks);
+                for (uint32_t c = op.data_off; c < w.chunks.size(); c++)
+                    fprintf(stderr, " [%s nl=%u rm=%u gate=%u src=%u]", w.chunks[c].kind ? "S" : "G", w.chunks[c].nl,
+                            w.chunks[c].reg_mask, w.chunks[c].gate_rb, w.chunks[c].n_src);
+                fprintf(stderr, "\n");
             }
         }
         w.ops.push_back(op);
@@ -514,6 +691,10 @@ Step build_tile_step(const std::vector<const Atom*>& atoms, uint64_t tile_target
     off = align16(off + w.ops.size() * sizeof(QvOp));
     h.off_chunks = (uint32_t)off;
     off = align16(off + w.chunks.size() * sizeof(QvChunk));
+    h.off_sources = (uint32_t)off;
+    off = align16(off + w.sources.size() * sizeof(QvSource));
+    h.n_sources = (uint32_t)w.sources.size();
+    h.n_slice_entries = (uint32_t)w.slice_entries;
     h.off_matrices = (uint32_t)off;
     off = align16(off + w.mats.size() * sizeof(cd));
     h.n_table_entries = (uint32_t)w.tables.size();
@@ -529,6 +710,7 @@ Step build_tile_step(const std::vector<const Atom*>& atoms, uint64_t tile_target
     if (!w.rounds.empty()) std::memcpy(st.blob.data() + h.off_rounds, w.rounds.data(), w.rounds.size() * sizeof(QvRound));
     if (!w.ops.empty()) std::memcpy(st.blob.data() + h.off_ops, w.ops.data(), w.ops.size() * sizeof(QvOp));
     if (!w.chunks.empty()) std::memcpy(st.blob.data() + h.off_chunks, w.chunks.data(), w.chunks.size() * sizeof(QvChunk));
+    if (!w.sources.empty()) std::memcpy(st.blob.data() + h.off_sources, w.sources.data(), w.sources.size() * sizeof(QvSource));
     if (!w.mats.empty()) std::memcpy(st.blob.data() + h.off_matrices, w.mats.data(), w.mats.size() * sizeof(cd));
     st.tables = std::move(w.tables);
     st.n_gates = (int)atoms.size();
@@ -805,7 +987,7 @@ std::string describe(const Tape& t) {
         QvPassHeader h;
         std::memcpy(&h, s.blob.data(), sizeof(h));
         os << "  [" << i << "] " << (s.is_remap ? "REMAP" : (s.uses_peers ? "PEER" : "TILE")) << " T=" << h.T
-           << " atoms=" << s.n_gates << " rounds=" << h.n_rounds << " ops=" << h.n_ops << " chunks=" << h.n_chunks
+           << " atoms=" << s.n_gates << " rounds=" << h.n_rounds << " ops=" << h.n_ops << " chunks=" << h.n_chunks << " sources=" << h.n_sources << " slice_entries=" << h.n_slice_entries
            << " bytes=" << h.blob_bytes << " tables=" << h.n_table_entries << " tilebits=";
         for (uint32_t k = 0; k < h.n_tile_segs; k++)
             os << (int)h.tile_segs[k].dst << "+" << (int)h.tile_segs[k].len << (k + 1 < h.n_tile_segs ? "," : "");

@@ -23,16 +23,22 @@ void run_tile_step(qvc* const* peers, const qv::Step& st) {
     const QvRound* rounds = (const QvRound*)(blob + h.off_rounds);
     const QvOp* ops = (const QvOp*)(blob + h.off_ops);
     const QvChunk* chunks = (const QvChunk*)(blob + h.off_chunks);
+    const QvSource* sources = (const QvSource*)(blob + h.off_sources);
     const qvc* mats = (const qvc*)(blob + h.off_matrices);
     const qvc* tables = (const qvc*)st.tables.data();
     const uint32_t tile_n = 1u << h.T;
     const uint64_t local_mask = (1ull << h.n_local_bits) - 1ull;
     std::vector<qvc> smem(tile_n);
     std::vector<uint32_t> ext(h.n_chunks ? h.n_chunks : 1);
+    std::vector<qvc> slices(QV_SLICE_ENTRIES);
     auto addr = [&](uint64_t p) { return peers[p >> h.n_local_bits] + (p & local_mask); };
     for (uint64_t tile = 0; tile < h.n_tiles; tile++) {
         const uint64_t base = qv_gather(tile, h.base_segs, h.n_base_segs) | h.fixed_bits;
         for (uint32_t c = 0; c < h.n_chunks; c++) ext[c] = (uint32_t)qv_gather(base, chunks[c].esegs, chunks[c].n_esegs);
+        for (uint32_t c = 0; c < h.n_chunks; c++)
+            if (chunks[c].kind)
+                for (uint32_t x = 0; x < (1u << chunks[c].nl); x++)
+                    slices[chunks[c].table_off + x] = qv_slice_entry(chunks[c], sources, tables, base, x);
         for (uint32_t e = 0; e < tile_n; e++) {
             const uint64_t p = base | qv_gather(e & (QV_THREADS - 1), h.tile_segs, h.n_tile_segs) | h.hi_off[e / QV_THREADS];
             smem[qv_swz(e)] = *addr(p);
@@ -49,7 +55,7 @@ void run_tile_step(qvc* const* peers, const qv::Step& st) {
                     if (s < (1u << rd.m)) a[s] = smem[se0 ^ rd.slot_xor[s]];
                     else { a[s].x = 0.0; a[s].y = 0.0; }
                 }
-                qv_apply_round(a, rd, ops, chunks, mats, tables, ext.data(), e0, base);
+                qv_apply_round(a, rd, ops, chunks, mats, tables, ext.data(), slices.data(), e0, base);
                 for (uint32_t s = 0; s < (1u << rd.m); s++) smem[se0 ^ rd.slot_xor[s]] = a[s];
             }
         }
