@@ -41,6 +41,15 @@ def measured_peaks():
     return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
 
 
+def measured_traffic():
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed ncu --set full capture."""
+    path = os.path.join(ROOT, "profiles", "r01_traffic.json")
+    try:
+        return json.load(open(path))
+    except Exception:
+        return {}
+
+
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
@@ -199,9 +208,13 @@ def run_ours(args):
     clk = clocks.stop()
     value = len(gates) * args.steps / dt
     pass_s = dt / (args.steps * info["passes"])
+    traffic = measured_traffic()
+    scale = (1 << n) / float(1 << 30)          # the ncu capture is at 30 qubits; DRAM bytes scale with the state
     roofline = {"bound": "hbm", "achieved": bytes_per_pass / pass_s / 1e9, "peak": peak, "unit": "GB/s",
-                "frac": bytes_per_pass / pass_s / 1e9 / peak, "traffic": None,
-                "kernel": "qv_tile_kernel (fused passes)", "peak_source": peak_src,
+                "frac": bytes_per_pass / pass_s / 1e9 / peak,
+                "traffic": traffic.get("fused_pass_dram_bytes", 0) * scale or None,
+                "kernel": "qv_tile_kernel, fused passes of the timed region (27-212 gates per launch: issue-bound, see profiles/r01_e_slices.md)",
+                "peak_source": peak_src, "traffic_source": traffic.get("source"),
                 "bytes_per_launch": bytes_per_pass, "launches_per_step": info["passes"]}
 
     # ---- unfused: every gate its own HBM pass (bounded sample of the same circuit)
@@ -212,6 +225,12 @@ def run_ours(args):
     unfused = {"gates_per_s": len(sample) / dtu, "hbm_gbs": bytes_per_pass / pass_u / 1e9,
                "frac_of_peak": bytes_per_pass / pass_u / 1e9 / peak, "ms_per_gate_pass": 1e3 * pass_u,
                "sample": f"first {len(sample)} gates of the circuit, one tile-kernel launch per gate"}
+    # the same kernel with ONE 1q/2q gate per launch: the HBM-bound case BASELINE.json's 70 % target is about
+    roofline_unfused = {"bound": "hbm", "achieved": unfused["hbm_gbs"], "peak": peak, "unit": "GB/s",
+                        "frac": unfused["frac_of_peak"],
+                        "traffic": traffic.get("single_gate_pass_dram_bytes", 0) * scale or None,
+                        "kernel": "qv_tile_kernel, one gate per launch (gate fusion off)", "peak_source": peak_src,
+                        "bytes_per_launch": bytes_per_pass, "launches": tape_u.info()["passes"]}
 
     # ---- e2e: through the public API with host buffers: reset, program (host arrays) -> device, run,
     #      10^3-shot sample + one probability back to the host.
@@ -250,7 +269,7 @@ def run_ours(args):
         "config": {"workload": f"qft-{n} (examples/qft.lisp qft-circuit, {len(gates)} gates), PURE-STATE-QVM, complex double, gate fusion on",
                    "state_bytes": 16 << n, "l2_policy": "state (16 GiB at 30 qubits) is far larger than the 126 MB L2; no flush needed",
                    "hbm_passes_per_step": info["passes"]},
-        "roofline": roofline, "unfused": unfused, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches),
+        "roofline": roofline, "roofline_unfused": roofline_unfused, "unfused": unfused, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches),
         "clocks": clk,
     }))
 
