@@ -66,6 +66,7 @@ def lib():
         L.orc_density_force_measurement.restype = None; L.orc_density_force_measurement.argtypes = [vp, i32, i32, i32, dbl]
         L.orc_density_measure_discard.restype = None; L.orc_density_measure_discard.argtypes = [vp, i32, i32]
         L.orc_density_diag_probs.restype = None; L.orc_density_diag_probs.argtypes = [vp, i32, vp]
+        L.orc_evolve_stochastic.restype = i32; L.orc_evolve_stochastic.argtypes = [vp, u64, i32, vp, i32, vp, dbl]
         L.orc_sample_tree.restype = None; L.orc_sample_tree.argtypes = [vp, u64, vp, u64, i32, vp]
         _lib = L
     return _lib
@@ -212,6 +213,13 @@ def density_diag_probs(rho, n):
     out = np.empty(1 << n, dtype=np.float64)
     lib().orc_density_diag_probs(_p(_state(rho)), n, _p(out))
     return out
+
+
+def evolve_stochastic(psi, kraus, qubits, r):
+    """%EVOLVE-PURE-STATE-STOCHASTICALLY (src/apply-gate.lisp:16-39) with draw r; returns the operator index."""
+    q = _nt(qubits)
+    ks = np.ascontiguousarray(np.stack([_mat(k, len(q)) for k in kraus]))
+    return int(lib().orc_evolve_stochastic(_p(_state(psi)), psi.size, len(q), _p(q), len(kraus), _p(ks), r))
 
 
 def max_threads() -> int:

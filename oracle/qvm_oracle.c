@@ -527,3 +527,24 @@ void orc_sample_tree(const double *psi_, uint64_t n_amps, const double *u, uint6
     }
     free(l1); free(l2); free(top);
 }
+
+/* %EVOLVE-PURE-STATE-STOCHASTICALLY src/apply-gate.lisp:16-39 with the uniform draw r supplied by the
+ * caller: for j = 0..m-1: trial <- psi; trial <- K_j trial; summed += |trial|^2; stop when summed >= r;
+ * then psi <- trial and NORMALIZE-WAVEFUNCTION.  Returns the index of the Kraus operator applied. */
+int orc_evolve_stochastic(double *psi_, uint64_t n_amps, int k, const int *qubits, int m, const double *kraus, double r) {
+    uint64_t d = 1ULL << k;
+    cplx *trial = (cplx *)malloc(sizeof(cplx) * n_amps);
+    double summed = 0.0;
+    int j = 0;
+    for (j = 0; j < m; j++) {
+        memcpy(trial, psi_, sizeof(cplx) * n_amps);
+        orc_apply_matrix((double *)trial, n_amps, k, qubits, kraus + 2 * d * d * (uint64_t)j);
+        summed += orc_norm2((const double *)trial, n_amps);
+        if (summed >= r) break;
+    }
+    if (j == m) j = m - 1;
+    memcpy(psi_, trial, sizeof(cplx) * n_amps);
+    free(trial);
+    orc_normalize(psi_, n_amps);
+    return j;
+}

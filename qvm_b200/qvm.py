@@ -174,6 +174,7 @@ class PureState:
         self.num_qubits = num_qubits
         self.vec = DeviceVector(1 << num_qubits, device)
         self.vec.set_zero_state()           # (setf (aref amplitudes 0) 1), :92-95
+        self.trial = None                   # TRIAL-AMPLITUDES, allocated on first noisy gate
 
     def state_elements(self) -> np.ndarray: return self.vec.download()
     def set_state_elements(self, amps): self.vec.upload(amps)
@@ -231,11 +232,31 @@ def apply_gate_to_state(gate, state, qubits: Sequence[int]) -> None:
     matrices (a KRAUS-LIST superoperator).  QUBITS in Quil argument order."""
     if isinstance(state, PureState):
         if isinstance(gate, (list, tuple)):
-            raise NotImplementedError("stochastic Kraus evolution of pure states is a 'next' row (SURVEY.md 8f #2)")
+            raise ValueError("a Kraus list on a pure state needs a uniform draw: use evolve_pure_state_stochastically")
         state.vec.apply_matrix(gate, qubits)
     else:
         kraus = list(gate) if isinstance(gate, (list, tuple)) else [gate]
         state.vec.density_apply_kraus(state.num_qubits, kraus, qubits)
+
+
+def evolve_pure_state_stochastically(kraus_map, state: "PureState", qubits: Sequence[int], r: float) -> int:
+    """%EVOLVE-PURE-STATE-STOCHASTICALLY (src/apply-gate.lisp:16-39): pick Kraus operator j with probability
+    <psi|K_j^dagger K_j|psi> by inverse-transform sampling with the host-drawn uniform r, lazily: every
+    candidate is applied to a scratch copy (the TRIAL-AMPLITUDES of src/state-representation.lisp:63-70) and
+    its squared norm accumulated until the sum reaches r; the trial then becomes the state and is normalised.
+    Returns the index of the operator applied."""
+    if state.trial is None:                      # CHECK-ALLOCATE-COMPUTATION-SPACE :104-115
+        state.trial = DeviceVector(state.vec.length, state.vec.device)
+    summed, j = 0.0, 0
+    for j, k in enumerate(kraus_map):
+        state.trial.copy_from(state.vec)
+        state.trial.apply_matrix(k, qubits)
+        summed += state.trial.norm2()
+        if summed >= r:
+            break
+    state.vec, state.trial = state.trial, state.vec          # (rotatef amplitudes trial-amplitudes)
+    state.vec.normalize()
+    return j
 
 
 # ---------------------------------------------------------------------------- machines
@@ -282,6 +303,13 @@ class PureStateQVM(BaseQVM):
     def __init__(self, num_qubits: int, device: int = 0, seed: Optional[int] = None):
         super().__init__(seed)
         self.state = PureState(num_qubits, device)
+        self.superoperator_definitions: Dict[Tuple[str, Tuple[int, ...]], list] = {}
+
+    def set_superoperator(self, name: str, qubits: Sequence[int], kraus) -> None:
+        """SET-SUPEROPERATOR: replace gate NAME on QUBITS by a Kraus map, applied stochastically
+        (src/transition.lisp:155-180, tests/state-representation-tests.lisp:55-66)."""
+        G.check_kraus_ops(list(kraus))
+        self.superoperator_definitions[(name, tuple(qubits))] = list(kraus)
 
     # qvm::amplitudes / (setf qvm::amplitudes) : the device<->host sync points
     @property
@@ -338,12 +366,22 @@ class PureStateQVM(BaseQVM):
                 if compiled:
                     # COMPILE-LOADED-PROGRAM: a maximal run of gates becomes one fused tape
                     j = i
-                    while j < len(ins) and isinstance(ins[j], GateApp):
+                    while (j < len(ins) and isinstance(ins[j], GateApp)
+                           and (ins[j].name, tuple(ins[j].qubits)) not in self.superoperator_definitions):
                         j += 1
+                    if j == i:        # a noisy gate: stochastic evolution, like the interpreted path
+                        evolve_pure_state_stochastically(self.superoperator_definitions[(x.name, tuple(x.qubits))],
+                                                         self.state, x.qubits, self.random())
+                        i += 1
+                        continue
                     self.state.vec.apply_gates(self._gate_list(ins[i:j]), fuse=fuse_gates_during_compilation)
                     i = j
                     continue
-                self.state.vec.apply_matrix(prog.gate_matrix(x), x.qubits)
+                key = (x.name, tuple(x.qubits))
+                if key in self.superoperator_definitions and not x.modifiers:
+                    evolve_pure_state_stochastically(self.superoperator_definitions[key], self.state, x.qubits, self.random())
+                else:
+                    self.state.vec.apply_matrix(prog.gate_matrix(x), x.qubits)
             elif isinstance(x, Measure):
                 if compiled and compile_measure_chains:
                     # COMPILE-MEASURE-CHAINS src/compile-gate.lisp:551-599

@@ -354,3 +354,28 @@ def test_density_noisy_qaoa_fused_vs_oracle(Q, O):
     O.density_apply_kraus(rho, n, kk, (3, 1))
     st.apply_ops([(kk, (3, 1))])
     assert_close(st.state_elements(), rho)
+
+
+def test_stochastic_kraus_on_pure_state(Q, O):
+    """SURVEY 8f #2: %evolve-pure-state-stochastically, same uniform draw on both sides."""
+    n = 10
+    kraus = G.depolarizing_kraus_map(0.5)
+    kk = G.kraus_kron(G.damping_kraus_map(3.0, 1.0), G.dephasing_kraus_map(2.0, 1.0))
+    for r, ks, qs in [(0.05, kraus, (3,)), (0.7, kraus, (9,)), (0.93, kraus, (0,)), (0.999, kraus, (5,)),
+                      (0.4, kk, (7, 2)), (0.97, kk, (1, 8))]:
+        psi = rand_state(n, int(r * 1000))
+        st = Q.PureState(n)
+        st.set_state_elements(psi)
+        j_gpu = Q.evolve_pure_state_stochastically(ks, st, qs, r)
+        ref = psi.copy()
+        j_ref = O.evolve_stochastic(ref, ks, qs, r)
+        assert j_gpu == j_ref
+        assert_close(st.state_elements(), ref)
+    # tests/state-representation-tests.lisp:55-66: depolarised "I 0" sometimes flips the measured bit
+    ones = 0
+    for seed in range(60):
+        qvm = Q.make_qvm(2, seed=seed)
+        qvm.set_superoperator("I", (0,), G.depolarizing_kraus_map(0.5))
+        qvm.load_program("DECLARE R0 BIT\nI 0\nMEASURE 0 R0").run()
+        ones += int(qvm.registers["R0"][0])
+    assert 0 < ones < 60
