@@ -126,6 +126,12 @@ int qvmcuda_density_diag_probs(qvmcuda_state *s, int n_qubits, double *out);
  *      read/write peer shards over NVLink. */
 int qvmcuda_shard_export(qvmcuda_state *s, uint8_t handle[64]);
 int qvmcuda_shard_attach(qvmcuda_state *s, int rank, int world, const uint8_t *handles /* world*64 */);
+/* Optional second shard buffer: with it, remaps are out-of-place PULLS (every rank gathers the amplitudes it
+ * will own from all ranks' current buffers, then all ranks flip buffers), which moves every amplitude over
+ * NVLink once instead of twice.  Costs 2x shard memory; without it remaps run in place through the tile kernel.
+ * Protocol: every rank calls export_alt, the host all-gathers the handles, every rank calls attach_alt. */
+int qvmcuda_shard_export_alt(qvmcuda_state *s, uint8_t handle[64]);
+int qvmcuda_shard_attach_alt(qvmcuda_state *s, const uint8_t *handles /* world*64 */);
 /* Schedule a gate run against the shard's current qubit layout (gate qubits are LOGICAL, 0 <= q <
  * log2(shard length) + log2(world); every rank must pass the same gate list).  The tape is run step by
  * step: a step whose flags have QVMCUDA_STEP_PEER set reads/writes peer shards over NVLink, so the host

@@ -297,6 +297,40 @@ __global__ void __launch_bounds__(QV_THREADS) qv_final_sum_kernel(const double* 
 }
 
 // ---------------------------------------------------------------------------
+// Pull remap (multi-GPU): dst[p] = current[src_rank][src_off] where (src_rank, src_off) is the destination
+// index (rank, p) with every (local_bit, global_bit) pair swapped.  Local bits are >= 4, so 16 consecutive
+// destinations share a 256-byte source run: coalesced 128-bit NVLink reads, local streaming writes.
+// Bound: NVLink ingress, (1 - 2^-pairs) of the shard (measured peer-read peak ~ 675-785 GB/s, scripts/p2p_probe.cu).
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(QV_THREADS)
+qv_remap_pull_kernel(const __grid_constant__ QvPeers cur, qvc* __restrict__ dst, const __grid_constant__ QvRemap rm) {
+    const uint32_t n_local = rm.n_local_bits;
+    const uint64_t n = 1ull << n_local;
+    const uint64_t local_mask = n - 1ull;
+    const uint64_t rank_bits = (uint64_t)rm.rank << n_local;
+    const uint64_t stride = (uint64_t)gridDim.x * QV_THREADS * 4;
+    for (uint64_t p0 = ((uint64_t)blockIdx.x * QV_THREADS * 4) + threadIdx.x; p0 < n; p0 += stride) {
+        qvc v[4];
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            const uint64_t pj = p0 + (uint64_t)j * QV_THREADS;
+            if (pj >= n) continue;
+            const uint64_t P = rank_bits | pj;
+            uint64_t S = P;
+            for (uint32_t i = 0; i < rm.n_pairs; i++) {
+                const uint64_t lb = (P >> rm.local_bit[i]) & 1ull, gb = (P >> rm.global_bit[i]) & 1ull;
+                const uint64_t x = lb ^ gb;
+                S ^= (x << rm.local_bit[i]) | (x << rm.global_bit[i]);
+            }
+            v[j] = qv_ld_stream(cur.base[(S >> n_local) & (QV_MAX_PEERS - 1)] + (S & local_mask));
+        }
+#pragma unroll
+        for (int j = 0; j < 4; j++)
+            if (p0 + (uint64_t)j * QV_THREADS < n) qv_st_stream(dst + p0 + (uint64_t)j * QV_THREADS, v[j]);
+    }
+}
+
+// ---------------------------------------------------------------------------
 // Element-wise passes.
 // ---------------------------------------------------------------------------
 // mode 0: psi *= f                                                 (NORMALIZE-WAVEFUNCTION wavefunction.lisp:349-364)

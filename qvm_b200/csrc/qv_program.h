@@ -117,6 +117,19 @@ struct QvPassHeader {
     uint64_t hi_off[16];            // physical-index bits of tile-local index 256*i (host-precomputed gather)
 };
 
+// Pull remap (multi-GPU): every rank gathers the amplitudes it will own AFTER the physical bit swaps
+// (local_bit[i] <-> global_bit[i]) from the current buffers of all ranks into its alternate buffer; then all
+// ranks flip buffers.  Each amplitude crosses NVLink exactly once (an in-place exchange through the tile
+// kernel moves it twice: pulled by the rank that handles the tile and pushed back).
+struct QvRemap {
+    uint32_t n_pairs;
+    uint32_t n_local_bits;
+    uint32_t rank;
+    uint32_t pad;
+    uint32_t local_bit[8];
+    uint32_t global_bit[8];
+};
+
 // A k>=3 dense gate runs as its own pass through the generic kernel.
 struct QvBigGate {
     uint32_t k;

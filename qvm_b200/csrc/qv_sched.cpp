@@ -823,7 +823,24 @@ Tape compile(const std::vector<Gate>& gates, int n_bits, const CompileOptions& o
             return w2p[a] > w2p[b];     // prefer high local bits: longer contiguous runs stay put
         });
         if (cand.size() < globals.size()) throw std::runtime_error("scheduler: no local bit available for a remap");
-        // one peer pass exchanges as many (global, victim) pairs as the tile has room for
+        if (opt.remap_pull) {
+            // one out-of-place pull moves every needed pair at once
+            Step st;
+            st.kind = Step::REMAP;
+            st.uses_peers = true;
+            st.is_remap = true;
+            st.remap.n_pairs = (uint32_t)globals.size();
+            st.remap.n_local_bits = (uint32_t)geo.n_local;
+            st.remap.rank = (uint32_t)geo.rank;
+            for (size_t i = 0; i < globals.size(); i++) {
+                st.remap.local_bit[i] = (uint32_t)w2p[cand[i]];
+                st.remap.global_bit[i] = (uint32_t)w2p[globals[i]];
+            }
+            tape.steps.push_back(std::move(st));
+            for (size_t i = 0; i < globals.size(); i++) std::swap(w2p[cand[i]], w2p[globals[i]]);
+            return;
+        }
+        // in place: one peer pass exchanges as many (global, victim) pairs as the tile has room for
         const size_t per_pass = (size_t)std::max(1, cap_high / 2);
         for (size_t first = 0; first < globals.size(); first += per_pass) {
             const size_t last = std::min(globals.size(), first + per_pass);
@@ -982,6 +999,12 @@ std::string describe(const Tape& t) {
         const Step& s = t.steps[i];
         if (s.kind == Step::BIG) {
             os << "  [" << i << "] BIG k=" << s.big.k << "\n";
+            continue;
+        }
+        if (s.kind == Step::REMAP) {
+            os << "  [" << i << "] REMAP(pull)";
+            for (uint32_t k = 0; k < s.remap.n_pairs; k++) os << " " << s.remap.local_bit[k] << "<->" << s.remap.global_bit[k];
+            os << "\n";
             continue;
         }
         QvPassHeader h;

@@ -32,13 +32,15 @@ struct CompileOptions {
     bool absorb_swaps = false;   // true: exact SWAP gates only relabel qubits (l2p changes)
     int n_local_bits = 0;        // log2(amplitudes on this device); 0 = n_bits (single device)
     int rank = 0;                // value of the physical bits >= n_local_bits on this device
+    bool remap_pull = false;     // remaps as out-of-place pulls into the alternate buffer (needs 2x shard memory)
 };
 
 struct Step {
-    enum Kind { TILE = 0, BIG = 1 } kind = TILE;
+    enum Kind { TILE = 0, BIG = 1, REMAP = 2 } kind = TILE;
     std::vector<uint8_t> blob;   // TILE: QvPassHeader followed by rounds/ops/chunks/matrices (<= QV_PROG_LARGE_BYTES)
     std::vector<cd> tables;      // TILE: diagonal factor tables (global memory)
     QvBigGate big{};             // BIG
+    QvRemap remap{};             // REMAP (pull remap into the alternate buffer; all ranks flip afterwards)
     std::vector<cd> bigmat;      // BIG: row-major 2^k x 2^k
     int n_gates = 0;             // logical gates (atoms) folded into this step
     bool uses_peers = false;     // TILE: the tile spans rank bits -> peer shards are read/written (needs barriers)

@@ -71,6 +71,10 @@ struct qvmcuda_state {
     int rank = 0, world = 1;
     QvPeers peers{};
     std::vector<void*> opened;     // IPC-opened peer pointers
+    // alternate shard buffer for pull remaps (out of place, then every rank flips)
+    qvc* d_alt = nullptr;
+    QvPeers peers_alt{};
+    bool remap_pull = false;       // every rank has attached every rank's alternate buffer
     // immediate-mode program upload
     uint8_t* d_scratch = nullptr;
     uint8_t* h_scratch = nullptr;  // pinned
@@ -158,10 +162,30 @@ int launch_big(qvmcuda_state* s, const qv::Step& st, const uint8_t* d_mat) {
 }
 
 // run a compiled tape whose step data already sits in d_buf
+// Pull remap: gather this rank's future shard from every rank's current buffer into the alternate
+// buffer, then flip (every rank runs the same step, so all pointer tables flip together).
+int launch_remap(qvmcuda_state* s, const qv::Step& st) {
+    if (!s->remap_pull || !s->d_alt) return fail("pull remap without an attached alternate buffer");
+    uint64_t blocks = (s->n_amps + QV_THREADS * 4 - 1) / (QV_THREADS * 4);
+    const uint64_t cap = (uint64_t)s->sm_count * 8 * 4;
+    if (blocks > cap) blocks = cap;
+    qv_remap_pull_kernel<<<(int)blocks, QV_THREADS, 0, s->stream>>>(s->peers, s->d_alt, st.remap);
+    g_launches++;
+    CK(cudaGetLastError());
+    std::swap(s->d_amps, s->d_alt);
+    std::swap(s->peers, s->peers_alt);
+    return 0;
+}
+
+int launch_step(qvmcuda_state* s, const qv::Step& st, const uint8_t* d_data) {
+    if (st.kind == qv::Step::TILE) return launch_tile(s, st, d_data);
+    if (st.kind == qv::Step::BIG) return launch_big(s, st, d_data);
+    return launch_remap(s, st);
+}
+
 int run_steps(qvmcuda_state* s, const qv::Tape& tape, const std::vector<size_t>& offsets, const uint8_t* d_buf) {
     for (size_t i = 0; i < tape.steps.size(); i++) {
-        const qv::Step& st = tape.steps[i];
-        int rc = st.kind == qv::Step::TILE ? launch_tile(s, st, d_buf + offsets[i]) : launch_big(s, st, d_buf + offsets[i]);
+        int rc = launch_step(s, tape.steps[i], d_buf + offsets[i]);
         if (rc) return rc;
     }
     return 0;
@@ -191,6 +215,7 @@ qv::CompileOptions make_options(const qvmcuda_state* s, uint32_t flags) {
     if (s) {
         opt.rank = s->rank;
         opt.n_local_bits = s->n_bits;
+        opt.remap_pull = s->remap_pull;
     }
     return opt;
 }
@@ -381,6 +406,7 @@ int qvmcuda_state_destroy(qvmcuda_state* s) {
         DeviceGuard dg(s->device);
         cudaStreamSynchronize(s->stream);
         for (void* p : s->opened) cudaIpcCloseMemHandle(p);
+        if (s->d_alt) cudaFree(s->d_alt);
         cudaFree(s->d_amps);
         cudaFree(s->d_partial);
         if (s->d_scratch) cudaFree(s->d_scratch);
@@ -571,7 +597,7 @@ int qvmcuda_tape_run_step(qvmcuda_state* s, qvmcuda_tape* t, int step) {
     uint8_t* d_buf = nullptr;
     if (int rc = tape_device_buffer(s, t, &d_buf)) return rc;
     const qv::Step& st = t->tape.steps[step];
-    return st.kind == qv::Step::TILE ? launch_tile(s, st, d_buf + t->offsets[step]) : launch_big(s, st, d_buf + t->offsets[step]);
+    return launch_step(s, st, d_buf + t->offsets[step]);
 }
 
 int qvmcuda_tape_commit(qvmcuda_state* s, qvmcuda_tape* t) {
@@ -860,6 +886,44 @@ int qvmcuda_shard_attach(qvmcuda_state* s, int rank, int world, const uint8_t* h
     const int total = s->n_bits + log2_exact((uint64_t)world);
     s->l2p.resize(total);
     for (int i = 0; i < total; i++) s->l2p[i] = i;
+    return 0;
+}
+
+int qvmcuda_shard_export_alt(qvmcuda_state* s, uint8_t handle[64]) {
+    if (!s || !handle) return fail("null argument");
+    std::lock_guard<std::mutex> lk(s->mu);
+    DeviceGuard dg(s->device);
+    if (!s->d_alt) {
+        size_t free_b = 0, total_b = 0;
+        CK(cudaMemGetInfo(&free_b, &total_b));
+        const size_t need = s->n_amps * sizeof(qvc);
+        if (free_b < need + (size_t(2) << 30)) return fail("not enough device memory for an alternate shard buffer");
+        CK(cudaMalloc((void**)&s->d_alt, need));
+    }
+    cudaIpcMemHandle_t h;
+    CK(cudaIpcGetMemHandle(&h, s->d_alt));
+    std::memcpy(handle, &h, 64);
+    return 0;
+}
+
+int qvmcuda_shard_attach_alt(qvmcuda_state* s, const uint8_t* handles) {
+    if (!s || !handles) return fail("null argument");
+    std::lock_guard<std::mutex> lk(s->mu);
+    if (s->world < 2 || !s->d_alt) return fail("attach the shards and export the alternate buffer first");
+    DeviceGuard dg(s->device);
+    for (int r = 0; r < s->world; r++) {
+        if (r == s->rank) {
+            s->peers_alt.base[r] = s->d_alt;
+            continue;
+        }
+        cudaIpcMemHandle_t h;
+        std::memcpy(&h, handles + 64 * (size_t)r, 64);
+        void* p = nullptr;
+        CK(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
+        s->opened.push_back(p);
+        s->peers_alt.base[r] = (qvc*)p;
+    }
+    s->remap_pull = true;
     return 0;
 }
 

@@ -48,6 +48,18 @@ class CudaShardEngine:
         allh = np.frombuffer(b"".join(handles), dtype=np.uint8).copy()
         L.check(L.lib().qvmcuda_shard_attach(self.vec.handle, rank, world, L.ptr(allh)))
         self.n_total = n_local + _log2(world)
+        # Optional alternate buffer: remaps become out-of-place pulls (each amplitude crosses NVLink once).
+        # Every rank must succeed, otherwise all fall back to the in-place exchange through the tile kernel.
+        self.remap_pull = False
+        if not os.environ.get("QVM_REMAP_INPLACE"):
+            alt = np.zeros(64, dtype=np.uint8)
+            ok = L.lib().qvmcuda_shard_export_alt(self.vec.handle, L.ptr(alt)) == 0
+            alts = [None] * world
+            dist.all_gather_object(alts, alt.tobytes() if ok else None)
+            if all(a is not None for a in alts):
+                allalt = np.frombuffer(b"".join(alts), dtype=np.uint8).copy()
+                L.check(L.lib().qvmcuda_shard_attach_alt(self.vec.handle, L.ptr(allalt)))
+                self.remap_pull = True
 
     def compile(self, gates, fuse=True, absorb_swaps=False):
         L = self.L

@@ -98,7 +98,30 @@ void run_big_step(qvc* psi, int n_bits, const qv::Step& st) {   // psi = this ra
     }
 }
 
+// Pull remap (Step::REMAP): dst shard of every rank gathers from all current shards, then the buffers flip.
+// Same index algebra as qv_remap_pull_kernel.
+void run_remap_step(std::vector<qvc*>& cur, std::vector<qvc*>& alt, int n_local, const qv::Step& st_of_rank0) {
+    const QvRemap& rm = st_of_rank0.remap;
+    const uint64_t n = 1ull << n_local, local_mask = n - 1ull;
+    for (size_t r = 0; r < cur.size(); r++) {
+        for (uint64_t p = 0; p < n; p++) {
+            const uint64_t P = ((uint64_t)r << n_local) | p;
+            uint64_t S = P;
+            for (uint32_t i = 0; i < rm.n_pairs; i++) {
+                const uint64_t x = ((P >> rm.local_bit[i]) ^ (P >> rm.global_bit[i])) & 1ull;
+                S ^= (x << rm.local_bit[i]) | (x << rm.global_bit[i]);
+            }
+            alt[r][p] = cur[S >> n_local][S & local_mask];
+        }
+    }
+    std::swap(cur, alt);
+}
+
+bool g_remap_pull = false;
+
 }  // namespace
+
+extern "C" void qvtest_set_remap_pull(int on) { g_remap_pull = on != 0; }
 
 extern "C" int qvtest_run(double* psi, int n_bits, int n_gates, const int* ks, const int* qubits_flat,
                           const double* mats_flat, int fuse, int tile_bits, int absorb_swaps,
@@ -174,14 +197,26 @@ extern "C" int qvtest_run_sharded(double* psi, int n_bits, int world, int n_gate
             opt.absorb_swaps = absorb_swaps != 0;
             opt.n_local_bits = n_local;
             opt.rank = r;
+            opt.remap_pull = g_remap_pull;
             tapes[r] = qv::compile(gates, n_bits, opt, l2p);
             if (tapes[r].steps.size() != tapes[0].steps.size() || tapes[r].l2p != tapes[0].l2p)
                 throw std::runtime_error("ranks disagree on the schedule");
         }
         std::vector<qvc*> peers(world);
         for (int r = 0; r < world; r++) peers[r] = (qvc*)psi + ((size_t)r << n_local);
+        std::vector<qvc> altbuf(g_remap_pull ? ((size_t)1 << n_bits) : 0);
+        std::vector<qvc*> alts(world);
+        for (int r = 0; r < world; r++) alts[r] = altbuf.data() + (g_remap_pull ? ((size_t)r << n_local) : 0);
         int peer_steps = 0;
         for (size_t i = 0; i < tapes[0].steps.size(); i++) {
+            if (tapes[0].steps[i].kind == qv::Step::REMAP) {
+                for (int r = 0; r < world; r++)
+                    if (tapes[r].steps[i].kind != qv::Step::REMAP || tapes[r].steps[i].remap.rank != (uint32_t)r)
+                        throw std::runtime_error("ranks disagree on a remap step");
+                run_remap_step(peers, alts, n_local, tapes[0].steps[i]);
+                peer_steps++;
+                continue;
+            }
             for (int r = 0; r < world; r++) {
                 const qv::Step& st = tapes[r].steps[i];
                 if (st.kind != tapes[0].steps[i].kind || st.uses_peers != tapes[0].steps[i].uses_peers)
@@ -191,6 +226,8 @@ extern "C" int qvtest_run_sharded(double* psi, int n_bits, int world, int n_gate
             }
             if (tapes[0].steps[i].uses_peers) peer_steps++;
         }
+        if (peers[0] != (qvc*)psi)   // an odd number of flips: the result sits in the alternate buffers
+            std::memcpy(psi, altbuf.data(), sizeof(qvc) << n_bits);
         if (l2p_inout) std::memcpy(l2p_inout, tapes[0].l2p.data(), sizeof(int) * n_bits);
         if (desc && desc_len > 0) {
             std::string s = qv::describe(tapes[0]);

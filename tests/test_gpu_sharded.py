@@ -20,8 +20,12 @@ def _free_port():
     return p
 
 
-def _worker(rank, world, port, q):
+def _worker(rank, world, port, q, inplace):
     try:
+        if inplace:
+            os.environ["QVM_REMAP_INPLACE"] = "1"     # remaps as in-place peer passes of the tile kernel
+        else:
+            os.environ.pop("QVM_REMAP_INPLACE", None)  # remaps as out-of-place pulls into the alternate buffer
         sys.path.insert(0, HERE)
         sys.path.insert(0, os.path.dirname(HERE))
         import torch
@@ -36,6 +40,7 @@ def _worker(rank, world, port, q):
 
         n = 19 + (world.bit_length() - 1)
         st = ShardedState(n, dist, device=rank)
+        assert st.engine.remap_pull == (not inplace)
         psi = helpers.rand_state(n, 21)
         st.scatter_logical(psi)
         rng = np.random.default_rng(5)
@@ -77,8 +82,9 @@ def _worker(rank, world, port, q):
         q.put((rank, traceback.format_exc()))
 
 
+@pytest.mark.parametrize("inplace", [False, True])
 @pytest.mark.parametrize("world", [2, 4, 8])
-def test_sharded_state_over_nvlink(world):
+def test_sharded_state_over_nvlink(world, inplace):
     import torch
     if torch.cuda.device_count() < world:
         pytest.skip(f"needs {world} GPUs")
@@ -86,7 +92,7 @@ def test_sharded_state_over_nvlink(world):
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = _free_port()
-    procs = [ctx.Process(target=_worker, args=(r, world, port, q)) for r in range(world)]
+    procs = [ctx.Process(target=_worker, args=(r, world, port, q, inplace)) for r in range(world)]
     for p in procs:
         p.start()
     results = [q.get(timeout=600) for _ in procs]

@@ -11,12 +11,13 @@ from qvm_b200 import circuits as CC
 
 @pytest.mark.parametrize("world", [2, 4, 8])
 @pytest.mark.parametrize("fuse", [True, False])
-def test_sharded_qft(world, fuse):
+@pytest.mark.parametrize("pull", [False, True])
+def test_sharded_qft(world, fuse, pull):
     n, tile_bits = 13, 7
     circ = CC.qft_circuit(range(n))
     a = rand_state(n)
     ref = run_oracle(a.copy(), circ)
-    steps, peer_steps, desc, l2p = run_emulator_sharded(a, n, world, circ, fuse=fuse, tile_bits=tile_bits)
+    steps, peer_steps, desc, l2p = run_emulator_sharded(a, n, world, circ, fuse=fuse, tile_bits=tile_bits, remap_pull=pull)
     assert peer_steps >= 1, desc
     assert_close(unpermute(a, l2p), ref)
 
@@ -29,11 +30,12 @@ def test_sharded_random_circuits(seed):
     circ = random_circuit(n, 50, rng, max_dense=4)
     a = rand_state(n, seed)
     ref = run_oracle(a.copy(), circ)
-    steps, peer_steps, desc, l2p = run_emulator_sharded(a, n, world, circ, fuse=True, tile_bits=7)
+    steps, peer_steps, desc, l2p = run_emulator_sharded(a, n, world, circ, fuse=True, tile_bits=7, remap_pull=bool(seed & 1))
     assert_close(unpermute(a, l2p), ref)
 
 
-def test_index_tracer_through_remaps():
+@pytest.mark.parametrize("pull", [False, True])
+def test_index_tracer_through_remaps(pull):
     """dqvm's debug wavefunction psi_i = i (dqvm/tests/program-tests.lisp:14-19): permutation-only circuits
     move integer labels exactly, so any address-algebra slip shows up as a wrong integer."""
     from qvm_b200 import gates as G
@@ -46,7 +48,8 @@ def test_index_tracer_through_remaps():
                      (G.gate_matrix("X"), (a,))][int(rng.integers(0, 4))])
     psi = np.arange(1 << n).astype(np.complex128)
     ref = run_oracle(psi.copy(), circ)
-    _, _, _, l2p = run_emulator_sharded(psi, n, world, circ, fuse=True, tile_bits=6)
+    _, peer_steps, desc, l2p = run_emulator_sharded(psi, n, world, circ, fuse=True, tile_bits=6, remap_pull=pull)
+    assert peer_steps >= 1 and (("REMAP(pull)" in desc) == pull), desc
     assert np.array_equal(unpermute(psi, l2p), ref)
 
 
