@@ -30,17 +30,16 @@ __device__ __forceinline__ void qv_cp_async16(qvc* smem_dst, const qvc* gsrc) {
     const uint32_t d = (uint32_t)__cvta_generic_to_shared(smem_dst);
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gsrc) : "memory");
 }
-__device__ __forceinline__ void qv_cp_async_wait_all() {
-    asm volatile("cp.async.commit_group;" ::: "memory");
-    asm volatile("cp.async.wait_group 0;" ::: "memory");
-}
 
 // ---------------------------------------------------------------------------
 // The tile kernel: one CTA = one tile of 2^T amplitudes staged in shared memory
 // (XOR-swizzled, see qv_swz), rounds of register-resident groups, write back.
-// 256 threads, <= 80 registers, 64 KiB of shared memory at T=12 -> 3 CTAs per SM.
+//   M = 3 : 256 threads, 8 amplitudes per thread per round, <= 80 registers  }  64 KiB tile + 10.5 KiB of
+//   M = 4 : 128 threads, 16 amplitudes per thread per round, <= 168 registers }  per-tile tables -> 3 CTAs / SM
+//           (fewer, fatter threads: micro-op decode is amortised over twice the amplitudes and a
+//           pass over 8 tile bits needs 2 rounds instead of 3; used for passes that carry many gates)
 //   FULL  = true : T == 12 (every state of >= 12 qubits): all loop bounds are compile-time, the
-//                  tile-local -> physical address of element tid + 256*i is
+//                  tile-local -> physical address of element tid + THREADS*i is
 //                  (base | gather(tid)) | hi_off[i] with hi_off precomputed by the host.
 //   PEERS = true : tile bits include rank bits, amplitudes come from / go to peer
 //                  shards over NVLink (P2P loads/stores on IPC-mapped pointers).
@@ -48,14 +47,19 @@ __device__ __forceinline__ void qv_cp_async_wait_all() {
 struct QvProgSmall { uint8_t bytes[QV_PROG_SMALL_BYTES]; };
 struct QvProgLarge { uint8_t bytes[QV_PROG_LARGE_BYTES]; };
 
-template <typename PROG, bool PEERS, bool FULL>
-__global__ void __launch_bounds__(QV_THREADS, 3)
+template <typename PROG, bool PEERS, bool FULL, int M>
+__global__ void __launch_bounds__((M == 4 ? QV_THREADS_WIDE : QV_THREADS), 3)
 qv_tile_kernel(const __grid_constant__ PROG prog, const __grid_constant__ QvPeers peers,
                const qvc* __restrict__ tables) {
+    constexpr int THREADS = (M == 4 ? QV_THREADS_WIDE : QV_THREADS);
+    constexpr int NS = 1 << M;
+    constexpr int ITERS = 4096 / THREADS;
     extern __shared__ __align__(16) uint8_t qv_smem_raw[];
     qvc* tile = reinterpret_cast<qvc*>(qv_smem_raw);
-    __shared__ uint32_t s_ext[QV_MAX_PASS_CHUNKS];
     __shared__ qvc s_slice[QV_SLICE_ENTRIES];
+    __shared__ uint32_t s_ext[QV_MAX_EXT];
+    __shared__ uint32_t s_srcext[QV_MAX_SOURCES];
+    __shared__ uint8_t s_pred[QV_MAX_PREDS];
 
     // The control program sits in the constant bank (kernel parameters): every read below is a
     // uniform constant load, matrices reach the FP64 pipe through uniform registers.
@@ -68,78 +72,89 @@ qv_tile_kernel(const __grid_constant__ PROG prog, const __grid_constant__ QvPeer
     const uint32_t n_local = h->n_local_bits;
     const uint64_t local_mask = (1ull << n_local) - 1ull;
     const uint32_t n_rounds = h->n_rounds;
-    const uint32_t n_chunks = h->n_chunks;
     const QvRound* rounds = reinterpret_cast<const QvRound*>(blob + h->off_rounds);
-    const QvOp* ops = reinterpret_cast<const QvOp*>(blob + h->off_ops);
-    const QvChunk* chunks = reinterpret_cast<const QvChunk*>(blob + h->off_chunks);
+    const QvUop* uops = reinterpret_cast<const QvUop*>(blob + h->off_uops);
+    const QvExt* exts = reinterpret_cast<const QvExt*>(blob + h->off_ext);
     const QvSource* sources = reinterpret_cast<const QvSource*>(blob + h->off_sources);
-    const qvc* mats = reinterpret_cast<const qvc*>(blob + h->off_matrices);
+    const QvSlice* slices = reinterpret_cast<const QvSlice*>(blob + h->off_slices);
+    const uint8_t* slice_of = blob + h->off_slice_of;
+    const QvPred* preds = reinterpret_cast<const QvPred*>(blob + h->off_preds);
 
     const uint32_t tid = threadIdx.x;
-    const uint32_t iters = FULL ? 16u : (tile_n + QV_THREADS - 1) / QV_THREADS;
-    // tile-local e = tid + 256*i: the gather is bitwise linear, so split it.
+    const uint32_t iters = FULL ? (uint32_t)ITERS : (tile_n + THREADS - 1) / THREADS;
+    // tile-local e = tid + THREADS*i: the gather is bitwise linear, so split it.
     const uint64_t glo = qv_gather((uint64_t)tid, h->tile_segs, h->n_tile_segs);
-    // qv_swz only mixes bits 3..5 into bits 0..2, so the slot of tid + 256*i is qv_swz(tid) + 256*i
+    // qv_swz only mixes bits 3..5 into bits 0..2, so the slot of tid + THREADS*i is qv_swz(tid) + THREADS*i
     qvc* const my_tile = tile + qv_swz(tid);
     qvc* const own = peers.base[PEERS ? 0 : (fixed_bits >> n_local) & (QV_MAX_PEERS - 1)];
 
     for (uint64_t t = blockIdx.x; t < n_tiles; t += gridDim.x) {
         const uint64_t base = qv_gather(t, h->base_segs, h->n_base_segs) | fixed_bits;
         const uint64_t pbase = PEERS ? (base | glo) : ((base | glo) & local_mask);
-        if (tid < n_chunks) s_ext[tid] = (uint32_t)qv_gather(base, chunks[tid].esegs, chunks[tid].n_esegs);
-        // per-tile diagonal slices: warp w builds the slices of chunks w, w+8, ... (their external bits are
-        // constant over the tile, so all sources over the same local bits collapse into one small table)
-        for (uint32_t c = tid >> 5; c < n_chunks; c += QV_THREADS / 32) {
-            const QvChunk& ch = chunks[c];
-            if (ch.kind) {
-                const uint32_t cnt = 1u << ch.nl;
-                for (uint32_t x = tid & 31; x < cnt; x += 32)
-                    s_slice[ch.table_off + x] = qv_slice_entry(ch, sources, tables, base, x);
-            }
-        }
 
-        // ---- HBM -> shared memory: 16 asynchronous 16-byte copies in flight per thread
+        // ---- HBM -> shared memory: asynchronous 16-byte copies, all of a thread's copies in flight at once
         if (FULL) {
 #pragma unroll
-            for (int i = 0; i < 16; i++) {
+            for (int i = 0; i < ITERS; i++) {
                 const uint64_t p = pbase | h->hi_off[i];
                 const qvc* src = PEERS ? peers.base[(p >> n_local) & (QV_MAX_PEERS - 1)] + (p & local_mask) : own + p;
-                qv_cp_async16(my_tile + i * QV_THREADS, src);
+                qv_cp_async16(my_tile + i * THREADS, src);
             }
         } else {
             for (uint32_t i = 0; i < iters; i++) {
-                const uint32_t e = tid + i * QV_THREADS;
+                const uint32_t e = tid + i * THREADS;
                 if (e < tile_n) {
                     const uint64_t p = pbase | h->hi_off[i];
                     const qvc* src = PEERS ? peers.base[(p >> n_local) & (QV_MAX_PEERS - 1)] + (p & local_mask) : own + p;
-                    qv_cp_async16(my_tile + i * QV_THREADS, src);
+                    qv_cp_async16(my_tile + i * THREADS, src);
                 }
             }
         }
-        qv_cp_async_wait_all();
+        asm volatile("cp.async.commit_group;" ::: "memory");
+
+        // ---- per-tile tables, built while the copies fly: external index parts, control predicates,
+        //      then the diagonal slices (all factors whose external bits are constant over this tile
+        //      collapse into small shared-memory tables)
+        if (h->n_ext | h->n_sources | h->n_preds) {
+            for (uint32_t i = tid; i < h->n_ext; i += THREADS)
+                s_ext[i] = (uint32_t)qv_gather(base, exts[i].esegs, exts[i].n_esegs) << exts[i].shift;
+            for (uint32_t i = tid; i < h->n_sources; i += THREADS)
+                s_srcext[i] = (uint32_t)qv_gather(base, sources[i].esegs, sources[i].n_esegs) << sources[i].nl;
+            for (uint32_t i = tid; i < h->n_preds; i += THREADS)
+                s_pred[i] = (base & preds[i].mask) == preds[i].val ? 1 : 0;
+            __syncthreads();
+            for (uint32_t f = tid; f < h->n_slice_entries; f += THREADS) {
+                const QvSlice& sl = slices[slice_of[f]];
+                s_slice[f] = qv_slice_entry(sl, sources, s_srcext, tables, f - sl.off);
+            }
+        }
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
         __syncthreads();
 
-        // ---- rounds: 2^m amplitudes per thread in registers, every op of the round applied there
+        // ---- rounds: 2^m amplitudes per thread in registers, every micro-op of the round applied there
         for (uint32_t r = 0; r < n_rounds; r++) {
             const QvRound& rd = rounds[r];
-            const uint32_t m = FULL ? 3u : rd.m;
+            const uint32_t m = FULL ? (uint32_t)M : rd.m;
             const uint32_t nslots = 1u << m;
             const uint32_t ngroups = tile_n >> m;
-            for (uint32_t g = tid; g < ngroups; g += QV_THREADS) {
+            const uint32_t u_end = rd.first_uop + rd.n_uops;
+            for (uint32_t g = tid; g < ngroups; g += THREADS) {
                 uint32_t e0 = g;
                 if (m > 0) e0 = qv_insert_zero(e0, rd.regpos[0]);
                 if (m > 1) e0 = qv_insert_zero(e0, rd.regpos[1]);
                 if (m > 2) e0 = qv_insert_zero(e0, rd.regpos[2]);
+                if (M > 3 && m > 3) e0 = qv_insert_zero(e0, rd.regpos[3]);
                 const uint32_t se0 = qv_swz(e0);
-                qvc a[8];
+                qvc a[NS];
 #pragma unroll
-                for (int s = 0; s < 8; s++) {
+                for (int s = 0; s < NS; s++) {
                     if (FULL || (uint32_t)s < nslots) a[s] = tile[se0 ^ rd.slot_xor[s]];
                     else { a[s].x = 0.0; a[s].y = 0.0; }
                 }
-                qv_apply_round(a, rd, ops, chunks, mats, tables, s_ext, s_slice, e0, base);
+                for (uint32_t u = rd.first_uop; u < u_end; u++)
+                    qv_run_uop<NS>(a, uops[u], g, blob, tables, s_slice, s_ext, s_pred);
 #pragma unroll
-                for (int s = 0; s < 8; s++)
+                for (int s = 0; s < NS; s++)
                     if (FULL || (uint32_t)s < nslots) tile[se0 ^ rd.slot_xor[s]] = a[s];
             }
             __syncthreads();
@@ -148,18 +163,18 @@ qv_tile_kernel(const __grid_constant__ PROG prog, const __grid_constant__ QvPeer
         // ---- shared memory -> HBM
         if (FULL) {
 #pragma unroll
-            for (int i = 0; i < 16; i++) {
+            for (int i = 0; i < ITERS; i++) {
                 const uint64_t p = pbase | h->hi_off[i];
                 qvc* dst = PEERS ? peers.base[(p >> n_local) & (QV_MAX_PEERS - 1)] + (p & local_mask) : own + p;
-                qv_st_stream(dst, my_tile[i * QV_THREADS]);
+                qv_st_stream(dst, my_tile[i * THREADS]);
             }
         } else {
             for (uint32_t i = 0; i < iters; i++) {
-                const uint32_t e = tid + i * QV_THREADS;
+                const uint32_t e = tid + i * THREADS;
                 if (e < tile_n) {
                     const uint64_t p = pbase | h->hi_off[i];
                     qvc* dst = PEERS ? peers.base[(p >> n_local) & (QV_MAX_PEERS - 1)] + (p & local_mask) : own + p;
-                    qv_st_stream(dst, my_tile[i * QV_THREADS]);
+                    qv_st_stream(dst, my_tile[i * THREADS]);
                 }
             }
         }

@@ -5,10 +5,15 @@
 // (the low L bits, so every HBM access is a run of 2^L*16 contiguous bytes, plus
 // arbitrary higher bits) vary inside the tile, the remaining bits select the
 // tile.  Inside the tile a pass runs ROUNDS: in a round each thread keeps a
-// GROUP of 2^m (m<=3) amplitudes in registers, the m "register bits" being
-// tile-local bit positions, and applies every OP of the round to them before
-// the group goes back to shared memory.  So one HBM pass can apply many gates,
-// and one shared-memory pass applies several of them.
+// GROUP of 2^m (m <= 4) amplitudes in registers, the m "register bits" being
+// tile-local bit positions, and applies every MICRO-OP of the round to them
+// before the group goes back to shared memory.  So one HBM pass can apply many
+// gates, and one shared-memory pass applies several of them.
+//
+// A micro-op is fully resolved by the host: its `kind` selects one specialised
+// code path (register bits, real/complex, gating are part of the kind), table
+// addresses, index fields and slot offsets are precomputed, so that the device
+// spends its instructions on FP64 math, not on decoding.
 //
 // Everything in here is physical: the host scheduler (qv_sched.cpp) has already
 // translated logical qubits into physical index bits.  All structs are PODs
@@ -18,30 +23,48 @@
 
 #define QV_MAX_TILE_BITS 12      // 2^12 amplitudes * 16 B = 64 KiB of shared memory per CTA
 #define QV_MIN_LOW_BITS 4        // low bits always inside the tile: 256-byte HBM runs at worst
-#define QV_REG_BITS 3            // 2^3 amplitudes per thread per round
+#define QV_MAX_REG_BITS 4        // up to 2^4 amplitudes per thread per round
+#define QV_MAX_SLOTS 16
 #define QV_MAX_SEGS 12
 #define QV_CHUNK_SEGS 8
 #define QV_MAX_CHUNK_BITS 8      // diagonal factor tables have <= 256 entries
-#define QV_THREADS 256
+#define QV_MAX_SOURCE_BITS 10    // source tables of a slice have <= 1024 entries
+#define QV_THREADS 256           // block size of the streaming kernels and of the 3-register-bit tile kernel
+#define QV_THREADS_WIDE 128      // block size of the 4-register-bit tile kernel (fewer, fatter threads)
 #define QV_MAX_PEERS 8
-#define QV_MAX_PASS_CHUNKS 256   // per-tile chunk offsets are staged in shared memory
+#define QV_MAX_EXT 128           // per-tile external index parts staged in shared memory
+#define QV_MAX_SOURCES 192       // per-tile source offsets staged in shared memory
+#define QV_MAX_PREDS 64          // per-tile control predicates (controls on bits outside the tile)
+#define QV_MAX_SLICES 64
 #define QV_SLICE_ENTRIES 544     // per-tile diagonal slices staged in shared memory (8.5 KiB; 3 CTAs/SM still fit)
-// The control part of a pass (header, rounds, ops, chunk descriptors, matrices) is handed to the
+#define QV_MAX_SLICE_BUILD 6144  // bound on sum(2^nl * n_src) per tile (slice construction work)
+// The control part of a pass (header, rounds, micro-ops, descriptors, matrices) is handed to the
 // kernel as a __grid_constant__ parameter: it lives in the constant bank, so ptxas reads matrices
 // through uniform registers instead of spending vector registers on them.  Two size classes.
 #define QV_PROG_SMALL_BYTES 3584
 #define QV_PROG_LARGE_BYTES 28672
 
-enum QvOpType : uint32_t {
-    QV_OP_DENSE1 = 1,   // 2x2 complex matrix on register bit rb0
-    QV_OP_DENSE2 = 2,   // 4x4 complex matrix on register bits rb0 < rb1 (matrix bit0 <-> rb0)
-    QV_OP_DIAG = 3,     // product of chunk-table lookups (merged diagonal gates)
+// Micro-op kinds.  RB = register bit index (0..3), PAIR = index of the register-bit pair
+// (0,1) (0,2) (1,2) (0,3) (1,3) (2,3).
+enum QvUopKind : uint32_t {
+    QV_K_DENSE1 = 0,         // + 2*RB + (complex ? 1 : 0)            2x2 matrix on register bit RB
+    QV_K_DENSE2 = 8,         // + 2*PAIR + (complex ? 1 : 0)          4x4 matrix on a register-bit pair
+    QV_K_DIAG_COMMON = 20,   // no register bit in the table index: one factor for the whole group
+    QV_K_DIAG_GATED1 = 21,   // + RB: gated by RB, no other register bit in the index: one factor for the gated slots
+    QV_K_DIAG_GATEDN = 25,   // + RB: gated by RB, other register bits in the index: one lookup per gated slot
+    QV_K_DIAG_ONEBIT = 29,   // + RB: exactly one register bit in the index, not gating: two lookups
+    QV_K_DIAG_ALL = 33,      // one lookup per slot
+    QV_K_COUNT = 34,
 };
 
-enum QvOpFlags : uint32_t {
-    QV_F_CTRL_LOCAL = 1u,   // cm_local/cv_local restrict the op to matching tile-local indices
-    QV_F_CTRL_EXT = 2u,     // cm_ext/cv_ext restrict the op to matching tiles (CTA-uniform)
-    QV_F_REAL = 4u,         // matrix has no imaginary parts (H, X, RY, CNOT, SWAP ...)
+enum QvUopFlags : uint32_t {
+    QV_UF_CTRL = 1u,      // dense: restricted by cm/cv (group level) and slot_ok (slot level)
+    QV_UF_PRED = 2u,      // dense: restricted to tiles whose predicate `pred` holds (controls outside the tile)
+    QV_UF_SLICE = 4u,     // diag: table is a per-tile slice in shared memory (else a global-memory table)
+    QV_UF_EXT = 8u,       // diag: add the per-tile external index part `ext`
+    QV_UF_FIELD2 = 16u,   // diag: a second index field
+    QV_UF_GENERIC = 32u,  // diag: index fields come from a segment list (more than two fields)
+    QV_UF_SCALE = 64u,    // diag (single-lookup kinds): multiply the entry by the one-entry slice `scale`
 };
 
 // gather/deposit of one contiguous bit field: ((x >> src) & ((1<<len)-1)) << dst
@@ -49,55 +72,70 @@ struct QvSeg {
     uint8_t src, len, dst, pad;
 };
 
-// One source table of a SLICE chunk: index = (gather_ext(base) << nl) | local_index.
+// A micro-op.  The group counter g (the tile-local index with the register bits squeezed out)
+// addresses everything that depends on the non-register bits.
+struct QvUop {
+    uint8_t kind;                   // QvUopKind
+    uint8_t flags;
+    uint8_t pred;                   // index of the per-tile predicate (QV_UF_PRED)
+    uint8_t ext;                    // index of the per-tile external index part (QV_UF_EXT)
+    uint32_t data;                  // dense: byte offset of the row-major matrix in the blob
+                                    // diag : entry offset of the table (slice area or global table pool)
+    uint32_t cm, cv;                // dense: control mask / value over g
+                                    // diag : cm = field 0, cv = field 1; field = shift | (mask << 8), value = (g >> shift) & mask
+    uint16_t slot_ok;               // dense: slots allowed by controls on register bits
+    uint16_t segs;                  // diag (QV_UF_GENERIC): byte offset of a QvSegList in the blob
+    uint8_t slot_off[QV_MAX_SLOTS]; // diag: table index contribution of register slot r
+    uint16_t scale;                 // diag (QV_UF_SCALE): entry of the slice area holding the per-tile scalar
+    uint16_t pad16;
+    uint32_t pad[2];
+};                                  // 48 bytes
+
+struct QvSegList {
+    uint32_t n;
+    QvSeg segs[QV_CHUNK_SEGS];
+};
+
+// Per-tile external part of a global table index: gather(tile base) << shift.
+struct QvExt {
+    uint8_t n_esegs, shift, pad[2];
+    QvSeg esegs[QV_CHUNK_SEGS];
+};
+
+// One source table of a slice: entry x of the slice takes the factor
+// tables[table_off + ((gather_ext(base) << nl) | gather_local(x))].
 struct QvSource {
     uint32_t table_off;             // offset in complex entries into the pass's table pool
-    uint8_t n_esegs, pad[3];
-    QvSeg esegs[QV_CHUNK_SEGS];
+    uint8_t n_esegs, n_lsegs, nl, pad;
+    QvSeg esegs[QV_CHUNK_SEGS];     // from the tile base
+    QvSeg lsegs[QV_CHUNK_SEGS];     // from the slice index x
 };
 
-// One factor of a merged diagonal.
-//   kind 0 (GLOBAL): phase = table[gather_local(e) | gather_ext(base)], table in global memory.
-//   kind 1 (SLICE) : all source tables over the same tile-local bits are multiplied together ONCE PER
-//                    TILE (their external bits are constant there) into a 2^nl-entry slice in shared
-//                    memory; phase = slice[gather_local(e)].
-struct QvChunk {
-    uint32_t table_off;             // offset in complex entries into the pass's table pool
-    uint8_t n_lsegs, n_esegs;       // fields gathered from the tile-local index / the tile base
-    uint8_t reg_mask;               // which register bits of the op's round feed this chunk
-    uint8_t gate_rb;                // 1 + register bit r such that every entry with that bit clear is exactly 1; 0 = none
-    QvSeg lsegs[QV_CHUNK_SEGS];     // only the NON-register local bits (register bits go through slot_off)
-    QvSeg esegs[QV_CHUNK_SEGS];
-    uint32_t slot_off[8];           // table-index contribution of register slot r (host-precomputed)
-    uint16_t kind;                  // 0 = GLOBAL, 1 = SLICE (table_off then counts entries into the slice area)
-    uint16_t nl;                    // SLICE: log2(entries)
-    uint16_t first_src, n_src;      // SLICE: its sources
+// A per-tile slice: all diagonal factors over the same tile-local bits, with their external bits
+// frozen to the tile's value, multiplied together ONCE PER TILE into 2^nl shared-memory entries.
+struct QvSlice {
+    uint16_t off;                   // first entry in the slice area
+    uint16_t nl;                    // log2(entries)
+    uint16_t first_src, n_src;
 };
 
-struct QvOp {
-    uint32_t type;
-    uint32_t flags;
-    uint8_t rb0, rb1, pad0, pad1;
-    uint32_t cm_local, cv_local;    // control over the tile-local index e
-    uint64_t cm_ext, cv_ext;        // control over the physical index bits outside the tile
-    uint32_t data_off;              // DENSE: offset in complex entries into the matrix pool (row-major)
-                                    // DIAG : index of the first chunk in the chunk array
-    uint32_t n_chunks;
-    uint32_t pad2[2];
+struct QvPred {
+    uint64_t mask, val;             // predicate: (tile base & mask) == val
 };
 
 struct QvRound {
-    uint32_t m;                     // register bits in this round (<= QV_REG_BITS, <= T)
-    uint32_t regpos[QV_REG_BITS];   // tile-local bit positions, ascending
-    uint32_t first_op, n_ops;
-    uint32_t pad[2];
-    uint32_t slot_dep[8];           // tile-local index offset of register slot r
-    uint32_t slot_xor[8];           // qv_swz(slot_dep[r]): the swizzle is XOR-linear, so the shared-memory
-                                    // slot of (e0 | dep) is qv_swz(e0) ^ slot_xor[r]
-};
+    uint32_t m;                     // register bits in this round (<= reg_bits of the pass, <= T)
+    uint32_t regpos[QV_MAX_REG_BITS];   // tile-local bit positions, ascending
+    uint32_t first_uop, n_uops;
+    uint32_t pad;
+    uint16_t slot_xor[QV_MAX_SLOTS];    // qv_swz(tile-local offset of slot r): the swizzle is XOR-linear, so the
+                                        // shared-memory slot of (e0 | dep) is qv_swz(e0) ^ slot_xor[r]
+};                                  // 64 bytes
 
 struct QvPassHeader {
     uint32_t T;                     // tile bits
+    uint32_t reg_bits;              // 3: 256-thread kernel, 8 amplitudes per thread; 4: 128-thread kernel, 16 per thread
+    uint32_t threads_log2;          // log2(block size) the gather split below was computed for
     uint32_t n_tile_segs;           // tile-local index e -> physical index bits
     QvSeg tile_segs[QV_MAX_SEGS];
     uint32_t n_base_segs;           // tile id -> physical index bits
@@ -105,16 +143,15 @@ struct QvPassHeader {
     uint64_t fixed_bits;            // OR'd into every physical index of the pass (rank bits, group split)
     uint64_t n_tiles;               // tiles this device processes
     uint32_t n_local_bits;          // log2(amplitudes per shard): physical bits above it select the peer
-    uint32_t n_rounds;
-    uint32_t n_ops;
-    uint32_t n_chunks;
+    uint32_t n_rounds, n_uops, n_ext, n_sources, n_slices, n_slice_entries, n_preds;
     // byte offsets from the start of the control blob (the diagonal tables travel separately,
     // in global memory)
-    uint32_t off_rounds, off_ops, off_chunks, off_sources, off_matrices, n_table_entries, n_sources, n_slice_entries;
+    uint32_t off_rounds, off_uops, off_ext, off_sources, off_slices, off_slice_of, off_preds, off_matrices;
+    uint32_t n_table_entries;
     uint32_t blob_bytes;
     uint32_t uses_peers;            // tile bits include a physical bit >= n_local_bits
-    uint32_t pad;
-    uint64_t hi_off[16];            // physical-index bits of tile-local index 256*i (host-precomputed gather)
+    uint32_t n_diag_uops;           // statistics for describe()
+    uint64_t hi_off[32];            // physical-index bits of tile-local index (block size)*i (host-precomputed gather)
 };
 
 // Pull remap (multi-GPU): every rank gathers the amplitudes it will own AFTER the physical bit swaps

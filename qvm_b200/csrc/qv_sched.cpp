@@ -144,12 +144,7 @@ std::vector<QvSeg> make_segs(const std::vector<int>& srcpos, const std::vector<i
     return segs;
 }
 
-// ---------------------------------------------------------------- diagonal chunks (physical space)
-struct Chunk {
-    std::vector<int> bits;      // sorted physical positions; table index bit i <-> bits[i]
-    std::vector<cd> table;
-};
-
+// ---------------------------------------------------------------- diagonal factors (physical space)
 struct DiagFactor {
     std::vector<int> pos;       // physical bit of entry index bit j
     std::vector<cd> diag;
@@ -160,35 +155,6 @@ struct TileMap {
     std::vector<int> tilebits;          // sorted physical bits inside the tile
     std::vector<int> local_of;          // physical bit -> tile-local position or -1
 };
-
-void chunk_multiply(Chunk& c, const DiagFactor& f) {
-    const size_t n = c.table.size();
-    std::vector<int> idx_of(f.pos.size());
-    for (size_t j = 0; j < f.pos.size(); j++)
-        idx_of[j] = (int)(std::find(c.bits.begin(), c.bits.end(), f.pos[j]) - c.bits.begin());
-    for (size_t t = 0; t < n; t++) {
-        uint32_t fi = 0;
-        for (size_t j = 0; j < f.pos.size(); j++)
-            if (t >> idx_of[j] & 1) fi |= 1u << j;
-        c.table[t] *= f.diag[fi];
-    }
-}
-
-void chunk_extend(Chunk& c, const std::vector<int>& newbits) {
-    std::vector<int> old = c.bits;
-    c.bits = newbits;
-    std::vector<cd> nt((size_t)1 << newbits.size());
-    std::vector<int> idx_of(old.size());
-    for (size_t j = 0; j < old.size(); j++)
-        idx_of[j] = (int)(std::find(newbits.begin(), newbits.end(), old[j]) - newbits.begin());
-    for (size_t t = 0; t < nt.size(); t++) {
-        uint32_t oi = 0;
-        for (size_t j = 0; j < old.size(); j++)
-            if (t >> idx_of[j] & 1) oi |= 1u << j;
-        nt[t] = c.table[oi];
-    }
-    c.table.swap(nt);
-}
 
 // Physical bits b of a factor such that every entry with bit b clear is exactly 1 (controlled phases:
 // CPHASE/CZ are gated by both of their qubits, T / PHASE by their only qubit, RZ by none).
@@ -203,56 +169,6 @@ uint64_t gating_bits(const DiagFactor& f) {
     return g;
 }
 
-// Merge the factors of one diagonal group into chunk tables of <= QV_MAX_CHUNK_BITS bits.  Factors that
-// are gated by the same REGISTER bit of the round (reg_phys) are kept together, so that the whole chunk
-// stays gated by it and the kernel only touches the slots where that bit is set.
-std::vector<Chunk> build_chunks(const std::vector<DiagFactor>& factors, uint64_t reg_phys) {
-    std::vector<Chunk> chunks;
-    std::vector<int> chunk_gate;      // physical gate bit of the chunk or -1
-    std::vector<uint64_t> gates(factors.size());
-    int cnt[64] = {0};
-    for (size_t i = 0; i < factors.size(); i++) {
-        gates[i] = gating_bits(factors[i]) & reg_phys;
-        for (int b = 0; b < 64; b++)
-            if (gates[i] >> b & 1) cnt[b]++;
-    }
-    for (size_t fi = 0; fi < factors.size(); fi++) {
-        const DiagFactor& f = factors[fi];
-        std::vector<int> fb = f.pos;
-        std::sort(fb.begin(), fb.end());
-        // preferred gate: the candidate register bit shared by most factors of the group
-        int want_gate = -1;
-        for (int b = 0; b < 64; b++)
-            if ((gates[fi] >> b & 1) && (want_gate < 0 || cnt[b] > cnt[want_gate])) want_gate = b;
-        int best = -1;
-        size_t best_size = 1000;
-        std::vector<int> best_union;
-        for (size_t ci = 0; ci < chunks.size(); ci++) {
-            if (chunk_gate[ci] != want_gate) continue;
-            std::vector<int> u;
-            std::set_union(chunks[ci].bits.begin(), chunks[ci].bits.end(), fb.begin(), fb.end(), std::back_inserter(u));
-            if (u.size() > QV_MAX_CHUNK_BITS) continue;
-            if (u.size() < best_size) {
-                best_size = u.size();
-                best = (int)ci;
-                best_union.swap(u);
-            }
-        }
-        if (best < 0) {
-            Chunk c;
-            c.bits = fb;
-            c.table.assign((size_t)1 << fb.size(), cd(1.0, 0.0));
-            chunks.push_back(std::move(c));
-            chunk_gate.push_back(want_gate);
-            best = (int)chunks.size() - 1;
-        } else if (best_union.size() != chunks[best].bits.size()) {
-            chunk_extend(chunks[best], best_union);
-        }
-        chunk_multiply(chunks[best], f);
-    }
-    return chunks;
-}
-
 // ---------------------------------------------------------------- pass builder
 struct RoundOp {
     bool is_diag = false;
@@ -263,12 +179,17 @@ struct RoundOp {
 
 struct BlobWriter {
     std::vector<QvRound> rounds;
-    std::vector<QvOp> ops;
-    std::vector<QvChunk> chunks;
+    std::vector<QvUop> uops;
+    std::vector<QvExt> exts;
     std::vector<QvSource> sources;
+    std::vector<QvSlice> slices;
+    std::vector<QvPred> preds;
+    std::vector<QvSegList> seglists;
     std::vector<cd> mats;
     std::vector<cd> tables;
     size_t slice_entries = 0;
+    size_t slice_build = 0;             // sum of 2^nl * n_src: per-tile construction work
+    size_t n_diag_uops = 0;
 };
 
 struct Layout {
@@ -276,267 +197,419 @@ struct Layout {
     int phys(int w) const { return (*w2p)[w]; }
 };
 
+// f with physical bit b fixed to 1 (b disappears from the factor).
+DiagFactor restrict_to_one(const DiagFactor& f, int b) {
+    DiagFactor r;
+    size_t jb = 0;
+    for (size_t j = 0; j < f.pos.size(); j++) {
+        if (f.pos[j] == b) jb = j;
+        else r.pos.push_back(f.pos[j]);
+    }
+    r.diag.resize(f.diag.size() / 2);
+    for (size_t t = 0; t < r.diag.size(); t++) {
+        const size_t lo = t & (((size_t)1 << jb) - 1);
+        const size_t full = ((t >> jb) << (jb + 1)) | ((size_t)1 << jb) | lo;
+        r.diag[t] = f.diag[full];
+    }
+    return r;
+}
+
+// Table of the product of `facs` over the index layout `bits` (index bit i <-> physical bit bits[i]).
+std::vector<cd> product_table(const std::vector<DiagFactor>& facs, const std::vector<int>& bits) {
+    std::vector<cd> tab((size_t)1 << bits.size(), cd(1.0, 0.0));
+    for (const DiagFactor& f : facs) {
+        std::vector<int> idx_of(f.pos.size());
+        for (size_t j = 0; j < f.pos.size(); j++) {
+            const auto it = std::find(bits.begin(), bits.end(), f.pos[j]);
+            if (it == bits.end()) throw std::runtime_error("scheduler bug: factor bit missing from a table layout");
+            idx_of[j] = (int)(it - bits.begin());
+        }
+        for (size_t t = 0; t < tab.size(); t++) {
+            uint32_t fi = 0;
+            for (size_t j = 0; j < f.pos.size(); j++)
+                if (t >> idx_of[j] & 1) fi |= 1u << j;
+            tab[t] *= f.diag[fi];
+        }
+    }
+    return tab;
+}
+
+// One planned diagonal micro-op: the factors it multiplies together and the bits its table is indexed by.
+struct PlanChunk {
+    int gate = -1;                      // physical register bit the chunk is gated by (its factors are restricted to it), or -1
+    std::vector<int> lbits;             // sorted physical tile-local bits of the index (gate excluded)
+    std::vector<int> ebits;             // sorted physical bits outside the tile
+    std::vector<DiagFactor> facs;
+    bool as_slice = false;
+};
+
 void emit_round(BlobWriter& w, const std::vector<RoundOp>& rops, const std::vector<int>& regpos_local,
                 const TileMap& tm, const Layout& lay) {
+    const int m = (int)regpos_local.size();
     QvRound rd{};
-    rd.m = (uint32_t)regpos_local.size();
-    for (size_t i = 0; i < regpos_local.size(); i++) rd.regpos[i] = (uint32_t)regpos_local[i];
-    for (uint32_t sl = 0; sl < 8; sl++) {
+    rd.m = (uint32_t)m;
+    for (int i = 0; i < m; i++) rd.regpos[i] = (uint32_t)regpos_local[i];
+    for (uint32_t sl = 0; sl < QV_MAX_SLOTS; sl++) {
         uint32_t dep = 0;
-        for (size_t i = 0; i < regpos_local.size(); i++)
+        for (int i = 0; i < m; i++)
             if (sl >> i & 1) dep |= 1u << regpos_local[i];
-        rd.slot_dep[sl] = dep;
-        rd.slot_xor[sl] = dep ^ ((dep >> 3) & 7u);     // qv_swz
+        rd.slot_xor[sl] = (uint16_t)(dep ^ ((dep >> 3) & 7u));     // qv_swz
     }
-    rd.first_op = (uint32_t)w.ops.size();
+    rd.first_uop = (uint32_t)w.uops.size();
+
+    // register index of a tile-local position, or -1
+    auto reg_of = [&](int lp) {
+        for (int i = 0; i < m; i++)
+            if (regpos_local[i] == lp) return i;
+        return -1;
+    };
+    // position in the group counter g (tile-local index with the register bits squeezed out)
+    auto gpos_of = [&](int lp) {
+        int below = 0;
+        for (int i = 0; i < m; i++)
+            if (regpos_local[i] < lp) below++;
+        return lp - below;
+    };
+    uint64_t reg_phys = 0;
+    for (int lp : regpos_local) reg_phys |= 1ull << tm.tilebits[lp];
+    static const int pair_index[4][4] = {{-1, 0, 1, 3}, {0, -1, 2, 4}, {1, 2, -1, 5}, {3, 4, 5, -1}};
+
     for (const RoundOp& ro : rops) {
-        QvOp op{};
         if (!ro.is_diag) {
             const Atom& a = *ro.dense;
+            QvUop u{};
             auto rb_of = [&](int wire) {
-                const int lp = tm.local_of[lay.phys(wire)];
-                for (size_t i = 0; i < regpos_local.size(); i++)
-                    if (regpos_local[i] == lp) return (int)i;
-                throw std::runtime_error("scheduler bug: target bit is not a register bit");
+                const int r = reg_of(tm.local_of[lay.phys(wire)]);
+                if (r < 0) throw std::runtime_error("scheduler bug: target bit is not a register bit");
+                return r;
             };
             std::vector<cd> mat = a.mat;
-            if (a.tw.size() == 1) {
-                op.type = QV_OP_DENSE1;
-                op.rb0 = (uint8_t)rb_of(a.tw[0]);
-            } else {
-                op.type = QV_OP_DENSE2;
-                int r0 = rb_of(a.tw[0]), r1 = rb_of(a.tw[1]);
+            int r0 = rb_of(a.tw[0]), r1 = -1;
+            if (a.tw.size() == 2) {
+                r1 = rb_of(a.tw[1]);
                 if (r0 > r1) {   // matrix index bit 0 must be the lower register bit
                     std::swap(r0, r1);
                     static const int sw[4] = {0, 2, 1, 3};
                     for (int r = 0; r < 4; r++)
                         for (int c = 0; c < 4; c++) mat[sw[r] * 4 + sw[c]] = a.mat[r * 4 + c];
                 }
-                op.rb0 = (uint8_t)r0;
-                op.rb1 = (uint8_t)r1;
             }
             bool real = true;
             for (const cd& e : mat)
                 if (e.imag() != 0.0) real = false;
-            if (real) op.flags |= QV_F_REAL;
+            u.kind = (uint8_t)(r1 < 0 ? QV_K_DENSE1 + 2 * r0 + (real ? 0 : 1) : QV_K_DENSE2 + 2 * pair_index[r0][r1] + (real ? 0 : 1));
+            uint32_t slot_ok = 0xffffu;
+            QvPred pred{};
             for (int wq = 0; wq < 64; wq++) {
                 if (!(a.cmask >> wq & 1)) continue;
                 const bool one = a.cval >> wq & 1;
                 const int b = lay.phys(wq);
-                if (tm.local_of[b] >= 0) {
-                    op.flags |= QV_F_CTRL_LOCAL;
-                    op.cm_local |= 1u << tm.local_of[b];
-                    if (one) op.cv_local |= 1u << tm.local_of[b];
+                const int lp = tm.local_of[b];
+                if (lp >= 0) {
+                    u.flags |= QV_UF_CTRL;
+                    const int r = reg_of(lp);
+                    if (r >= 0) {
+                        for (uint32_t sl = 0; sl < QV_MAX_SLOTS; sl++)
+                            if (((sl >> r) & 1u) != (one ? 1u : 0u)) slot_ok &= ~(1u << sl);
+                    } else {
+                        u.cm |= 1u << gpos_of(lp);
+                        if (one) u.cv |= 1u << gpos_of(lp);
+                    }
                 } else {
-                    op.flags |= QV_F_CTRL_EXT;
-                    op.cm_ext |= 1ull << b;
-                    if (one) op.cv_ext |= 1ull << b;
+                    u.flags |= QV_UF_PRED;
+                    pred.mask |= 1ull << b;
+                    if (one) pred.val |= 1ull << b;
                 }
             }
-            op.data_off = (uint32_t)w.mats.size();
+            u.slot_ok = (uint16_t)slot_ok;
+            if (u.flags & QV_UF_PRED) {
+                size_t pi = 0;
+                while (pi < w.preds.size() && !(w.preds[pi].mask == pred.mask && w.preds[pi].val == pred.val)) pi++;
+                if (pi == w.preds.size()) {
+                    if (w.preds.size() >= QV_MAX_PREDS) throw std::length_error("too many external control predicates in a pass");
+                    w.preds.push_back(pred);
+                }
+                u.pred = (uint8_t)pi;
+            }
+            u.data = (uint32_t)(w.mats.size() * sizeof(cd));   // made blob-relative when the blob is laid out
             w.mats.insert(w.mats.end(), mat.begin(), mat.end());
-        } else {
-            op.type = QV_OP_DIAG;
-            uint64_t reg_phys = 0;
-            for (int lp : regpos_local) reg_phys |= 1ull << tm.tilebits[lp];
-            op.data_off = (uint32_t)w.chunks.size();
+            w.uops.push_back(u);
+            continue;
+        }
 
-            // How the tile-local bits `lbits` (index bit i <-> lbits[i]) reach a table / slice index:
-            // register bits through slot_off, the others through lsegs.
-            auto map_local = [&](QvChunk& qc, const std::vector<int>& lbits) {
-                std::vector<int> lsrc, ldst;
-                for (size_t i = 0; i < lbits.size(); i++) {
-                    const int lp = tm.local_of[lbits[i]];
-                    bool is_reg = false;
-                    for (size_t r = 0; r < regpos_local.size(); r++)
-                        if (regpos_local[r] == lp) {
-                            qc.reg_mask |= (uint8_t)(1u << r);
-                            for (uint32_t sl = 0; sl < 8; sl++)
-                                if (sl >> r & 1) qc.slot_off[sl] |= 1u << i;
-                            is_reg = true;
-                        }
-                    if (is_reg) continue;
-                    lsrc.push_back(lp);
-                    ldst.push_back((int)i);
+        // ---------------- a merged diagonal: plan its chunks
+        // 1. choose a gate for every factor: the register bit (if any) that gates most factors of the group
+        const size_t nf = ro.factors.size();
+        std::vector<uint64_t> gates(nf);
+        int cnt[64] = {0};
+        for (size_t i = 0; i < nf; i++) {
+            gates[i] = gating_bits(ro.factors[i]) & reg_phys;
+            for (int b = 0; b < 64; b++)
+                if (gates[i] >> b & 1) cnt[b]++;
+        }
+        std::vector<int> want(nf, -1);
+        for (size_t i = 0; i < nf; i++)
+            for (int b = 0; b < 64; b++)
+                if ((gates[i] >> b & 1) && (want[i] < 0 || cnt[b] > cnt[want[i]])) want[i] = b;
+        // a gate whose factors would leave no other tile-local bit in the index yields a one-entry table:
+        // two or more of those are cheaper as ONE ungated chunk over their gate bits
+        {
+            uint64_t bucket_l[64] = {0};
+            for (size_t i = 0; i < nf; i++)
+                if (want[i] >= 0)
+                    for (int b : ro.factors[i].pos)
+                        if (b != want[i] && tm.local_of[b] >= 0) bucket_l[want[i]] |= 1ull << b;
+            int n_scalar = 0;
+            for (int b = 0; b < 64; b++)
+                if (cnt[b] && bucket_l[b] == 0) {
+                    bool used = false;
+                    for (size_t i = 0; i < nf; i++)
+                        if (want[i] == b) used = true;
+                    if (used) n_scalar++;
                 }
-                std::vector<QvSeg> ls = make_segs(lsrc, ldst);
-                if (ls.size() > QV_CHUNK_SEGS) throw std::runtime_error("scheduler bug: chunk needs too many segments");
-                qc.n_lsegs = (uint8_t)ls.size();
-                std::copy(ls.begin(), ls.end(), qc.lsegs);
-            };
-            // A chunk is gated by register bit r when every table entry with that bit clear is exactly 1.
-            auto detect_gate = [&](QvChunk& qc, const std::vector<const Chunk*>& tabs) {
-                for (size_t r = 0; r < regpos_local.size() && !qc.gate_rb; r++) {
-                    if (!(qc.reg_mask >> r & 1)) continue;
-                    bool all_one = true;
-                    for (const Chunk* c : tabs) {
-                        size_t ibit = 0;
-                        for (size_t i = 0; i < c->bits.size(); i++)
-                            if (tm.local_of[c->bits[i]] == regpos_local[r]) ibit = i;
-                        for (size_t t = 0; t < c->table.size() && all_one; t++)
-                            if (!(t >> ibit & 1) && c->table[t] != cd(1.0, 0.0)) all_one = false;
-                    }
-                    if (all_one) qc.gate_rb = (uint8_t)(r + 1);
+            if (n_scalar >= 2)
+                for (size_t i = 0; i < nf; i++)
+                    if (want[i] >= 0 && bucket_l[want[i]] == 0) want[i] = -1;
+        }
+        // 2. greedy packing: a factor joins the chunk of its gate whose tile-local index grows least;
+        //    external bits do not count (they are frozen per tile when the chunk becomes a slice)
+        std::vector<PlanChunk> plan;
+        for (size_t i = 0; i < nf; i++) {
+            DiagFactor f = want[i] >= 0 ? restrict_to_one(ro.factors[i], want[i]) : ro.factors[i];
+            std::vector<int> L, E;
+            for (int b : f.pos) (tm.local_of[b] >= 0 ? L : E).push_back(b);
+            std::sort(L.begin(), L.end());
+            std::sort(E.begin(), E.end());
+            int best = -1;
+            size_t best_size = 1000;
+            std::vector<int> best_union;
+            for (size_t ci = 0; ci < plan.size(); ci++) {
+                if (plan[ci].gate != want[i]) continue;
+                std::vector<int> u;
+                std::set_union(plan[ci].lbits.begin(), plan[ci].lbits.end(), L.begin(), L.end(), std::back_inserter(u));
+                if (u.size() > QV_MAX_CHUNK_BITS) continue;
+                if (u.size() < best_size) {
+                    best_size = u.size();
+                    best = (int)ci;
+                    best_union.swap(u);
                 }
+            }
+            if (best < 0) {
+                PlanChunk pc;
+                pc.gate = want[i];
+                pc.lbits = L;
+                plan.push_back(std::move(pc));
+                best = (int)plan.size() - 1;
+            } else {
+                plan[best].lbits = best_union;
+            }
+            std::vector<int> eu;
+            std::set_union(plan[best].ebits.begin(), plan[best].ebits.end(), E.begin(), E.end(), std::back_inserter(eu));
+            plan[best].ebits.swap(eu);
+            plan[best].facs.push_back(std::move(f));
+        }
+        // 3. emit
+        // A slice over the index layout `lay_bits` (index bit i <-> physical tile-local bit lay_bits[i]): its
+        // factors are packed into source tables over (a subset of the layout, external bits).
+        auto make_slice = [&](const std::vector<int>& lay_bits, const std::vector<DiagFactor>& facs) -> uint32_t {
+            struct Src {
+                std::vector<int> l, e;
+                std::vector<DiagFactor> facs;
             };
-            auto emit_global = [&](const Chunk& c) {
-                QvChunk qc{};
-                qc.table_off = (uint32_t)w.tables.size();
-                w.tables.insert(w.tables.end(), c.table.begin(), c.table.end());
-                // table index bit i <-> c.bits[i] (ascending physical); local and external bits interleave
-                std::vector<int> lsrc, ldst, esrc, edst;
-                for (size_t i = 0; i < c.bits.size(); i++) {
-                    const int b = c.bits[i];
-                    if (tm.local_of[b] >= 0) {
-                        bool is_reg = false;
-                        for (size_t r = 0; r < regpos_local.size(); r++)
-                            if (regpos_local[r] == tm.local_of[b]) {
-                                qc.reg_mask |= (uint8_t)(1u << r);
-                                for (uint32_t sl = 0; sl < 8; sl++)
-                                    if (sl >> r & 1) qc.slot_off[sl] |= 1u << i;
-                                is_reg = true;
-                            }
-                        if (is_reg) continue;
-                        lsrc.push_back(tm.local_of[b]);
-                        ldst.push_back((int)i);
-                    } else {
-                        esrc.push_back(b);
-                        edst.push_back((int)i);
-                    }
-                }
-                detect_gate(qc, {&c});
-                std::vector<QvSeg> ls = make_segs(lsrc, ldst), es = make_segs(esrc, edst);
-                if (ls.size() > QV_CHUNK_SEGS || es.size() > QV_CHUNK_SEGS)
-                    throw std::runtime_error("scheduler bug: chunk needs too many segments");
-                qc.n_lsegs = (uint8_t)ls.size();
-                qc.n_esegs = (uint8_t)es.size();
-                std::copy(ls.begin(), ls.end(), qc.lsegs);
-                std::copy(es.begin(), es.end(), qc.esegs);
-                w.chunks.push_back(qc);
-            };
-            // SLICE chunk over the local bits `lbits` whose sources are `srcs` (bits = lbits then external bits)
-            auto emit_slice = [&](const std::vector<int>& lbits, const std::vector<Chunk>& srcs) {
-                QvChunk qc{};
-                qc.kind = 1;
-                qc.nl = (uint16_t)lbits.size();
-                qc.table_off = (uint32_t)w.slice_entries;
-                w.slice_entries += (size_t)1 << lbits.size();
-                qc.first_src = (uint16_t)w.sources.size();
-                qc.n_src = (uint16_t)srcs.size();
-                map_local(qc, lbits);
-                std::vector<const Chunk*> tabs;
-                for (const Chunk& c : srcs) {
-                    tabs.push_back(&c);
-                    QvSource src{};
-                    src.table_off = (uint32_t)w.tables.size();
-                    w.tables.insert(w.tables.end(), c.table.begin(), c.table.end());
-                    std::vector<int> esrc, edst;
-                    for (size_t i = lbits.size(); i < c.bits.size(); i++) {
-                        esrc.push_back(c.bits[i]);
-                        edst.push_back((int)(i - lbits.size()));
-                    }
-                    std::vector<QvSeg> es = make_segs(esrc, edst);
-                    if (es.size() > QV_CHUNK_SEGS) throw std::runtime_error("scheduler bug: source needs too many segments");
-                    src.n_esegs = (uint8_t)es.size();
-                    std::copy(es.begin(), es.end(), src.esegs);
-                    w.sources.push_back(src);
-                }
-                detect_gate(qc, tabs);
-                w.chunks.push_back(qc);
-            };
-
-            // 1. split the factors: purely tile-local ones, ones with external bits and few local bits
-            //    (grouped by their exact local bit set), and the rest.
-            std::vector<DiagFactor> local_pool, global_pool;
-            std::vector<std::pair<std::vector<int>, std::vector<DiagFactor>>> ext_groups;
-            for (const DiagFactor& f : ro.factors) {
+            std::vector<Src> srcs;
+            for (const DiagFactor& f : facs) {
                 std::vector<int> L, E;
                 for (int b : f.pos) (tm.local_of[b] >= 0 ? L : E).push_back(b);
                 std::sort(L.begin(), L.end());
-                if (E.empty()) local_pool.push_back(f);
-                else if (L.size() <= 3) {
-                    size_t gi = 0;
-                    while (gi < ext_groups.size() && ext_groups[gi].first != L) gi++;
-                    if (gi == ext_groups.size()) ext_groups.push_back({L, {}});
-                    ext_groups[gi].second.push_back(f);
-                } else global_pool.push_back(f);
-            }
-            // 2. external groups -> one SLICE each: all their tables collapse per tile into 2^|L| entries
-            for (auto& grp : ext_groups) {
-                const std::vector<int>& L = grp.first;
-                if (w.slice_entries + ((size_t)1 << L.size()) > QV_SLICE_ENTRIES ||
-                    w.sources.size() + grp.second.size() > 60000) {
-                    global_pool.insert(global_pool.end(), grp.second.begin(), grp.second.end());
-                    continue;
-                }
-                const size_t cap_ext = 10 - L.size();
-                std::vector<Chunk> srcs;
-                std::vector<std::vector<int>> src_ext;
-                for (const DiagFactor& f : grp.second) {
-                    std::vector<int> fe;
-                    for (int b : f.pos)
-                        if (tm.local_of[b] < 0) fe.push_back(b);
-                    std::sort(fe.begin(), fe.end());
-                    int best = -1;
-                    size_t best_size = 1000;
-                    std::vector<int> best_union;
-                    for (size_t si = 0; si < srcs.size(); si++) {
-                        std::vector<int> u;
-                        std::set_union(src_ext[si].begin(), src_ext[si].end(), fe.begin(), fe.end(), std::back_inserter(u));
-                        if (u.size() > cap_ext) continue;
-                        if (u.size() < best_size) {
-                            best_size = u.size();
-                            best = (int)si;
-                            best_union.swap(u);
-                        }
+                std::sort(E.begin(), E.end());
+                int best = -1;
+                size_t best_size = 1000;
+                std::vector<int> bl, be;
+                for (size_t si = 0; si < srcs.size(); si++) {
+                    std::vector<int> ul, ue;
+                    std::set_union(srcs[si].l.begin(), srcs[si].l.end(), L.begin(), L.end(), std::back_inserter(ul));
+                    std::set_union(srcs[si].e.begin(), srcs[si].e.end(), E.begin(), E.end(), std::back_inserter(ue));
+                    if (ul.size() + ue.size() > QV_MAX_SOURCE_BITS) continue;
+                    if (ul.size() + ue.size() < best_size) {
+                        best_size = ul.size() + ue.size();
+                        best = (int)si;
+                        bl.swap(ul);
+                        be.swap(ue);
                     }
-                    if (best < 0) {
-                        Chunk c;
-                        c.bits = L;
-                        c.bits.insert(c.bits.end(), fe.begin(), fe.end());
-                        c.table.assign((size_t)1 << c.bits.size(), cd(1.0, 0.0));
-                        srcs.push_back(std::move(c));
-                        src_ext.push_back(fe);
-                        best = (int)srcs.size() - 1;
-                    } else if (best_union.size() != src_ext[best].size()) {
-                        std::vector<int> nb = L;
-                        nb.insert(nb.end(), best_union.begin(), best_union.end());
-                        chunk_extend(srcs[best], nb);
-                        src_ext[best] = best_union;
-                    }
-                    chunk_multiply(srcs[best], f);
                 }
-                emit_slice(L, srcs);
+                if (best < 0) {
+                    if (L.size() + E.size() > QV_MAX_SOURCE_BITS) throw std::runtime_error("scheduler bug: diagonal factor too wide");
+                    srcs.push_back(Src{L, E, {}});
+                    best = (int)srcs.size() - 1;
+                } else {
+                    srcs[best].l.swap(bl);
+                    srcs[best].e.swap(be);
+                }
+                srcs[best].facs.push_back(f);
             }
-            // 3. tile-local factors -> chunks of <= 8 bits; small ones are staged as slices (shared-memory
-            //    lookups), big ones stay in global memory (L1-resident) so the slice area is kept for the
-            //    external groups, where the per-tile collapse saves whole lookups
-            for (const Chunk& c : build_chunks(local_pool, reg_phys)) {
-                if (c.table.size() <= 16 && w.slice_entries + c.table.size() <= QV_SLICE_ENTRIES) emit_slice(c.bits, {c});
-                else emit_global(c);
+            const size_t entries = (size_t)1 << lay_bits.size();
+            if (w.slice_entries + entries > QV_SLICE_ENTRIES || w.slices.size() >= QV_MAX_SLICES ||
+                w.sources.size() + srcs.size() > QV_MAX_SOURCES || w.slice_build + entries * srcs.size() > QV_MAX_SLICE_BUILD)
+                throw std::length_error("per-tile slice area exhausted");
+            QvSlice qs{};
+            qs.off = (uint16_t)w.slice_entries;
+            qs.nl = (uint16_t)lay_bits.size();
+            qs.first_src = (uint16_t)w.sources.size();
+            qs.n_src = (uint16_t)srcs.size();
+            for (const Src& sc : srcs) {
+                QvSource qsrc{};
+                // source index = its local bits in slice-layout order, then its external bits
+                std::vector<int> sl_local, lsrc, ldst;
+                for (size_t j = 0; j < lay_bits.size(); j++)
+                    if (std::find(sc.l.begin(), sc.l.end(), lay_bits[j]) != sc.l.end()) {
+                        lsrc.push_back((int)j);
+                        ldst.push_back((int)sl_local.size());
+                        sl_local.push_back(lay_bits[j]);
+                    }
+                if (sl_local.size() != sc.l.size()) throw std::runtime_error("scheduler bug: slice source bit outside the slice layout");
+                std::vector<int> bits = sl_local;
+                bits.insert(bits.end(), sc.e.begin(), sc.e.end());
+                qsrc.nl = (uint8_t)sl_local.size();
+                qsrc.table_off = (uint32_t)w.tables.size();
+                const std::vector<cd> tab = product_table(sc.facs, bits);
+                w.tables.insert(w.tables.end(), tab.begin(), tab.end());
+                std::vector<QvSeg> ls = make_segs(lsrc, ldst);
+                std::vector<int> esrc, edst;
+                for (size_t j = 0; j < sc.e.size(); j++) {
+                    esrc.push_back(sc.e[j]);
+                    edst.push_back((int)j);
+                }
+                std::vector<QvSeg> es = make_segs(esrc, edst);
+                if (ls.size() > QV_CHUNK_SEGS || es.size() > QV_CHUNK_SEGS) throw std::length_error("slice source needs too many segments");
+                qsrc.n_lsegs = (uint8_t)ls.size();
+                qsrc.n_esegs = (uint8_t)es.size();
+                std::copy(ls.begin(), ls.end(), qsrc.lsegs);
+                std::copy(es.begin(), es.end(), qsrc.esegs);
+                w.sources.push_back(qsrc);
             }
-            // 4. everything else: tables in global memory, indexed by local and external bits
-            for (const Chunk& c : build_chunks(global_pool, reg_phys)) emit_global(c);
-            op.n_chunks = (uint32_t)w.chunks.size() - op.data_off;
-            if (getenv("QV_SCHED_DEBUG")) {
-                fprintf(stderr, "  DIAG op: %zu factors (%zu local, %zu ext groups, %zu global) -> %u chunks:", ro.factors.size(),
-                        local_pool.size(), ext_groups.size(), global_pool.size(), op.n_chunks);
-                for (uint32_t c = op.data_off; c < w.chunks.size(); c++)
-                    fprintf(stderr, " [%s nl=%u rm=%u gate=%u src=%u]", w.chunks[c].kind ? "S" : "G", w.chunks[c].nl,
-                            w.chunks[c].reg_mask, w.chunks[c].gate_rb, w.chunks[c].n_src);
-                fprintf(stderr, "\n");
+            w.slice_build += entries * srcs.size();
+            w.slice_entries += entries;
+            w.slices.push_back(qs);
+            return qs.off;
+        };
+        // One diagonal micro-op over the tile-local bits `lbits` (sorted physical), gated by `gate` (or -1).
+        //   facs       : what the table holds (as a slice when as_slice, else a static global-memory table)
+        //   scale_facs : factors with external bits only; their per-tile product (a one-entry slice) is
+        //                multiplied into the looked-up entry (kinds with a single lookup per group only)
+        auto emit_diag = [&](int gate, const std::vector<int>& lbits, const std::vector<DiagFactor>& facs, bool as_slice,
+                             const std::vector<DiagFactor>& scale_facs) {
+            // index layout: non-register tile-local bits (ascending), then register bits
+            std::vector<int> nonreg, regb;
+            for (int b : lbits) (reg_of(tm.local_of[b]) >= 0 ? regb : nonreg).push_back(b);
+            std::vector<int> lay_bits = nonreg;
+            lay_bits.insert(lay_bits.end(), regb.begin(), regb.end());
+            QvUop u{};
+            uint32_t reg_mask = 0;
+            for (size_t j = 0; j < regb.size(); j++) {
+                const int r = reg_of(tm.local_of[regb[j]]);
+                reg_mask |= 1u << r;
+                for (uint32_t sl = 0; sl < QV_MAX_SLOTS; sl++)
+                    if (sl >> r & 1) u.slot_off[sl] |= (uint8_t)(1u << (nonreg.size() + j));
+            }
+            const int gate_r = gate >= 0 ? reg_of(tm.local_of[gate]) : -1;
+            if (gate_r >= 0) u.kind = (uint8_t)((reg_mask ? QV_K_DIAG_GATEDN : QV_K_DIAG_GATED1) + gate_r);
+            else if (reg_mask == 0) u.kind = QV_K_DIAG_COMMON;
+            else if ((reg_mask & (reg_mask - 1)) == 0) {
+                int r = 0;
+                while (!(reg_mask >> r & 1)) r++;
+                u.kind = (uint8_t)(QV_K_DIAG_ONEBIT + r);
+            } else u.kind = QV_K_DIAG_ALL;
+            // index fields over the group counter g
+            std::vector<int> src, dst;
+            for (size_t j = 0; j < nonreg.size(); j++) {
+                src.push_back(gpos_of(tm.local_of[nonreg[j]]));
+                dst.push_back((int)j);
+            }
+            std::vector<QvSeg> sg = make_segs(src, dst);
+            auto field = [](const QvSeg& q) { return (uint32_t)(q.src - q.dst) | ((((1u << q.len) - 1u) << q.dst) << 8); };
+            if (sg.size() > QV_CHUNK_SEGS) throw std::runtime_error("scheduler bug: chunk needs too many segments");
+            if (sg.size() >= 1) u.cm = field(sg[0]);
+            if (sg.size() == 2) {
+                u.cv = field(sg[1]);
+                u.flags |= QV_UF_FIELD2;
+            } else if (sg.size() > 2) {
+                QvSegList sl{};
+                sl.n = (uint32_t)sg.size();
+                std::copy(sg.begin(), sg.end(), sl.segs);
+                u.flags |= QV_UF_GENERIC;
+                u.segs = (uint16_t)w.seglists.size();      // made blob-relative when the blob is laid out
+                w.seglists.push_back(sl);
+            }
+            if (as_slice) {
+                u.flags |= QV_UF_SLICE;
+                u.data = make_slice(lay_bits, facs);
+            } else {
+                u.data = (uint32_t)w.tables.size();
+                const std::vector<cd> tab = product_table(facs, lay_bits);
+                w.tables.insert(w.tables.end(), tab.begin(), tab.end());
+            }
+            if (!scale_facs.empty()) {
+                if (reg_mask) throw std::runtime_error("scheduler bug: scaled diagonal with per-slot lookups");
+                u.flags |= QV_UF_SCALE;
+                u.scale = (uint16_t)make_slice({}, scale_facs);
+            }
+            w.uops.push_back(u);
+            w.n_diag_uops++;
+            if (getenv("QV_SCHED_DEBUG"))
+                fprintf(stderr, "    uop kind=%u gate=%d nonreg=%zu reg=%zu facs=%zu %s scale_facs=%zu\n", (unsigned)u.kind, gate,
+                        nonreg.size(), regb.size(), facs.size(), as_slice ? "SLICE" : "GLOBAL", scale_facs.size());
+        };
+        auto local_bits_of = [&](const std::vector<DiagFactor>& facs) {
+            std::vector<int> bits;
+            for (const DiagFactor& f : facs)
+                for (int b : f.pos)
+                    if (tm.local_of[b] >= 0 && std::find(bits.begin(), bits.end(), b) == bits.end()) bits.push_back(b);
+            std::sort(bits.begin(), bits.end());
+            return bits;
+        };
+        for (PlanChunk& pc : plan) {
+            std::vector<DiagFactor> loc, ext;
+            for (DiagFactor& f : pc.facs) {
+                bool has_ext = false;
+                for (int b : f.pos)
+                    if (tm.local_of[b] < 0) has_ext = true;
+                (has_ext ? ext : loc).push_back(f);
+            }
+            const size_t entries = (size_t)1 << pc.lbits.size();
+            bool any_reg = false;
+            for (int b : pc.lbits)
+                if (reg_of(tm.local_of[b]) >= 0) any_reg = true;
+            if (ext.empty()) {
+                // static table: tiny ones are staged per tile in shared memory, the others stay in global memory (L1-resident)
+                emit_diag(pc.gate, pc.lbits, loc, entries <= 16, {});
+            } else if (loc.empty() || entries <= 32) {
+                emit_diag(pc.gate, pc.lbits, pc.facs, true, {});
+            } else {
+                const std::vector<int> le = local_bits_of(ext);
+                if (le.empty() && !any_reg) {
+                    // static table x per-tile scalar in one micro-op
+                    emit_diag(pc.gate, pc.lbits, loc, false, ext);
+                } else {
+                    emit_diag(pc.gate, local_bits_of(loc), loc, false, {});
+                    emit_diag(pc.gate, le, ext, true, {});
+                }
             }
         }
-        w.ops.push_back(op);
+        if (getenv("QV_SCHED_DEBUG")) fprintf(stderr, "  DIAG group: %zu factors -> %zu chunks (slice entries so far %zu, build %zu)\n", nf, plan.size(), w.slice_entries, w.slice_build);
     }
-    rd.n_ops = (uint32_t)w.ops.size() - rd.first_op;
+    rd.n_uops = (uint32_t)w.uops.size() - rd.first_uop;
     w.rounds.push_back(rd);
+    if (getenv("QV_SCHED_DEBUG")) {
+        fprintf(stderr, " ROUND regpos:");
+        for (int lp : regpos_local) fprintf(stderr, " %d(phys %d)", lp, tm.tilebits[lp]);
+        fprintf(stderr, " uops=%u\n", rd.n_uops);
+    }
 }
 
 // Split the ordered atoms of one pass into register rounds (same greedy + commutation look-ahead
-// as the pass level, one level down: <= QV_REG_BITS target bits per round).
-void build_rounds(BlobWriter& w, const std::vector<const Atom*>& atoms, const TileMap& tm, const Layout& lay) {
-    const int m_max = std::min(QV_REG_BITS, tm.T);
+// as the pass level, one level down: <= reg_bits target bits per round).
+void build_rounds(BlobWriter& w, const std::vector<const Atom*>& atoms, const TileMap& tm, const Layout& lay, int reg_bits) {
+    const int m_max = std::min(reg_bits, tm.T);
     std::vector<const Atom*> pending = atoms;
     while (!pending.empty()) {
         std::vector<const Atom*> deferred;
@@ -602,7 +675,19 @@ void build_rounds(BlobWriter& w, const std::vector<const Atom*>& atoms, const Ti
 
 struct Geometry {
     int n_bits, n_local, T, lmin, rank;
+    int reg_bits;       // 0 = choose per pass (4 for passes that carry many gates, else 3)
 };
+
+// Work estimate of a pass: dense atoms and diagonal atoms it carries.  Passes with many gates run on the
+// 128-thread / 16-amplitudes-per-thread kernel (micro-op decode amortised over twice the amplitudes, fewer
+// rounds); light passes keep the 256-thread kernel, which is the better HBM streamer.
+int choose_reg_bits(const std::vector<const Atom*>& atoms, const Geometry& geo) {
+    if (geo.reg_bits) return geo.reg_bits;
+    if (geo.T != QV_MAX_TILE_BITS) return 3;
+    size_t dense = 0, diag = 0;
+    for (const Atom* a : atoms) (a->kind == Atom::DENSE ? dense : diag)++;
+    return (dense >= 4 || dense + diag >= 12) ? 4 : 3;
+}
 
 // tile_targets: physical bits that must be inside the tile.
 Step build_tile_step(const std::vector<const Atom*>& atoms, uint64_t tile_targets, const Geometry& geo,
@@ -623,11 +708,15 @@ Step build_tile_step(const std::vector<const Atom*>& atoms, uint64_t tile_target
     const uint64_t tile_global = tb & ~local_mask;          // rank bits that vary inside the tile
     const int s = popc(tile_global);
 
+    const int reg_bits = choose_reg_bits(atoms, geo);
+    const int threads_log2 = reg_bits == 4 ? 7 : 8;
     BlobWriter w;
-    build_rounds(w, atoms, tm, lay);
+    build_rounds(w, atoms, tm, lay, reg_bits);
 
     QvPassHeader h{};
     h.T = (uint32_t)tm.T;
+    h.reg_bits = (uint32_t)reg_bits;
+    h.threads_log2 = (uint32_t)threads_log2;
     {
         std::vector<int> src(tm.T), dst(tm.T);
         for (int i = 0; i < tm.T; i++) {
@@ -669,9 +758,9 @@ Step build_tile_step(const std::vector<const Atom*>& atoms, uint64_t tile_target
         h.n_base_segs = (uint32_t)sg.size();
         std::copy(sg.begin(), sg.end(), h.base_segs);
     }
-    for (int i = 0; i < 16; i++) {
+    for (int i = 0; i < 32; i++) {
         uint64_t off = 0;
-        const uint32_t e = (uint32_t)i * QV_THREADS;
+        const uint32_t e = (uint32_t)i << threads_log2;
         for (int t = 0; t < tm.T; t++)
             if (e >> t & 1) off |= 1ull << tm.tilebits[t];
         h.hi_off[i] = off;
@@ -681,37 +770,61 @@ Step build_tile_step(const std::vector<const Atom*>& atoms, uint64_t tile_target
     h.n_local_bits = (uint32_t)geo.n_local;
     h.uses_peers = s > 0 ? 1u : 0u;
     h.n_rounds = (uint32_t)w.rounds.size();
-    h.n_ops = (uint32_t)w.ops.size();
-    h.n_chunks = (uint32_t)w.chunks.size();
+    h.n_uops = (uint32_t)w.uops.size();
+    h.n_diag_uops = (uint32_t)w.n_diag_uops;
+    h.n_ext = (uint32_t)w.exts.size();
+    h.n_sources = (uint32_t)w.sources.size();
+    h.n_slices = (uint32_t)w.slices.size();
+    h.n_slice_entries = (uint32_t)w.slice_entries;
+    h.n_preds = (uint32_t)w.preds.size();
+    std::vector<uint8_t> slice_of(w.slice_entries);
+    for (size_t i = 0; i < w.slices.size(); i++)
+        for (size_t x = 0; x < ((size_t)1 << w.slices[i].nl); x++) slice_of[w.slices[i].off + x] = (uint8_t)i;
     auto align16 = [](size_t x) { return (x + 15) & ~(size_t)15; };
     size_t off = align16(sizeof(QvPassHeader));
     h.off_rounds = (uint32_t)off;
     off = align16(off + w.rounds.size() * sizeof(QvRound));
-    h.off_ops = (uint32_t)off;
-    off = align16(off + w.ops.size() * sizeof(QvOp));
-    h.off_chunks = (uint32_t)off;
-    off = align16(off + w.chunks.size() * sizeof(QvChunk));
+    h.off_uops = (uint32_t)off;
+    off = align16(off + w.uops.size() * sizeof(QvUop));
+    h.off_ext = (uint32_t)off;
+    off = align16(off + w.exts.size() * sizeof(QvExt));
     h.off_sources = (uint32_t)off;
     off = align16(off + w.sources.size() * sizeof(QvSource));
-    h.n_sources = (uint32_t)w.sources.size();
-    h.n_slice_entries = (uint32_t)w.slice_entries;
+    h.off_slices = (uint32_t)off;
+    off = align16(off + w.slices.size() * sizeof(QvSlice));
+    h.off_slice_of = (uint32_t)off;
+    off = align16(off + slice_of.size());
+    h.off_preds = (uint32_t)off;
+    off = align16(off + w.preds.size() * sizeof(QvPred));
+    const size_t off_seglists = off;
+    off = align16(off + w.seglists.size() * sizeof(QvSegList));
     h.off_matrices = (uint32_t)off;
     off = align16(off + w.mats.size() * sizeof(cd));
     h.n_table_entries = (uint32_t)w.tables.size();
     h.blob_bytes = (uint32_t)off;
     if (off > QV_PROG_LARGE_BYTES) throw std::length_error("pass control program too large");
-    if (w.chunks.size() > QV_MAX_PASS_CHUNKS) throw std::length_error("too many diagonal chunks in a pass");
+    for (QvUop& u : w.uops) {
+        if (u.kind < QV_K_DIAG_COMMON) u.data += h.off_matrices;
+        else if (u.flags & QV_UF_GENERIC) u.segs = (uint16_t)(off_seglists + u.segs * sizeof(QvSegList));
+    }
 
     Step st;
     st.kind = Step::TILE;
     st.uses_peers = s > 0;
     st.blob.assign(off, 0);
     std::memcpy(st.blob.data(), &h, sizeof(h));
-    if (!w.rounds.empty()) std::memcpy(st.blob.data() + h.off_rounds, w.rounds.data(), w.rounds.size() * sizeof(QvRound));
-    if (!w.ops.empty()) std::memcpy(st.blob.data() + h.off_ops, w.ops.data(), w.ops.size() * sizeof(QvOp));
-    if (!w.chunks.empty()) std::memcpy(st.blob.data() + h.off_chunks, w.chunks.data(), w.chunks.size() * sizeof(QvChunk));
-    if (!w.sources.empty()) std::memcpy(st.blob.data() + h.off_sources, w.sources.data(), w.sources.size() * sizeof(QvSource));
-    if (!w.mats.empty()) std::memcpy(st.blob.data() + h.off_matrices, w.mats.data(), w.mats.size() * sizeof(cd));
+    auto put = [&](size_t at, const void* src, size_t bytes) {
+        if (bytes) std::memcpy(st.blob.data() + at, src, bytes);
+    };
+    put(h.off_rounds, w.rounds.data(), w.rounds.size() * sizeof(QvRound));
+    put(h.off_uops, w.uops.data(), w.uops.size() * sizeof(QvUop));
+    put(h.off_ext, w.exts.data(), w.exts.size() * sizeof(QvExt));
+    put(h.off_sources, w.sources.data(), w.sources.size() * sizeof(QvSource));
+    put(h.off_slices, w.slices.data(), w.slices.size() * sizeof(QvSlice));
+    put(h.off_slice_of, slice_of.data(), slice_of.size());
+    put(h.off_preds, w.preds.data(), w.preds.size() * sizeof(QvPred));
+    put(off_seglists, w.seglists.data(), w.seglists.size() * sizeof(QvSegList));
+    put(h.off_matrices, w.mats.data(), w.mats.size() * sizeof(cd));
     st.tables = std::move(w.tables);
     st.n_gates = (int)atoms.size();
     return st;
@@ -753,6 +866,8 @@ Tape compile(const std::vector<Gate>& gates, int n_bits, const CompileOptions& o
     geo.n_bits = n_bits;
     geo.n_local = opt.n_local_bits > 0 ? opt.n_local_bits : n_bits;
     geo.rank = opt.rank;
+    geo.reg_bits = opt.reg_bits;
+    if (opt.reg_bits != 0 && opt.reg_bits != 3 && opt.reg_bits != 4) throw std::runtime_error("reg_bits must be 0 (auto), 3 or 4");
     geo.T = std::min(opt.tile_bits, geo.n_local);
     if (geo.n_local > n_bits) throw std::runtime_error("n_local_bits exceeds the qubit count");
     const int g_bits = n_bits - geo.n_local;
@@ -929,7 +1044,7 @@ Tape compile(const std::vector<Gate>& gates, int n_bits, const CompileOptions& o
             // conservative size of the atom in the control program (round + op + chunk + matrix)
             // rough size of the atom in the control program; diagonals merge into shared chunks, so they
             // are cheap -- the real size is checked when the pass is built (see the retry below)
-            const size_t need_bytes = a->kind == Atom::DENSE ? sizeof(QvOp) + a->mat.size() * sizeof(cd) + 32 : 16;
+            const size_t need_bytes = a->kind == Atom::DENSE ? sizeof(QvUop) + a->mat.size() * sizeof(cd) + 32 : 16;
             if (!blocked && est_bytes + need_bytes > QV_PROG_LARGE_BYTES - 2048) blocked = true;
             if (!blocked) {
                 if (a->kind == Atom::BIG) blocked = true;
@@ -1010,7 +1125,8 @@ std::string describe(const Tape& t) {
         QvPassHeader h;
         std::memcpy(&h, s.blob.data(), sizeof(h));
         os << "  [" << i << "] " << (s.is_remap ? "REMAP" : (s.uses_peers ? "PEER" : "TILE")) << " T=" << h.T
-           << " atoms=" << s.n_gates << " rounds=" << h.n_rounds << " ops=" << h.n_ops << " chunks=" << h.n_chunks << " sources=" << h.n_sources << " slice_entries=" << h.n_slice_entries
+           << " m=" << h.reg_bits << " atoms=" << s.n_gates << " rounds=" << h.n_rounds << " uops=" << h.n_uops << " diag_uops=" << h.n_diag_uops
+           << " slices=" << h.n_slices << " sources=" << h.n_sources << " slice_entries=" << h.n_slice_entries
            << " bytes=" << h.blob_bytes << " tables=" << h.n_table_entries << " tilebits=";
         for (uint32_t k = 0; k < h.n_tile_segs; k++)
             os << (int)h.tile_segs[k].dst << "+" << (int)h.tile_segs[k].len << (k + 1 < h.n_tile_segs ? "," : "");

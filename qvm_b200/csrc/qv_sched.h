@@ -32,12 +32,13 @@ struct CompileOptions {
     bool absorb_swaps = false;   // true: exact SWAP gates only relabel qubits (l2p changes)
     int n_local_bits = 0;        // log2(amplitudes on this device); 0 = n_bits (single device)
     int rank = 0;                // value of the physical bits >= n_local_bits on this device
+    int reg_bits = 0;            // amplitudes per thread per round = 2^reg_bits: 3, 4, or 0 = chosen per pass
     bool remap_pull = false;     // remaps as out-of-place pulls into the alternate buffer (needs 2x shard memory)
 };
 
 struct Step {
     enum Kind { TILE = 0, BIG = 1, REMAP = 2 } kind = TILE;
-    std::vector<uint8_t> blob;   // TILE: QvPassHeader followed by rounds/ops/chunks/matrices (<= QV_PROG_LARGE_BYTES)
+    std::vector<uint8_t> blob;   // TILE: QvPassHeader followed by rounds/micro-ops/descriptors/matrices (<= QV_PROG_LARGE_BYTES)
     std::vector<cd> tables;      // TILE: diagonal factor tables (global memory)
     QvBigGate big{};             // BIG
     QvRemap remap{};             // REMAP (pull remap into the alternate buffer; all ranks flip afterwards)

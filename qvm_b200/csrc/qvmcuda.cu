@@ -116,17 +116,18 @@ int tile_grid(const qvmcuda_state* s, uint64_t n_tiles) {
     return (int)(n_tiles < cap ? n_tiles : cap);
 }
 
-template <typename PROG, bool PEERS, bool FULL>
+template <typename PROG, bool PEERS, bool FULL, int M>
 int launch_tile_t(qvmcuda_state* s, const qv::Step& st, const QvPassHeader& h, const uint8_t* d_tables) {
     static std::atomic<bool> attr_set{false};
     if (!attr_set.exchange(true)) {
-        CK(cudaFuncSetAttribute(qv_tile_kernel<PROG, PEERS, FULL>, cudaFuncAttributeMaxDynamicSharedMemorySize, 65536));
-        CK(cudaFuncSetAttribute(qv_tile_kernel<PROG, PEERS, FULL>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+        CK(cudaFuncSetAttribute(qv_tile_kernel<PROG, PEERS, FULL, M>, cudaFuncAttributeMaxDynamicSharedMemorySize, 65536));
+        CK(cudaFuncSetAttribute(qv_tile_kernel<PROG, PEERS, FULL, M>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
     }
     static thread_local PROG prog;   // 28 KiB: keep it off the stack
     std::memcpy(prog.bytes, st.blob.data(), st.blob.size());
     const size_t smem = (size_t)sizeof(qvc) << h.T;
-    qv_tile_kernel<PROG, PEERS, FULL><<<tile_grid(s, h.n_tiles), QV_THREADS, smem, s->stream>>>(prog, s->peers, (const qvc*)d_tables);
+    const int threads = M == 4 ? QV_THREADS_WIDE : QV_THREADS;
+    qv_tile_kernel<PROG, PEERS, FULL, M><<<tile_grid(s, h.n_tiles), threads, smem, s->stream>>>(prog, s->peers, (const qvc*)d_tables);
     g_launches++;
     CK(cudaGetLastError());
     return 0;
@@ -135,8 +136,14 @@ int launch_tile_t(qvmcuda_state* s, const qv::Step& st, const QvPassHeader& h, c
 template <typename PROG>
 int launch_tile_p(qvmcuda_state* s, const qv::Step& st, const QvPassHeader& h, const uint8_t* d_tables) {
     const bool full = h.T == QV_MAX_TILE_BITS;
-    if (h.uses_peers) return full ? launch_tile_t<PROG, true, true>(s, st, h, d_tables) : launch_tile_t<PROG, true, false>(s, st, h, d_tables);
-    return full ? launch_tile_t<PROG, false, true>(s, st, h, d_tables) : launch_tile_t<PROG, false, false>(s, st, h, d_tables);
+    if (h.reg_bits == 4) {
+        // the 16-amplitudes-per-thread kernel exists for full tiles only (the scheduler never asks otherwise)
+        if (!full || h.threads_log2 != 7) return fail("4 register bits need a full 12-bit tile");
+        return h.uses_peers ? launch_tile_t<PROG, true, true, 4>(s, st, h, d_tables) : launch_tile_t<PROG, false, true, 4>(s, st, h, d_tables);
+    }
+    if (h.reg_bits != 3 || h.threads_log2 != 8) return fail("malformed pass header");
+    if (h.uses_peers) return full ? launch_tile_t<PROG, true, true, 3>(s, st, h, d_tables) : launch_tile_t<PROG, true, false, 3>(s, st, h, d_tables);
+    return full ? launch_tile_t<PROG, false, true, 3>(s, st, h, d_tables) : launch_tile_t<PROG, false, false, 3>(s, st, h, d_tables);
 }
 
 int launch_tile(qvmcuda_state* s, const qv::Step& st, const uint8_t* d_tables) {
@@ -212,6 +219,8 @@ qv::CompileOptions make_options(const qvmcuda_state* s, uint32_t flags) {
     qv::CompileOptions opt;
     opt.fuse = (flags & QVMCUDA_FUSE) != 0;
     opt.absorb_swaps = (flags & QVMCUDA_ABSORB_SWAPS) != 0;
+    static const int forced_reg_bits = getenv("QVMCUDA_REG_BITS") ? atoi(getenv("QVMCUDA_REG_BITS")) : 0;   // profiling knob: 3 or 4
+    if (forced_reg_bits == 3 || forced_reg_bits == 4) opt.reg_bits = forced_reg_bits;
     if (s) {
         opt.rank = s->rank;
         opt.n_local_bits = s->n_bits;

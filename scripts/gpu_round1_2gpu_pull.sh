@@ -1,0 +1,11 @@
+#!/bin/bash
+# 2-GPU session: sharded parity over NVLink in both remap modes + sharded bench, pull vs in-place remaps
+set -x
+mkdir -p gpurun_out
+timeout 900 python -m pytest tests/test_gpu_sharded.py -x -q -m gpu > gpurun_out/pytest_2gpu_pull.log 2>&1; echo "pytest rc=$?" >> gpurun_out/pytest_2gpu_pull.log
+tail -30 gpurun_out/pytest_2gpu_pull.log
+RUN="python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1"
+QVM_DIST_TRACE=1 timeout 600 $RUN --master-port 29531 bench.py --gpus 2 --steps 3 --warmup 2 > gpurun_out/bench_2gpu_pull.log 2>&1; echo "bench rc=$?"
+grep -E '^\{|dist\]' gpurun_out/bench_2gpu_pull.log | tail -30
+QVM_REMAP_INPLACE=1 QVM_DIST_TRACE=1 timeout 600 $RUN --master-port 29532 bench.py --gpus 2 --steps 3 --warmup 2 > gpurun_out/bench_2gpu_inplace.log 2>&1; echo "bench rc=$?"
+grep -E '^\{|dist\]' gpurun_out/bench_2gpu_inplace.log | tail -30

@@ -49,8 +49,10 @@ def flatten_circuit(circ):
     return ks, qf, np.ascontiguousarray(mf)
 
 
-def run_emulator(psi, n, circ, fuse=True, tile_bits=12, absorb_swaps=False):
+def run_emulator(psi, n, circ, fuse=True, tile_bits=12, absorb_swaps=False, reg_bits=0):
+    """reg_bits: 3 / 4 force the 8- / 16-amplitudes-per-thread round format, 0 = the scheduler's own choice."""
     ks, qf, mf = flatten_circuit(circ)
+    emulator().qvtest_set_reg_bits(int(reg_bits))
     desc = C.create_string_buffer(1 << 16)
     l2p = np.arange(n, dtype=np.int32)
     p = lambda a: a.ctypes.data_as(C.c_void_p)
@@ -128,7 +130,7 @@ def random_circuit(n, n_gates, rng, max_dense=3):
     return circ
 
 
-def run_emulator_sharded(psi, n, world, circ, fuse=True, tile_bits=12, absorb_swaps=False, remap_pull=False):
+def run_emulator_sharded(psi, n, world, circ, fuse=True, tile_bits=12, absorb_swaps=False, remap_pull=False, reg_bits=0):
     """Emulates `world` ranks (shards back to back in psi) running the sharded schedule; remap_pull selects
     out-of-place pull remaps into alternate shard buffers instead of in-place peer passes."""
     ks, qf, mf = flatten_circuit(circ)
@@ -138,6 +140,7 @@ def run_emulator_sharded(psi, n, world, circ, fuse=True, tile_bits=12, absorb_sw
     emu = emulator()
     emu.qvtest_run_sharded.restype = C.c_int
     emu.qvtest_set_remap_pull(int(remap_pull))
+    emu.qvtest_set_reg_bits(int(reg_bits))
     rc = emu.qvtest_run_sharded(p(psi), n, world, len(circ), p(ks), p(qf), p(mf), int(fuse), tile_bits,
                                 int(absorb_swaps), p(l2p), desc, len(desc))
     if rc < 0:

@@ -7,6 +7,7 @@
 // (`pytest -m "not gpu"`).  It is never linked into libqvmcuda and is not a
 // fallback: the product fails loudly without a GPU.
 #include <cstring>
+#include <stdexcept>
 #include <string>
 #include <vector>
 
@@ -21,48 +22,69 @@ void run_tile_step(qvc* const* peers, const qv::Step& st) {
     QvPassHeader h;
     std::memcpy(&h, blob, sizeof(h));
     const QvRound* rounds = (const QvRound*)(blob + h.off_rounds);
-    const QvOp* ops = (const QvOp*)(blob + h.off_ops);
-    const QvChunk* chunks = (const QvChunk*)(blob + h.off_chunks);
+    const QvUop* uops = (const QvUop*)(blob + h.off_uops);
+    const QvExt* exts = (const QvExt*)(blob + h.off_ext);
     const QvSource* sources = (const QvSource*)(blob + h.off_sources);
-    const qvc* mats = (const qvc*)(blob + h.off_matrices);
+    const QvSlice* slices = (const QvSlice*)(blob + h.off_slices);
+    const uint8_t* slice_of = blob + h.off_slice_of;
+    const QvPred* preds = (const QvPred*)(blob + h.off_preds);
     const qvc* tables = (const qvc*)st.tables.data();
     const uint32_t tile_n = 1u << h.T;
+    const uint32_t threads = 1u << h.threads_log2;
     const uint64_t local_mask = (1ull << h.n_local_bits) - 1ull;
     std::vector<qvc> smem(tile_n);
-    std::vector<uint32_t> ext(h.n_chunks ? h.n_chunks : 1);
-    std::vector<qvc> slices(QV_SLICE_ENTRIES);
+    std::vector<uint32_t> s_ext(QV_MAX_EXT), s_srcext(QV_MAX_SOURCES);
+    std::vector<uint8_t> s_pred(QV_MAX_PREDS);
+    std::vector<qvc> s_slice(QV_SLICE_ENTRIES);
+    if (h.n_ext > QV_MAX_EXT || h.n_sources > QV_MAX_SOURCES || h.n_preds > QV_MAX_PREDS || h.n_slice_entries > QV_SLICE_ENTRIES ||
+        h.n_slices > QV_MAX_SLICES)
+        throw std::runtime_error("emulator: per-tile table limits exceeded");
     auto addr = [&](uint64_t p) { return peers[p >> h.n_local_bits] + (p & local_mask); };
+    // the split address computation of the kernel: (base | gather(tid)) | hi_off[i] for e = tid + threads*i
+    auto phys = [&](uint64_t base, uint32_t e) {
+        return base | qv_gather(e & (threads - 1), h.tile_segs, h.n_tile_segs) | h.hi_off[e >> h.threads_log2];
+    };
     for (uint64_t tile = 0; tile < h.n_tiles; tile++) {
         const uint64_t base = qv_gather(tile, h.base_segs, h.n_base_segs) | h.fixed_bits;
-        for (uint32_t c = 0; c < h.n_chunks; c++) ext[c] = (uint32_t)qv_gather(base, chunks[c].esegs, chunks[c].n_esegs);
-        for (uint32_t c = 0; c < h.n_chunks; c++)
-            if (chunks[c].kind)
-                for (uint32_t x = 0; x < (1u << chunks[c].nl); x++)
-                    slices[chunks[c].table_off + x] = qv_slice_entry(chunks[c], sources, tables, base, x);
-        for (uint32_t e = 0; e < tile_n; e++) {
-            const uint64_t p = base | qv_gather(e & (QV_THREADS - 1), h.tile_segs, h.n_tile_segs) | h.hi_off[e / QV_THREADS];
-            smem[qv_swz(e)] = *addr(p);
+        for (uint32_t i = 0; i < h.n_ext; i++) s_ext[i] = (uint32_t)qv_gather(base, exts[i].esegs, exts[i].n_esegs) << exts[i].shift;
+        for (uint32_t i = 0; i < h.n_sources; i++)
+            s_srcext[i] = (uint32_t)qv_gather(base, sources[i].esegs, sources[i].n_esegs) << sources[i].nl;
+        for (uint32_t i = 0; i < h.n_preds; i++) s_pred[i] = (base & preds[i].mask) == preds[i].val ? 1 : 0;
+        for (uint32_t f = 0; f < h.n_slice_entries; f++) {
+            const QvSlice& sl = slices[slice_of[f]];
+            s_slice[f] = qv_slice_entry(sl, sources, s_srcext.data(), tables, f - sl.off);
         }
+        for (uint32_t e = 0; e < tile_n; e++) smem[qv_swz(e)] = *addr(phys(base, e));
         for (uint32_t r = 0; r < h.n_rounds; r++) {
             const QvRound& rd = rounds[r];
+            if (rd.m > h.reg_bits) throw std::runtime_error("emulator: round uses more register bits than the pass declares");
             const uint32_t ngroups = tile_n >> rd.m;
             for (uint32_t g = 0; g < ngroups; g++) {
                 uint32_t e0 = g;
                 for (uint32_t j = 0; j < rd.m; j++) e0 = qv_insert_zero(e0, rd.regpos[j]);
                 const uint32_t se0 = qv_swz(e0);
-                qvc a[8];
-                for (uint32_t s = 0; s < 8; s++) {
-                    if (s < (1u << rd.m)) a[s] = smem[se0 ^ rd.slot_xor[s]];
-                    else { a[s].x = 0.0; a[s].y = 0.0; }
+                if (h.reg_bits <= 3) {      // the 8-slot instantiation, as the 256-thread kernel
+                    qvc a[8];
+                    for (uint32_t s = 0; s < 8; s++) {
+                        if (s < (1u << rd.m)) a[s] = smem[se0 ^ rd.slot_xor[s]];
+                        else { a[s].x = 0.0; a[s].y = 0.0; }
+                    }
+                    for (uint32_t u = rd.first_uop; u < rd.first_uop + rd.n_uops; u++)
+                        qv_run_uop<8>(a, uops[u], g, blob, tables, s_slice.data(), s_ext.data(), s_pred.data());
+                    for (uint32_t s = 0; s < (1u << rd.m); s++) smem[se0 ^ rd.slot_xor[s]] = a[s];
+                } else {                    // the 16-slot instantiation, as the 128-thread kernel
+                    qvc a[16];
+                    for (uint32_t s = 0; s < 16; s++) {
+                        if (s < (1u << rd.m)) a[s] = smem[se0 ^ rd.slot_xor[s]];
+                        else { a[s].x = 0.0; a[s].y = 0.0; }
+                    }
+                    for (uint32_t u = rd.first_uop; u < rd.first_uop + rd.n_uops; u++)
+                        qv_run_uop<16>(a, uops[u], g, blob, tables, s_slice.data(), s_ext.data(), s_pred.data());
+                    for (uint32_t s = 0; s < (1u << rd.m); s++) smem[se0 ^ rd.slot_xor[s]] = a[s];
                 }
-                qv_apply_round(a, rd, ops, chunks, mats, tables, ext.data(), slices.data(), e0, base);
-                for (uint32_t s = 0; s < (1u << rd.m); s++) smem[se0 ^ rd.slot_xor[s]] = a[s];
             }
         }
-        for (uint32_t e = 0; e < tile_n; e++) {
-            const uint64_t p = base | qv_gather(e & (QV_THREADS - 1), h.tile_segs, h.n_tile_segs) | h.hi_off[e / QV_THREADS];
-            *addr(p) = smem[qv_swz(e)];
-        }
+        for (uint32_t e = 0; e < tile_n; e++) *addr(phys(base, e)) = smem[qv_swz(e)];
     }
 }
 
@@ -118,10 +140,12 @@ void run_remap_step(std::vector<qvc*>& cur, std::vector<qvc*>& alt, int n_local,
 }
 
 bool g_remap_pull = false;
+int g_reg_bits = 0;
 
 }  // namespace
 
 extern "C" void qvtest_set_remap_pull(int on) { g_remap_pull = on != 0; }
+extern "C" void qvtest_set_reg_bits(int m) { g_reg_bits = m; }
 
 extern "C" int qvtest_run(double* psi, int n_bits, int n_gates, const int* ks, const int* qubits_flat,
                           const double* mats_flat, int fuse, int tile_bits, int absorb_swaps,
@@ -142,6 +166,7 @@ extern "C" int qvtest_run(double* psi, int n_bits, int n_gates, const int* ks, c
         opt.fuse = fuse != 0;
         opt.tile_bits = tile_bits;
         opt.absorb_swaps = absorb_swaps != 0;
+        opt.reg_bits = g_reg_bits;
         std::vector<int> l2p;
         if (l2p_inout) l2p.assign(l2p_inout, l2p_inout + n_bits);
         qv::Tape tape = qv::compile(gates, n_bits, opt, l2p);
@@ -195,6 +220,7 @@ extern "C" int qvtest_run_sharded(double* psi, int n_bits, int world, int n_gate
             opt.fuse = fuse != 0;
             opt.tile_bits = tile_bits;
             opt.absorb_swaps = absorb_swaps != 0;
+            opt.reg_bits = g_reg_bits;
             opt.n_local_bits = n_local;
             opt.rank = r;
             opt.remap_pull = g_remap_pull;
@@ -272,6 +298,7 @@ extern "C" void* qvtest_shard_compile(int n_bits, int world, int rank, int n_gat
         opt.fuse = fuse != 0;
         opt.tile_bits = tile_bits;
         opt.absorb_swaps = absorb_swaps != 0;
+        opt.reg_bits = g_reg_bits;
         opt.n_local_bits = n_bits - gb;
         opt.rank = rank;
         std::vector<int> l2p(l2p_in, l2p_in + n_bits);

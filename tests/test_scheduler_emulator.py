@@ -9,30 +9,32 @@ from qvm_b200 import circuits as CC
 
 @pytest.mark.parametrize("n,tile_bits", [(1, 12), (2, 12), (3, 12), (5, 12), (8, 4), (9, 5), (10, 6), (13, 12), (15, 12)])
 @pytest.mark.parametrize("fuse", [True, False])
-def test_qft_matches_oracle(n, tile_bits, fuse):
+@pytest.mark.parametrize("reg_bits", [3, 4])
+def test_qft_matches_oracle(n, tile_bits, fuse, reg_bits):
     circ = CC.qft_circuit(range(n))
     a = rand_state(n)
     b = a.copy()
-    steps, desc, _ = run_emulator(a, n, circ, fuse=fuse, tile_bits=tile_bits)
+    steps, desc, _ = run_emulator(a, n, circ, fuse=fuse, tile_bits=tile_bits, reg_bits=reg_bits)
     run_oracle(b, circ)
     assert_close(a, b)
     if not fuse:
         assert steps >= len(circ)
 
 
-@pytest.mark.parametrize("seed", range(12))
+@pytest.mark.parametrize("seed", range(24))
 def test_random_circuits_match_oracle(seed):
+    reg_bits = (3, 4, 0)[seed % 3]
     rng = np.random.default_rng(1000 + seed)
     n = int(rng.integers(1, 14))
     tile_bits = int(rng.integers(3, 13))
     circ = random_circuit(n, int(rng.integers(5, 60)), rng, max_dense=4)
     a = rand_state(n, seed)
     b = a.copy()
-    run_emulator(a, n, circ, fuse=True, tile_bits=tile_bits)
+    run_emulator(a, n, circ, fuse=True, tile_bits=tile_bits, reg_bits=reg_bits)
     run_oracle(b, circ)
     assert_close(a, b)
     c = rand_state(n, seed)
-    run_emulator(c, n, circ, fuse=False, tile_bits=tile_bits)
+    run_emulator(c, n, circ, fuse=False, tile_bits=tile_bits, reg_bits=reg_bits)
     assert_close(c, b)
 
 
