@@ -57,7 +57,6 @@ qv_tile_kernel(const __grid_constant__ PROG prog, const __grid_constant__ QvPeer
     extern __shared__ __align__(16) uint8_t qv_smem_raw[];
     qvc* tile = reinterpret_cast<qvc*>(qv_smem_raw);
     __shared__ qvc s_slice[QV_SLICE_ENTRIES];
-    __shared__ uint32_t s_ext[QV_MAX_EXT];
     __shared__ uint32_t s_srcext[QV_MAX_SOURCES];
     __shared__ uint8_t s_pred[QV_MAX_PREDS];
 
@@ -74,7 +73,6 @@ qv_tile_kernel(const __grid_constant__ PROG prog, const __grid_constant__ QvPeer
     const uint32_t n_rounds = h->n_rounds;
     const QvRound* rounds = reinterpret_cast<const QvRound*>(blob + h->off_rounds);
     const QvUop* uops = reinterpret_cast<const QvUop*>(blob + h->off_uops);
-    const QvExt* exts = reinterpret_cast<const QvExt*>(blob + h->off_ext);
     const QvSource* sources = reinterpret_cast<const QvSource*>(blob + h->off_sources);
     const QvSlice* slices = reinterpret_cast<const QvSlice*>(blob + h->off_slices);
     const uint8_t* slice_of = blob + h->off_slice_of;
@@ -87,6 +85,12 @@ qv_tile_kernel(const __grid_constant__ PROG prog, const __grid_constant__ QvPeer
     // qv_swz only mixes bits 3..5 into bits 0..2, so the slot of tid + THREADS*i is qv_swz(tid) + THREADS*i
     qvc* const my_tile = tile + qv_swz(tid);
     qvc* const own = peers.base[PEERS ? 0 : (fixed_bits >> n_local) & (QV_MAX_PEERS - 1)];
+    // store permutation (trailing X / CNOT / SWAP gates): slot read for destination e = tid + THREADS*i
+    const bool store_perm = h->store_perm != 0;
+    uint32_t st_lo = h->st_const;
+    if (store_perm)
+        for (uint32_t k = 0; k < T; k++)
+            if (tid >> k & 1) st_lo ^= h->st_col[k];
 
     for (uint64_t t = blockIdx.x; t < n_tiles; t += gridDim.x) {
         const uint64_t base = qv_gather(t, h->base_segs, h->n_base_segs) | fixed_bits;
@@ -112,12 +116,10 @@ qv_tile_kernel(const __grid_constant__ PROG prog, const __grid_constant__ QvPeer
         }
         asm volatile("cp.async.commit_group;" ::: "memory");
 
-        // ---- per-tile tables, built while the copies fly: external index parts, control predicates,
+        // ---- per-tile tables, built while the copies fly: source offsets, control predicates,
         //      then the diagonal slices (all factors whose external bits are constant over this tile
         //      collapse into small shared-memory tables)
-        if (h->n_ext | h->n_sources | h->n_preds) {
-            for (uint32_t i = tid; i < h->n_ext; i += THREADS)
-                s_ext[i] = (uint32_t)qv_gather(base, exts[i].esegs, exts[i].n_esegs) << exts[i].shift;
+        if (h->n_sources | h->n_preds) {
             for (uint32_t i = tid; i < h->n_sources; i += THREADS)
                 s_srcext[i] = (uint32_t)qv_gather(base, sources[i].esegs, sources[i].n_esegs) << sources[i].nl;
             for (uint32_t i = tid; i < h->n_preds; i += THREADS)
@@ -152,7 +154,7 @@ qv_tile_kernel(const __grid_constant__ PROG prog, const __grid_constant__ QvPeer
                     else { a[s].x = 0.0; a[s].y = 0.0; }
                 }
                 for (uint32_t u = rd.first_uop; u < u_end; u++)
-                    qv_run_uop<NS>(a, uops[u], g, blob, tables, s_slice, s_ext, s_pred);
+                    qv_run_uop<NS>(a, uops[u], g, blob, tables, s_slice, s_pred);
 #pragma unroll
                 for (int s = 0; s < NS; s++)
                     if (FULL || (uint32_t)s < nslots) tile[se0 ^ rd.slot_xor[s]] = a[s];
@@ -161,12 +163,19 @@ qv_tile_kernel(const __grid_constant__ PROG prog, const __grid_constant__ QvPeer
         }
 
         // ---- shared memory -> HBM
-        if (FULL) {
+        if (FULL && !store_perm) {
 #pragma unroll
             for (int i = 0; i < ITERS; i++) {
                 const uint64_t p = pbase | h->hi_off[i];
                 qvc* dst = PEERS ? peers.base[(p >> n_local) & (QV_MAX_PEERS - 1)] + (p & local_mask) : own + p;
                 qv_st_stream(dst, my_tile[i * THREADS]);
+            }
+        } else if (FULL) {
+#pragma unroll
+            for (int i = 0; i < ITERS; i++) {
+                const uint64_t p = pbase | h->hi_off[i];
+                qvc* dst = PEERS ? peers.base[(p >> n_local) & (QV_MAX_PEERS - 1)] + (p & local_mask) : own + p;
+                qv_st_stream(dst, tile[st_lo ^ h->st_hi[i]]);
             }
         } else {
             for (uint32_t i = 0; i < iters; i++) {
@@ -174,7 +183,7 @@ qv_tile_kernel(const __grid_constant__ PROG prog, const __grid_constant__ QvPeer
                 if (e < tile_n) {
                     const uint64_t p = pbase | h->hi_off[i];
                     qvc* dst = PEERS ? peers.base[(p >> n_local) & (QV_MAX_PEERS - 1)] + (p & local_mask) : own + p;
-                    qv_st_stream(dst, my_tile[i * THREADS]);
+                    qv_st_stream(dst, store_perm ? tile[st_lo ^ h->st_hi[i]] : my_tile[i * THREADS]);
                 }
             }
         }

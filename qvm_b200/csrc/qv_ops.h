@@ -204,97 +204,107 @@ QV_HD void qv_dense_dispatch(qvc (&a)[NS], uint32_t kind, const qvc* M, uint32_t
 }
 
 // ---------------------------------------------------------------------------------------------
-// Diagonal micro-ops: every amplitude is multiplied by one table entry.  The table index is
-// idx (the part that depends on the group and the tile) | slot_off[r] (the register bits).
-//   gated by RB: the table only holds the entries with that bit SET (every entry with the bit
-//   clear is exactly 1: controlled-phase ladders), so only half of the slots are touched.
+// Diagonal micro-ops: every amplitude (or every amplitude whose gate bit is set) is multiplied by one
+// table entry.
 // ---------------------------------------------------------------------------------------------
-template <int NS, int RB>
-QV_HD void qv_diag_gated1(qvc (&a)[NS], qvc t) {
+// slot number r with bit RB squeezed out
+template <int RB>
+QV_HD constexpr int qv_squeeze(int r) { return ((r >> (RB + 1)) << RB) | (r & ((1 << RB) - 1)); }
+
+// GATE = 0: all slots; GATE = 1 + RB: the slots with register bit RB set
+template <int NS, int GATE>
+QV_HD void qv_diag1(qvc (&a)[NS], qvc t) {
 #pragma unroll
     for (int r = 0; r < NS; r++)
-        if (r & (1 << RB)) qv_cmul_ip(a[r], t);
+        if (GATE == 0 || (r & (1 << (GATE > 0 ? GATE - 1 : 0)))) qv_cmul_ip(a[r], t);
 }
 
-template <int NS, int RB>
-QV_HD void qv_diag_gatedn(qvc (&a)[NS], const qvc* tab, uint32_t idx, const QvUop& u) {
+// tab points at the group's run of per-slot entries
+template <int NS, int GATE>
+QV_HD void qv_diagr(qvc (&a)[NS], const qvc* tab) {
 #pragma unroll
-    for (int r = 0; r < NS; r++)
-        if (r & (1 << RB)) qv_cmul_ip(a[r], tab[idx | u.slot_off[r]]);
-}
-
-template <int NS, int RB>
-QV_HD void qv_diag_onebit(qvc (&a)[NS], const qvc* tab, uint32_t idx, const QvUop& u) {
-    const qvc t0 = tab[idx], t1 = tab[idx | u.slot_off[1 << RB]];
-#pragma unroll
-    for (int r = 0; r < NS; r++) qv_cmul_ip(a[r], (r & (1 << RB)) ? t1 : t0);
+    for (int r = 0; r < NS; r++) {
+        if (GATE == 0) qv_cmul_ip(a[r], tab[r]);
+        else if (r & (1 << (GATE > 0 ? GATE - 1 : 0))) qv_cmul_ip(a[r], tab[qv_squeeze<(GATE > 0 ? GATE - 1 : 0)>(r)]);
+    }
 }
 
 template <int NS>
-QV_HD void qv_diag_dispatch(qvc (&a)[NS], uint32_t kind, const qvc* tab, uint32_t idx, const QvUop& u, const qvc* slices) {
-    if (kind <= QV_K_DIAG_GATED1 + 3) {
-        // one lookup for the whole group, optionally times a per-tile scalar
-        qvc t = tab[idx];
-        if (u.flags & QV_UF_SCALE) t = qv_cmul(t, slices[u.scale]);
-        switch (kind) {
-            case QV_K_DIAG_COMMON: {
-#pragma unroll
-                for (int r = 0; r < NS; r++) qv_cmul_ip(a[r], t);
-                break;
-            }
-            case QV_K_DIAG_GATED1 + 0: qv_diag_gated1<NS, 0>(a, t); break;
-            case QV_K_DIAG_GATED1 + 1: if (NS > 2) qv_diag_gated1<NS, (NS > 2 ? 1 : 0)>(a, t); break;
-            case QV_K_DIAG_GATED1 + 2: if (NS > 4) qv_diag_gated1<NS, (NS > 4 ? 2 : 0)>(a, t); break;
-            default: if (NS > 8) qv_diag_gated1<NS, (NS > 8 ? 3 : 0)>(a, t); break;
-        }
-        return;
+QV_HD void qv_diag1_dispatch(qvc (&a)[NS], uint32_t gate, qvc t) {
+    switch (gate) {
+        case 0: qv_diag1<NS, 0>(a, t); break;
+        case 1: qv_diag1<NS, 1>(a, t); break;
+        case 2: qv_diag1<NS, 2>(a, t); break;
+        case 3: qv_diag1<NS, 3>(a, t); break;
+        default: if (NS > 8) qv_diag1<NS, (NS > 8 ? 4 : 0)>(a, t); break;
     }
-    switch (kind) {
-        case QV_K_DIAG_GATEDN + 0: qv_diag_gatedn<NS, 0>(a, tab, idx, u); break;
-        case QV_K_DIAG_GATEDN + 1: if (NS > 2) qv_diag_gatedn<NS, (NS > 2 ? 1 : 0)>(a, tab, idx, u); break;
-        case QV_K_DIAG_GATEDN + 2: if (NS > 4) qv_diag_gatedn<NS, (NS > 4 ? 2 : 0)>(a, tab, idx, u); break;
-        case QV_K_DIAG_GATEDN + 3: if (NS > 8) qv_diag_gatedn<NS, (NS > 8 ? 3 : 0)>(a, tab, idx, u); break;
-        case QV_K_DIAG_ONEBIT + 0: qv_diag_onebit<NS, 0>(a, tab, idx, u); break;
-        case QV_K_DIAG_ONEBIT + 1: if (NS > 2) qv_diag_onebit<NS, (NS > 2 ? 1 : 0)>(a, tab, idx, u); break;
-        case QV_K_DIAG_ONEBIT + 2: if (NS > 4) qv_diag_onebit<NS, (NS > 4 ? 2 : 0)>(a, tab, idx, u); break;
-        case QV_K_DIAG_ONEBIT + 3: if (NS > 8) qv_diag_onebit<NS, (NS > 8 ? 3 : 0)>(a, tab, idx, u); break;
-        default: {
-#pragma unroll
-            for (int r = 0; r < NS; r++) qv_cmul_ip(a[r], tab[idx | u.slot_off[r]]);
-            break;
-        }
+}
+
+template <int NS>
+QV_HD void qv_diagr_dispatch(qvc (&a)[NS], uint32_t gate, const qvc* tab) {
+    switch (gate) {
+        case 0: qv_diagr<NS, 0>(a, tab); break;
+        case 1: qv_diagr<NS, 1>(a, tab); break;
+        case 2: qv_diagr<NS, 2>(a, tab); break;
+        case 3: qv_diagr<NS, 3>(a, tab); break;
+        default: if (NS > 8) qv_diagr<NS, (NS > 8 ? 4 : 0)>(a, tab); break;
     }
+}
+
+// log2 of the per-group run of a DIAGR table
+template <int NS>
+QV_HD constexpr uint32_t qv_slot_field(uint32_t gate) {
+    return (NS == 16 ? 4u : 3u) - (gate ? 1u : 0u);
 }
 
 // Apply one micro-op to a register group.
-//   tables : the pass's global-memory table pool        slices : the per-tile slice area
-//   s_ext  : per-tile external index parts (QvExt)      s_pred : per-tile control predicates (QvPred)
+//   tables : the pass's global-memory table pool        slices : the per-tile slice area (shared memory)
+//   s_pred : per-tile control predicates (QvPred)
 template <int NS>
 QV_HD void qv_run_uop(qvc (&a)[NS], const QvUop& u, uint32_t g, const uint8_t* blob, const qvc* tables,
-                      const qvc* slices, const uint32_t* s_ext, const uint8_t* s_pred) {
+                      const qvc* slices, const uint8_t* s_pred) {
     const uint32_t kind = u.kind;
-    const uint32_t flags = u.flags;
-    if (kind < QV_K_DIAG_COMMON) {
-        if ((flags & QV_UF_PRED) && !s_pred[u.pred]) return;
+    if (kind < QV_K_DIAG_BASE) {
+        const uint32_t flags = u.flags;
         const qvc* M = reinterpret_cast<const qvc*>(blob + u.data);
-        if (flags & QV_UF_CTRL) {
-            if ((g & u.cm) != u.cv) return;
-            qv_dense_dispatch<NS, true>(a, kind, M, u.slot_ok);
-        } else {
-            qv_dense_dispatch<NS, false>(a, kind, M, 0xffffu);
+        if (flags) {
+            if ((flags & QV_UF_PRED) && !s_pred[u.pred]) return;
+            if (flags & QV_UF_CTRL) {
+                if ((g & u.cm) != u.cv) return;
+                qv_dense_dispatch<NS, true>(a, kind, M, u.slot_ok);
+                return;
+            }
         }
+        qv_dense_dispatch<NS, false>(a, kind, M, 0xffffu);
+        return;
+    }
+    uint32_t idx;
+    if (u.flags & QV_UF_GENERIC) {
+        const QvSegList* sl = reinterpret_cast<const QvSegList*>(blob + u.segs);
+        idx = qv_gather32(g, sl->segs, sl->n);
     } else {
-        uint32_t idx;
-        if (flags & QV_UF_GENERIC) {
-            const QvSegList* sl = reinterpret_cast<const QvSegList*>(blob + u.segs);
-            idx = qv_gather32(g, sl->segs, sl->n);
+        idx = ((g >> (u.cm & 0xffu)) & (u.cm >> 8)) | ((g >> (u.cv & 0xffu)) & (u.cv >> 8));
+    }
+    if (kind < QV_K_DIAGR_S) {
+        qvc t;
+        uint32_t gate;
+        if (kind < QV_K_DIAG1_G) {
+            gate = kind - QV_K_DIAG1_S;
+            t = slices[u.data + idx];
         } else {
-            idx = (g >> (u.cm & 0xffu)) & (u.cm >> 8);
-            if (flags & QV_UF_FIELD2) idx |= (g >> (u.cv & 0xffu)) & (u.cv >> 8);
+            gate = kind - QV_K_DIAG1_G;
+            t = tables[u.data + idx];
         }
-        if (flags & QV_UF_EXT) idx |= s_ext[u.ext];
-        const qvc* tab = ((flags & QV_UF_SLICE) ? slices : tables) + u.data;
-        qv_diag_dispatch<NS>(a, kind, tab, idx, u, slices);
+        if (u.flags & QV_UF_SCALE) t = qv_cmul(t, slices[u.scale]);
+        qv_diag1_dispatch<NS>(a, gate, t);
+    } else if (kind < QV_K_DIAGR_G) {
+        const uint32_t gate = kind - QV_K_DIAGR_S;
+        qv_diagr_dispatch<NS>(a, gate, slices + u.data + (idx << qv_slot_field<NS>(gate)));
+    } else if (kind < QV_K_DIAGR_C) {
+        const uint32_t gate = kind - QV_K_DIAGR_G;
+        qv_diagr_dispatch<NS>(a, gate, tables + u.data + (idx << qv_slot_field<NS>(gate)));
+    } else {
+        qv_diagr_dispatch<NS>(a, kind - QV_K_DIAGR_C, reinterpret_cast<const qvc*>(blob + u.data));
     }
 }
 

@@ -32,7 +32,6 @@
 #define QV_THREADS 256           // block size of the streaming kernels and of the 3-register-bit tile kernel
 #define QV_THREADS_WIDE 128      // block size of the 4-register-bit tile kernel (fewer, fatter threads)
 #define QV_MAX_PEERS 8
-#define QV_MAX_EXT 128           // per-tile external index parts staged in shared memory
 #define QV_MAX_SOURCES 192       // per-tile source offsets staged in shared memory
 #define QV_MAX_PREDS 64          // per-tile control predicates (controls on bits outside the tile)
 #define QV_MAX_SLICES 64
@@ -45,26 +44,30 @@
 #define QV_PROG_LARGE_BYTES 28672
 
 // Micro-op kinds.  RB = register bit index (0..3), PAIR = index of the register-bit pair
-// (0,1) (0,2) (1,2) (0,3) (1,3) (2,3).
+// (0,1) (0,2) (1,2) (0,3) (1,3) (2,3).  GATE = 0: every slot, 1 + RB: only the slots whose register bit RB
+// is set (the table then only holds the entries with that bit set: every entry with the bit clear is
+// exactly 1 -- controlled-phase ladders).
+//   DIAG1: the table index has no register bit -> one lookup serves the whole group.
+//   DIAGR: the index is (nonreg_index << field) + slot, the slot field being the full slot number (or the
+//          slot number with the gate bit squeezed out), so per-slot offsets are compile-time constants.
+//   table space: S = per-tile slice in shared memory, G = global-memory table, C = constants in the blob.
 enum QvUopKind : uint32_t {
     QV_K_DENSE1 = 0,         // + 2*RB + (complex ? 1 : 0)            2x2 matrix on register bit RB
     QV_K_DENSE2 = 8,         // + 2*PAIR + (complex ? 1 : 0)          4x4 matrix on a register-bit pair
-    QV_K_DIAG_COMMON = 20,   // no register bit in the table index: one factor for the whole group
-    QV_K_DIAG_GATED1 = 21,   // + RB: gated by RB, no other register bit in the index: one factor for the gated slots
-    QV_K_DIAG_GATEDN = 25,   // + RB: gated by RB, other register bits in the index: one lookup per gated slot
-    QV_K_DIAG_ONEBIT = 29,   // + RB: exactly one register bit in the index, not gating: two lookups
-    QV_K_DIAG_ALL = 33,      // one lookup per slot
-    QV_K_COUNT = 34,
+    QV_K_DIAG_BASE = 20,
+    QV_K_DIAG1_S = 20,       // + GATE
+    QV_K_DIAG1_G = 25,       // + GATE
+    QV_K_DIAGR_S = 30,       // + GATE
+    QV_K_DIAGR_G = 35,       // + GATE
+    QV_K_DIAGR_C = 40,       // + GATE   (index has register bits only, no per-tile part)
+    QV_K_COUNT = 45,
 };
 
 enum QvUopFlags : uint32_t {
     QV_UF_CTRL = 1u,      // dense: restricted by cm/cv (group level) and slot_ok (slot level)
     QV_UF_PRED = 2u,      // dense: restricted to tiles whose predicate `pred` holds (controls outside the tile)
-    QV_UF_SLICE = 4u,     // diag: table is a per-tile slice in shared memory (else a global-memory table)
-    QV_UF_EXT = 8u,       // diag: add the per-tile external index part `ext`
-    QV_UF_FIELD2 = 16u,   // diag: a second index field
-    QV_UF_GENERIC = 32u,  // diag: index fields come from a segment list (more than two fields)
-    QV_UF_SCALE = 64u,    // diag (single-lookup kinds): multiply the entry by the one-entry slice `scale`
+    QV_UF_GENERIC = 4u,   // diag: index fields come from a segment list (more than two fields)
+    QV_UF_SCALE = 8u,     // diag (DIAG1 kinds): multiply the entry by the one-entry slice `scale`
 };
 
 // gather/deposit of one contiguous bit field: ((x >> src) & ((1<<len)-1)) << dst
@@ -78,28 +81,21 @@ struct QvUop {
     uint8_t kind;                   // QvUopKind
     uint8_t flags;
     uint8_t pred;                   // index of the per-tile predicate (QV_UF_PRED)
-    uint8_t ext;                    // index of the per-tile external index part (QV_UF_EXT)
+    uint8_t pad0;
     uint32_t data;                  // dense: byte offset of the row-major matrix in the blob
-                                    // diag : entry offset of the table (slice area or global table pool)
+                                    // diag : entry offset of the table (slice area / global table pool), byte offset in the blob for C
     uint32_t cm, cv;                // dense: control mask / value over g
                                     // diag : cm = field 0, cv = field 1; field = shift | (mask << 8), value = (g >> shift) & mask
     uint16_t slot_ok;               // dense: slots allowed by controls on register bits
     uint16_t segs;                  // diag (QV_UF_GENERIC): byte offset of a QvSegList in the blob
-    uint8_t slot_off[QV_MAX_SLOTS]; // diag: table index contribution of register slot r
     uint16_t scale;                 // diag (QV_UF_SCALE): entry of the slice area holding the per-tile scalar
-    uint16_t pad16;
-    uint32_t pad[2];
-};                                  // 48 bytes
+    uint16_t pad1;
+    uint32_t pad2[2];
+};                                  // 32 bytes
 
 struct QvSegList {
     uint32_t n;
     QvSeg segs[QV_CHUNK_SEGS];
-};
-
-// Per-tile external part of a global table index: gather(tile base) << shift.
-struct QvExt {
-    uint8_t n_esegs, shift, pad[2];
-    QvSeg esegs[QV_CHUNK_SEGS];
 };
 
 // One source table of a slice: entry x of the slice takes the factor
@@ -143,15 +139,23 @@ struct QvPassHeader {
     uint64_t fixed_bits;            // OR'd into every physical index of the pass (rank bits, group split)
     uint64_t n_tiles;               // tiles this device processes
     uint32_t n_local_bits;          // log2(amplitudes per shard): physical bits above it select the peer
-    uint32_t n_rounds, n_uops, n_ext, n_sources, n_slices, n_slice_entries, n_preds;
+    uint32_t n_rounds, n_uops, n_sources, n_slices, n_slice_entries, n_preds;
     // byte offsets from the start of the control blob (the diagonal tables travel separately,
     // in global memory)
-    uint32_t off_rounds, off_uops, off_ext, off_sources, off_slices, off_slice_of, off_preds, off_matrices;
+    uint32_t off_rounds, off_uops, off_sources, off_slices, off_slice_of, off_preds, off_matrices;
     uint32_t n_table_entries;
     uint32_t blob_bytes;
     uint32_t uses_peers;            // tile bits include a physical bit >= n_local_bits
     uint32_t n_diag_uops;           // statistics for describe()
     uint64_t hi_off[32];            // physical-index bits of tile-local index (block size)*i (host-precomputed gather)
+    // Store permutation: the trailing X / CNOT / SWAP gates of a pass are GF(2)-affine maps of the tile-local
+    // index, so they cost no arithmetic at all: the element written to tile-local position e is read from
+    // shared-memory slot qv_swz(A e ^ b) = st_lo(tid) ^ st_hi[i] for e = tid + (block size)*i.
+    uint32_t store_perm;            // 0: identity (plain write-back)
+    uint16_t st_col[QV_MAX_TILE_BITS];  // qv_swz(A column k): contribution of bit k of tid
+    uint16_t st_const;              // qv_swz(b)
+    uint16_t st_pad;
+    uint16_t st_hi[32];             // qv_swz(A ((block size)*i))
 };
 
 // Pull remap (multi-GPU): every rank gathers the amplitudes it will own AFTER the physical bit swaps

@@ -180,7 +180,6 @@ struct RoundOp {
 struct BlobWriter {
     std::vector<QvRound> rounds;
     std::vector<QvUop> uops;
-    std::vector<QvExt> exts;
     std::vector<QvSource> sources;
     std::vector<QvSlice> slices;
     std::vector<QvPred> preds;
@@ -220,7 +219,7 @@ std::vector<cd> product_table(const std::vector<DiagFactor>& facs, const std::ve
     for (const DiagFactor& f : facs) {
         std::vector<int> idx_of(f.pos.size());
         for (size_t j = 0; j < f.pos.size(); j++) {
-            const auto it = std::find(bits.begin(), bits.end(), f.pos[j]);
+            const auto it = std::find(bits.begin(), bits.end(), f.pos[j]);     // layout entries of -1 are don't-care bits
             if (it == bits.end()) throw std::runtime_error("scheduler bug: factor bit missing from a table layout");
             idx_of[j] = (int)(it - bits.begin());
         }
@@ -244,7 +243,7 @@ struct PlanChunk {
 };
 
 void emit_round(BlobWriter& w, const std::vector<RoundOp>& rops, const std::vector<int>& regpos_local,
-                const TileMap& tm, const Layout& lay) {
+                const TileMap& tm, const Layout& lay, int reg_bits) {
     const int m = (int)regpos_local.size();
     QvRound rd{};
     rd.m = (uint32_t)m;
@@ -372,7 +371,18 @@ void emit_round(BlobWriter& w, const std::vector<RoundOp>& rops, const std::vect
                     if (want[i] >= 0 && bucket_l[want[i]] == 0) want[i] = -1;
         }
         // 2. greedy packing: a factor joins the chunk of its gate whose tile-local index grows least;
-        //    external bits do not count (they are frozen per tile when the chunk becomes a slice)
+        //    external bits do not count (they are frozen per tile when the chunk becomes a slice).
+        //    Index width: the non-register bits, plus -- as soon as any register bit takes part -- the whole
+        //    slot field (per-slot table offsets are compile-time constants in the kernel).
+        auto eff_bits = [&](const std::vector<int>& lbits, int gate) {
+            size_t nonreg = 0;
+            bool any_reg = false;
+            for (int b : lbits) {
+                if (reg_of(tm.local_of[b]) >= 0) any_reg = true;
+                else nonreg++;
+            }
+            return nonreg + (any_reg ? (size_t)(reg_bits - (gate >= 0 ? 1 : 0)) : 0);
+        };
         std::vector<PlanChunk> plan;
         for (size_t i = 0; i < nf; i++) {
             DiagFactor f = want[i] >= 0 ? restrict_to_one(ro.factors[i], want[i]) : ro.factors[i];
@@ -387,7 +397,7 @@ void emit_round(BlobWriter& w, const std::vector<RoundOp>& rops, const std::vect
                 if (plan[ci].gate != want[i]) continue;
                 std::vector<int> u;
                 std::set_union(plan[ci].lbits.begin(), plan[ci].lbits.end(), L.begin(), L.end(), std::back_inserter(u));
-                if (u.size() > QV_MAX_CHUNK_BITS) continue;
+                if (eff_bits(u, want[i]) > QV_MAX_CHUNK_BITS) continue;
                 if (u.size() < best_size) {
                     best_size = u.size();
                     best = (int)ci;
@@ -447,7 +457,7 @@ void emit_round(BlobWriter& w, const std::vector<RoundOp>& rops, const std::vect
                 }
                 srcs[best].facs.push_back(f);
             }
-            const size_t entries = (size_t)1 << lay_bits.size();
+            const size_t entries = (size_t)1 << lay_bits.size();     // -1 layout entries are don't-care bits (replicated)
             if (w.slice_entries + entries > QV_SLICE_ENTRIES || w.slices.size() >= QV_MAX_SLICES ||
                 w.sources.size() + srcs.size() > QV_MAX_SOURCES || w.slice_build + entries * srcs.size() > QV_MAX_SLICE_BUILD)
                 throw std::length_error("per-tile slice area exhausted");
@@ -493,32 +503,35 @@ void emit_round(BlobWriter& w, const std::vector<RoundOp>& rops, const std::vect
             return qs.off;
         };
         // One diagonal micro-op over the tile-local bits `lbits` (sorted physical), gated by `gate` (or -1).
-        //   facs       : what the table holds (as a slice when as_slice, else a static global-memory table)
+        //   facs       : what the table holds (as a slice when as_slice, else a static table: global memory, or
+        //                constants in the blob when only register bits index it)
         //   scale_facs : factors with external bits only; their per-tile product (a one-entry slice) is
-        //                multiplied into the looked-up entry (kinds with a single lookup per group only)
+        //                multiplied into the looked-up entry (DIAG1 kinds only)
         auto emit_diag = [&](int gate, const std::vector<int>& lbits, const std::vector<DiagFactor>& facs, bool as_slice,
                              const std::vector<DiagFactor>& scale_facs) {
-            // index layout: non-register tile-local bits (ascending), then register bits
-            std::vector<int> nonreg, regb;
-            for (int b : lbits) (reg_of(tm.local_of[b]) >= 0 ? regb : nonreg).push_back(b);
-            std::vector<int> lay_bits = nonreg;
-            lay_bits.insert(lay_bits.end(), regb.begin(), regb.end());
-            QvUop u{};
-            uint32_t reg_mask = 0;
-            for (size_t j = 0; j < regb.size(); j++) {
-                const int r = reg_of(tm.local_of[regb[j]]);
-                reg_mask |= 1u << r;
-                for (uint32_t sl = 0; sl < QV_MAX_SLOTS; sl++)
-                    if (sl >> r & 1) u.slot_off[sl] |= (uint8_t)(1u << (nonreg.size() + j));
+            std::vector<int> nonreg;
+            bool any_reg = false;
+            for (int b : lbits) {
+                if (reg_of(tm.local_of[b]) >= 0) any_reg = true;
+                else nonreg.push_back(b);
             }
             const int gate_r = gate >= 0 ? reg_of(tm.local_of[gate]) : -1;
-            if (gate_r >= 0) u.kind = (uint8_t)((reg_mask ? QV_K_DIAG_GATEDN : QV_K_DIAG_GATED1) + gate_r);
-            else if (reg_mask == 0) u.kind = QV_K_DIAG_COMMON;
-            else if ((reg_mask & (reg_mask - 1)) == 0) {
-                int r = 0;
-                while (!(reg_mask >> r & 1)) r++;
-                u.kind = (uint8_t)(QV_K_DIAG_ONEBIT + r);
-            } else u.kind = QV_K_DIAG_ALL;
+            const uint32_t gate_code = gate_r >= 0 ? (uint32_t)gate_r + 1 : 0;
+            // index layout: the slot field (register bits in slot order, gate bit squeezed out; -1 = a slot bit this
+            // round does not use or the table does not depend on), then the non-register bits (ascending)
+            std::vector<int> lay_bits;
+            if (any_reg)
+                for (int r = 0; r < reg_bits; r++) {
+                    if (r == gate_r) continue;
+                    int phys = -1;
+                    if (r < m) {
+                        const int b = tm.tilebits[regpos_local[r]];
+                        if (std::find(lbits.begin(), lbits.end(), b) != lbits.end()) phys = b;
+                    }
+                    lay_bits.push_back(phys);
+                }
+            lay_bits.insert(lay_bits.end(), nonreg.begin(), nonreg.end());
+            QvUop u{};
             // index fields over the group counter g
             std::vector<int> src, dst;
             for (size_t j = 0; j < nonreg.size(); j++) {
@@ -529,35 +542,43 @@ void emit_round(BlobWriter& w, const std::vector<RoundOp>& rops, const std::vect
             auto field = [](const QvSeg& q) { return (uint32_t)(q.src - q.dst) | ((((1u << q.len) - 1u) << q.dst) << 8); };
             if (sg.size() > QV_CHUNK_SEGS) throw std::runtime_error("scheduler bug: chunk needs too many segments");
             if (sg.size() >= 1) u.cm = field(sg[0]);
-            if (sg.size() == 2) {
-                u.cv = field(sg[1]);
-                u.flags |= QV_UF_FIELD2;
-            } else if (sg.size() > 2) {
+            if (sg.size() == 2) u.cv = field(sg[1]);
+            if (sg.size() > 2) {
                 QvSegList sl{};
                 sl.n = (uint32_t)sg.size();
                 std::copy(sg.begin(), sg.end(), sl.segs);
                 u.flags |= QV_UF_GENERIC;
+                u.cm = u.cv = 0;
                 u.segs = (uint16_t)w.seglists.size();      // made blob-relative when the blob is laid out
                 w.seglists.push_back(sl);
             }
+            const char* where = "GLOBAL";
             if (as_slice) {
-                u.flags |= QV_UF_SLICE;
+                u.kind = (uint8_t)((any_reg ? QV_K_DIAGR_S : QV_K_DIAG1_S) + gate_code);
                 u.data = make_slice(lay_bits, facs);
+                where = "SLICE";
+            } else if (any_reg && nonreg.empty()) {
+                u.kind = (uint8_t)(QV_K_DIAGR_C + gate_code);
+                u.data = (uint32_t)(w.mats.size() * sizeof(cd));   // made blob-relative when the blob is laid out
+                const std::vector<cd> tab = product_table(facs, lay_bits);
+                w.mats.insert(w.mats.end(), tab.begin(), tab.end());
+                where = "CONST";
             } else {
+                u.kind = (uint8_t)((any_reg ? QV_K_DIAGR_G : QV_K_DIAG1_G) + gate_code);
                 u.data = (uint32_t)w.tables.size();
                 const std::vector<cd> tab = product_table(facs, lay_bits);
                 w.tables.insert(w.tables.end(), tab.begin(), tab.end());
             }
             if (!scale_facs.empty()) {
-                if (reg_mask) throw std::runtime_error("scheduler bug: scaled diagonal with per-slot lookups");
+                if (any_reg) throw std::runtime_error("scheduler bug: scaled diagonal with per-slot lookups");
                 u.flags |= QV_UF_SCALE;
                 u.scale = (uint16_t)make_slice({}, scale_facs);
             }
             w.uops.push_back(u);
             w.n_diag_uops++;
             if (getenv("QV_SCHED_DEBUG"))
-                fprintf(stderr, "    uop kind=%u gate=%d nonreg=%zu reg=%zu facs=%zu %s scale_facs=%zu\n", (unsigned)u.kind, gate,
-                        nonreg.size(), regb.size(), facs.size(), as_slice ? "SLICE" : "GLOBAL", scale_facs.size());
+                fprintf(stderr, "    uop kind=%u gate=%d nonreg=%zu any_reg=%d facs=%zu %s scale_facs=%zu\n", (unsigned)u.kind, gate,
+                        nonreg.size(), (int)any_reg, facs.size(), where, scale_facs.size());
         };
         auto local_bits_of = [&](const std::vector<DiagFactor>& facs) {
             std::vector<int> bits;
@@ -575,13 +596,13 @@ void emit_round(BlobWriter& w, const std::vector<RoundOp>& rops, const std::vect
                     if (tm.local_of[b] < 0) has_ext = true;
                 (has_ext ? ext : loc).push_back(f);
             }
-            const size_t entries = (size_t)1 << pc.lbits.size();
-            bool any_reg = false;
-            for (int b : pc.lbits)
-                if (reg_of(tm.local_of[b]) >= 0) any_reg = true;
+            const size_t entries = (size_t)1 << eff_bits(pc.lbits, pc.gate);
+            bool any_reg = false, any_nonreg = false;
+            for (int b : pc.lbits) (reg_of(tm.local_of[b]) >= 0 ? any_reg : any_nonreg) = true;
             if (ext.empty()) {
-                // static table: tiny ones are staged per tile in shared memory, the others stay in global memory (L1-resident)
-                emit_diag(pc.gate, pc.lbits, loc, entries <= 16, {});
+                // static table: register-only ones are constants in the blob, tiny ones are staged per tile in
+                // shared memory, the others stay in global memory (L1-resident)
+                emit_diag(pc.gate, pc.lbits, loc, any_nonreg && entries <= 16, {});
             } else if (loc.empty() || entries <= 32) {
                 emit_diag(pc.gate, pc.lbits, pc.facs, true, {});
             } else {
@@ -668,13 +689,14 @@ void build_rounds(BlobWriter& w, const std::vector<const Atom*>& atoms, const Ti
         for (int lp = tm.T - 1; lp >= 0 && (int)regpos.size() < m_max; lp--)
             if (std::find(regpos.begin(), regpos.end(), lp) == regpos.end()) regpos.push_back(lp);
         std::sort(regpos.begin(), regpos.end());
-        emit_round(w, rops, regpos, tm, lay);
+        emit_round(w, rops, regpos, tm, lay, reg_bits);
         pending.swap(deferred);
     }
 }
 
 struct Geometry {
     int n_bits, n_local, T, lmin, rank;
+    bool store_perm;    // fold trailing X / CNOT / SWAP gates into the write-back addressing
     int reg_bits;       // 0 = choose per pass (4 for passes that carry many gates, else 3)
 };
 
@@ -690,7 +712,25 @@ int choose_reg_bits(const std::vector<const Atom*>& atoms, const Geometry& geo) 
 }
 
 // tile_targets: physical bits that must be inside the tile.
-Step build_tile_step(const std::vector<const Atom*>& atoms, uint64_t tile_targets, const Geometry& geo,
+// X, singly-controlled X (CNOT, also control-on-zero) or SWAP with exact 0/1 entries.
+bool is_linear_perm(const Atom& a) {
+    if (a.kind != Atom::DENSE) return false;
+    const cd one(1.0, 0.0), zero(0.0, 0.0);
+    if (a.tw.size() == 1) {
+        if (popc(a.cmask) > 1) return false;
+        return a.mat[0] == zero && a.mat[1] == one && a.mat[2] == one && a.mat[3] == zero;
+    }
+    if (a.tw.size() == 2 && a.cmask == 0) {
+        static const int img[4] = {0, 2, 1, 3};
+        for (int r = 0; r < 4; r++)
+            for (int c = 0; c < 4; c++)
+                if (a.mat[r * 4 + c] != (img[r] == c ? one : zero)) return false;
+        return true;
+    }
+    return false;
+}
+
+Step build_tile_step(const std::vector<const Atom*>& atoms_in, uint64_t tile_targets, const Geometry& geo,
                      const Layout& lay) {
     TileMap tm;
     tm.T = geo.T;
@@ -707,6 +747,54 @@ Step build_tile_step(const std::vector<const Atom*>& atoms, uint64_t tile_target
     const uint64_t local_mask = (1ull << geo.n_local) - 1ull;
     const uint64_t tile_global = tb & ~local_mask;          // rank bits that vary inside the tile
     const int s = popc(tile_global);
+
+    // Trailing X / CNOT / SWAP atoms whose qubits all sit inside the tile are GF(2)-affine maps of the
+    // tile-local index: they are folded into the write-back addressing (store permutation) instead of
+    // running as arithmetic.  An atom may be pulled out from behind later atoms it commutes with.
+    std::vector<const Atom*> kept;
+    std::vector<const Atom*> stripped;      // in circuit order
+    {
+        uint64_t later_mix = 0, later_touch = 0;
+        std::vector<char> strip(atoms_in.size(), 0);
+        for (size_t i = atoms_in.size(); i-- > 0;) {
+            const Atom* a = atoms_in[i];
+            bool lin = geo.store_perm && is_linear_perm(*a);
+            if (lin)
+                for (int wq = 0; wq < 64; wq++)
+                    if ((a->touch >> wq & 1) && tm.local_of[lay.phys(wq)] < 0) lin = false;
+            if (lin && ((a->mix & later_touch) != 0 || (later_mix & a->touch) != 0)) lin = false;
+            if (lin) strip[i] = 1;
+            else {
+                later_mix |= a->mix;
+                later_touch |= a->touch;
+            }
+        }
+        for (size_t i = 0; i < atoms_in.size(); i++) (strip[i] ? stripped : kept).push_back(atoms_in[i]);
+    }
+    const std::vector<const Atom*>& atoms = kept;
+    // rows of the affine map src = A e ^ b that the write-back applies: pi_1 o ... o pi_k (every pi an involution)
+    uint32_t st_row[QV_MAX_TILE_BITS], st_b = 0;
+    for (int k = 0; k < QV_MAX_TILE_BITS; k++) st_row[k] = 1u << k;
+    for (size_t i = stripped.size(); i-- > 0;) {
+        const Atom& a = *stripped[i];
+        auto lp = [&](int wire) { return tm.local_of[lay.phys(wire)]; };
+        if (a.tw.size() == 2) {
+            const int x = lp(a.tw[0]), y = lp(a.tw[1]);
+            std::swap(st_row[x], st_row[y]);
+            const uint32_t bx = st_b >> x & 1, by = st_b >> y & 1;
+            st_b = (st_b & ~((1u << x) | (1u << y))) | (by << x) | (bx << y);
+        } else {
+            const int t = lp(a.tw[0]);
+            if (a.cmask == 0) st_b ^= 1u << t;
+            else {
+                int cw = 0;
+                while (!(a.cmask >> cw & 1)) cw++;
+                const int c = lp(cw);
+                st_row[t] ^= st_row[c];
+                st_b ^= ((st_b >> c & 1) ^ ((a.cval >> cw & 1) ? 0u : 1u)) << t;
+            }
+        }
+    }
 
     const int reg_bits = choose_reg_bits(atoms, geo);
     const int threads_log2 = reg_bits == 4 ? 7 : 8;
@@ -765,6 +853,19 @@ Step build_tile_step(const std::vector<const Atom*>& atoms, uint64_t tile_target
             if (e >> t & 1) off |= 1ull << tm.tilebits[t];
         h.hi_off[i] = off;
     }
+    if (!stripped.empty()) {
+        auto image = [&](uint32_t e) {      // A e (no constant)
+            uint32_t r = 0;
+            for (int k = 0; k < tm.T; k++)
+                if (__builtin_popcount(st_row[k] & e) & 1) r |= 1u << k;
+            return r;
+        };
+        auto swz = [](uint32_t e) { return e ^ ((e >> 3) & 7u); };
+        h.store_perm = 1;
+        for (int k = 0; k < tm.T; k++) h.st_col[k] = (uint16_t)swz(image(1u << k));
+        h.st_const = (uint16_t)swz(st_b);
+        for (int i = 0; i < 32; i++) h.st_hi[i] = (uint16_t)swz(image(((uint32_t)i << threads_log2) & ((1u << tm.T) - 1u)));
+    }
     h.fixed_bits = fixed;
     h.n_tiles = 1ull << nontile.size();
     h.n_local_bits = (uint32_t)geo.n_local;
@@ -772,7 +873,6 @@ Step build_tile_step(const std::vector<const Atom*>& atoms, uint64_t tile_target
     h.n_rounds = (uint32_t)w.rounds.size();
     h.n_uops = (uint32_t)w.uops.size();
     h.n_diag_uops = (uint32_t)w.n_diag_uops;
-    h.n_ext = (uint32_t)w.exts.size();
     h.n_sources = (uint32_t)w.sources.size();
     h.n_slices = (uint32_t)w.slices.size();
     h.n_slice_entries = (uint32_t)w.slice_entries;
@@ -786,8 +886,6 @@ Step build_tile_step(const std::vector<const Atom*>& atoms, uint64_t tile_target
     off = align16(off + w.rounds.size() * sizeof(QvRound));
     h.off_uops = (uint32_t)off;
     off = align16(off + w.uops.size() * sizeof(QvUop));
-    h.off_ext = (uint32_t)off;
-    off = align16(off + w.exts.size() * sizeof(QvExt));
     h.off_sources = (uint32_t)off;
     off = align16(off + w.sources.size() * sizeof(QvSource));
     h.off_slices = (uint32_t)off;
@@ -804,8 +902,8 @@ Step build_tile_step(const std::vector<const Atom*>& atoms, uint64_t tile_target
     h.blob_bytes = (uint32_t)off;
     if (off > QV_PROG_LARGE_BYTES) throw std::length_error("pass control program too large");
     for (QvUop& u : w.uops) {
-        if (u.kind < QV_K_DIAG_COMMON) u.data += h.off_matrices;
-        else if (u.flags & QV_UF_GENERIC) u.segs = (uint16_t)(off_seglists + u.segs * sizeof(QvSegList));
+        if (u.kind < QV_K_DIAG_BASE || u.kind >= QV_K_DIAGR_C) u.data += h.off_matrices;
+        if (u.kind >= QV_K_DIAG_BASE && (u.flags & QV_UF_GENERIC)) u.segs = (uint16_t)(off_seglists + u.segs * sizeof(QvSegList));
     }
 
     Step st;
@@ -818,7 +916,6 @@ Step build_tile_step(const std::vector<const Atom*>& atoms, uint64_t tile_target
     };
     put(h.off_rounds, w.rounds.data(), w.rounds.size() * sizeof(QvRound));
     put(h.off_uops, w.uops.data(), w.uops.size() * sizeof(QvUop));
-    put(h.off_ext, w.exts.data(), w.exts.size() * sizeof(QvExt));
     put(h.off_sources, w.sources.data(), w.sources.size() * sizeof(QvSource));
     put(h.off_slices, w.slices.data(), w.slices.size() * sizeof(QvSlice));
     put(h.off_slice_of, slice_of.data(), slice_of.size());
@@ -826,7 +923,7 @@ Step build_tile_step(const std::vector<const Atom*>& atoms, uint64_t tile_target
     put(off_seglists, w.seglists.data(), w.seglists.size() * sizeof(QvSegList));
     put(h.off_matrices, w.mats.data(), w.mats.size() * sizeof(cd));
     st.tables = std::move(w.tables);
-    st.n_gates = (int)atoms.size();
+    st.n_gates = (int)atoms_in.size();
     return st;
 }
 
@@ -867,6 +964,7 @@ Tape compile(const std::vector<Gate>& gates, int n_bits, const CompileOptions& o
     geo.n_local = opt.n_local_bits > 0 ? opt.n_local_bits : n_bits;
     geo.rank = opt.rank;
     geo.reg_bits = opt.reg_bits;
+    geo.store_perm = opt.store_perm;
     if (opt.reg_bits != 0 && opt.reg_bits != 3 && opt.reg_bits != 4) throw std::runtime_error("reg_bits must be 0 (auto), 3 or 4");
     geo.T = std::min(opt.tile_bits, geo.n_local);
     if (geo.n_local > n_bits) throw std::runtime_error("n_local_bits exceeds the qubit count");
@@ -1127,7 +1225,7 @@ std::string describe(const Tape& t) {
         os << "  [" << i << "] " << (s.is_remap ? "REMAP" : (s.uses_peers ? "PEER" : "TILE")) << " T=" << h.T
            << " m=" << h.reg_bits << " atoms=" << s.n_gates << " rounds=" << h.n_rounds << " uops=" << h.n_uops << " diag_uops=" << h.n_diag_uops
            << " slices=" << h.n_slices << " sources=" << h.n_sources << " slice_entries=" << h.n_slice_entries
-           << " bytes=" << h.blob_bytes << " tables=" << h.n_table_entries << " tilebits=";
+           << (h.store_perm ? " store_perm" : "") << " bytes=" << h.blob_bytes << " tables=" << h.n_table_entries << " tilebits=";
         for (uint32_t k = 0; k < h.n_tile_segs; k++)
             os << (int)h.tile_segs[k].dst << "+" << (int)h.tile_segs[k].len << (k + 1 < h.n_tile_segs ? "," : "");
         os << "\n";

@@ -23,7 +23,6 @@ void run_tile_step(qvc* const* peers, const qv::Step& st) {
     std::memcpy(&h, blob, sizeof(h));
     const QvRound* rounds = (const QvRound*)(blob + h.off_rounds);
     const QvUop* uops = (const QvUop*)(blob + h.off_uops);
-    const QvExt* exts = (const QvExt*)(blob + h.off_ext);
     const QvSource* sources = (const QvSource*)(blob + h.off_sources);
     const QvSlice* slices = (const QvSlice*)(blob + h.off_slices);
     const uint8_t* slice_of = blob + h.off_slice_of;
@@ -33,10 +32,10 @@ void run_tile_step(qvc* const* peers, const qv::Step& st) {
     const uint32_t threads = 1u << h.threads_log2;
     const uint64_t local_mask = (1ull << h.n_local_bits) - 1ull;
     std::vector<qvc> smem(tile_n);
-    std::vector<uint32_t> s_ext(QV_MAX_EXT), s_srcext(QV_MAX_SOURCES);
+    std::vector<uint32_t> s_srcext(QV_MAX_SOURCES);
     std::vector<uint8_t> s_pred(QV_MAX_PREDS);
     std::vector<qvc> s_slice(QV_SLICE_ENTRIES);
-    if (h.n_ext > QV_MAX_EXT || h.n_sources > QV_MAX_SOURCES || h.n_preds > QV_MAX_PREDS || h.n_slice_entries > QV_SLICE_ENTRIES ||
+    if (h.n_sources > QV_MAX_SOURCES || h.n_preds > QV_MAX_PREDS || h.n_slice_entries > QV_SLICE_ENTRIES ||
         h.n_slices > QV_MAX_SLICES)
         throw std::runtime_error("emulator: per-tile table limits exceeded");
     auto addr = [&](uint64_t p) { return peers[p >> h.n_local_bits] + (p & local_mask); };
@@ -46,7 +45,6 @@ void run_tile_step(qvc* const* peers, const qv::Step& st) {
     };
     for (uint64_t tile = 0; tile < h.n_tiles; tile++) {
         const uint64_t base = qv_gather(tile, h.base_segs, h.n_base_segs) | h.fixed_bits;
-        for (uint32_t i = 0; i < h.n_ext; i++) s_ext[i] = (uint32_t)qv_gather(base, exts[i].esegs, exts[i].n_esegs) << exts[i].shift;
         for (uint32_t i = 0; i < h.n_sources; i++)
             s_srcext[i] = (uint32_t)qv_gather(base, sources[i].esegs, sources[i].n_esegs) << sources[i].nl;
         for (uint32_t i = 0; i < h.n_preds; i++) s_pred[i] = (base & preds[i].mask) == preds[i].val ? 1 : 0;
@@ -70,7 +68,7 @@ void run_tile_step(qvc* const* peers, const qv::Step& st) {
                         else { a[s].x = 0.0; a[s].y = 0.0; }
                     }
                     for (uint32_t u = rd.first_uop; u < rd.first_uop + rd.n_uops; u++)
-                        qv_run_uop<8>(a, uops[u], g, blob, tables, s_slice.data(), s_ext.data(), s_pred.data());
+                        qv_run_uop<8>(a, uops[u], g, blob, tables, s_slice.data(), s_pred.data());
                     for (uint32_t s = 0; s < (1u << rd.m); s++) smem[se0 ^ rd.slot_xor[s]] = a[s];
                 } else {                    // the 16-slot instantiation, as the 128-thread kernel
                     qvc a[16];
@@ -79,12 +77,21 @@ void run_tile_step(qvc* const* peers, const qv::Step& st) {
                         else { a[s].x = 0.0; a[s].y = 0.0; }
                     }
                     for (uint32_t u = rd.first_uop; u < rd.first_uop + rd.n_uops; u++)
-                        qv_run_uop<16>(a, uops[u], g, blob, tables, s_slice.data(), s_ext.data(), s_pred.data());
+                        qv_run_uop<16>(a, uops[u], g, blob, tables, s_slice.data(), s_pred.data());
                     for (uint32_t s = 0; s < (1u << rd.m); s++) smem[se0 ^ rd.slot_xor[s]] = a[s];
                 }
             }
         }
-        for (uint32_t e = 0; e < tile_n; e++) *addr(phys(base, e)) = smem[qv_swz(e)];
+        for (uint32_t e = 0; e < tile_n; e++) {
+            uint32_t slot = qv_swz(e);
+            if (h.store_perm) {     // as the kernel: st_lo(tid) ^ st_hi[i] for e = tid + threads*i
+                slot = h.st_const;
+                for (uint32_t k = 0; k < h.T; k++)
+                    if ((e & (threads - 1)) >> k & 1) slot ^= h.st_col[k];
+                slot ^= h.st_hi[e >> h.threads_log2];
+            }
+            *addr(phys(base, e)) = smem[slot];
+        }
     }
 }
 

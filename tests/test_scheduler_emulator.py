@@ -71,3 +71,40 @@ def test_hadamard_and_bell_known_answers():
         b = O.zero_state(n)
         run_emulator(b, n, CC.bell_circuit(n))
         assert abs(abs(b[0]) ** 2 - 0.5) < 1e-14 and abs(abs(b[-1]) ** 2 - 0.5) < 1e-14
+
+
+@pytest.mark.parametrize("reg_bits", [3, 4])
+def test_trailing_permutation_gates_fold_into_the_write_back(reg_bits):
+    """X / CNOT / SWAP at the end of a pass are affine maps of the tile-local index: the scheduler folds them into
+    the store addressing (no arithmetic).  Mixed with gates they do and do not commute with."""
+    from qvm_b200 import gates as G
+    n = 11
+    rng = np.random.default_rng(77)
+    for trial in range(6):
+        circ = [(G.gate_matrix("H"), (int(q),)) for q in rng.choice(n, 4, replace=False)]
+        circ += [(G.gate_matrix("CPHASE", [0.4]), (0, 5)), (G.gate_matrix("RX", [0.3]), (2,))]
+        for _ in range(12):
+            a, b = (int(x) for x in rng.choice(n, 2, replace=False))
+            kind = int(rng.integers(0, 4))
+            if kind == 0:
+                circ.append((G.gate_matrix("CNOT"), (a, b)))
+            elif kind == 1:
+                circ.append((G.gate_matrix("SWAP"), (a, b)))
+            elif kind == 2:
+                circ.append((G.gate_matrix("X"), (a,)))
+            else:
+                circ.append((G.gate_matrix("CZ"), (a, b)))       # diagonal: commutes with controls only
+        a0 = rand_state(n, trial)
+        b0 = a0.copy()
+        steps, desc, _ = run_emulator(a0, n, circ, fuse=True, tile_bits=12, reg_bits=reg_bits)
+        run_oracle(b0, circ)
+        assert_close(a0, b0)
+        assert "store_perm" in desc, desc
+    # a pure SWAP network needs no rounds at all
+    circ = [(G.gate_matrix("SWAP"), (q, n - 1 - q)) for q in range(n // 2)]
+    a0 = rand_state(n, 5)
+    b0 = a0.copy()
+    steps, desc, _ = run_emulator(a0, n, circ, fuse=True, tile_bits=12, reg_bits=reg_bits)
+    run_oracle(b0, circ)
+    assert np.array_equal(a0, b0)
+    assert "rounds=0" in desc, desc
