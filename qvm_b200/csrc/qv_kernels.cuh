@@ -139,7 +139,6 @@ qv_tile_kernel(const __grid_constant__ PROG prog, const __grid_constant__ QvPeer
             const uint32_t m = FULL ? (uint32_t)M : rd.m;
             const uint32_t nslots = 1u << m;
             const uint32_t ngroups = tile_n >> m;
-            const uint32_t u_end = rd.first_uop + rd.n_uops;
             for (uint32_t g = tid; g < ngroups; g += THREADS) {
                 uint32_t e0 = g;
                 if (m > 0) e0 = qv_insert_zero(e0, rd.regpos[0]);
@@ -153,8 +152,17 @@ qv_tile_kernel(const __grid_constant__ PROG prog, const __grid_constant__ QvPeer
                     if (FULL || (uint32_t)s < nslots) a[s] = tile[se0 ^ rd.slot_xor[s]];
                     else { a[s].x = 0.0; a[s].y = 0.0; }
                 }
-                for (uint32_t u = rd.first_uop; u < u_end; u++)
-                    qv_run_uop<NS>(a, uops[u], g, blob, tables, s_slice, s_pred);
+                // Micro-op loop: the list ends with a QV_K_END sentinel, so the loop condition is the kind that is
+                // dispatched on anyway; the next header is fetched while the current micro-op runs.
+                const QvUopHead* hp = reinterpret_cast<const QvUopHead*>(uops + rd.first_uop);
+                QvUopHead nh = hp[0];
+                while ((nh.w0 & 0xffu) != QV_K_END) {
+                    const QvUopHead ch = nh;
+                    const QvUop& cu = *reinterpret_cast<const QvUop*>(hp);
+                    hp += sizeof(QvUop) / sizeof(QvUopHead);
+                    nh = hp[0];
+                    qv_run_uop<NS>(a, ch, cu, g, blob, tables, s_slice, s_pred);
+                }
 #pragma unroll
                 for (int s = 0; s < NS; s++)
                     if (FULL || (uint32_t)s < nslots) tile[se0 ^ rd.slot_xor[s]] = a[s];

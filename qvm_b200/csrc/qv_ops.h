@@ -229,83 +229,113 @@ QV_HD void qv_diagr(qvc (&a)[NS], const qvc* tab) {
     }
 }
 
-template <int NS>
-QV_HD void qv_diag1_dispatch(qvc (&a)[NS], uint32_t gate, qvc t) {
-    switch (gate) {
-        case 0: qv_diag1<NS, 0>(a, t); break;
-        case 1: qv_diag1<NS, 1>(a, t); break;
-        case 2: qv_diag1<NS, 2>(a, t); break;
-        case 3: qv_diag1<NS, 3>(a, t); break;
-        default: if (NS > 8) qv_diag1<NS, (NS > 8 ? 4 : 0)>(a, t); break;
-    }
-}
-
-template <int NS>
-QV_HD void qv_diagr_dispatch(qvc (&a)[NS], uint32_t gate, const qvc* tab) {
-    switch (gate) {
-        case 0: qv_diagr<NS, 0>(a, tab); break;
-        case 1: qv_diagr<NS, 1>(a, tab); break;
-        case 2: qv_diagr<NS, 2>(a, tab); break;
-        case 3: qv_diagr<NS, 3>(a, tab); break;
-        default: if (NS > 8) qv_diagr<NS, (NS > 8 ? 4 : 0)>(a, tab); break;
-    }
-}
-
 // log2 of the per-group run of a DIAGR table
 template <int NS>
 QV_HD constexpr uint32_t qv_slot_field(uint32_t gate) {
     return (NS == 16 ? 4u : 3u) - (gate ? 1u : 0u);
 }
 
-// Apply one micro-op to a register group.
+// The first 16 bytes of a micro-op (kind | flags << 8 | pred << 16, data, cm, cv): the kernel fetches the
+// NEXT micro-op's header while the current one runs, so that the decode latency is off the critical path.
+struct QvUopHead {
+    uint32_t w0, data, cm, cv;
+};
+
+// Rare variants (controls, predicates, scattered index fields): decoded step by step.
+template <int NS>
+QV_HD void qv_run_uop_slow(qvc (&a)[NS], const QvUopHead& h, const QvUop& u, uint32_t g, const uint8_t* blob,
+                           const qvc* tables, const qvc* slices, const uint8_t* s_pred) {
+    const uint32_t kind = h.w0 & 0xffu, flags = (h.w0 >> 8) & 0xffu;
+    if (kind < QV_K_DIAG_BASE) {
+        const qvc* M = reinterpret_cast<const qvc*>(blob + h.data);
+        if ((flags & QV_UF_PRED) && !s_pred[(h.w0 >> 16) & 0xffu]) return;
+        if (flags & QV_UF_CTRL) {
+            if ((g & h.cm) != h.cv) return;
+            qv_dense_dispatch<NS, true>(a, kind, M, u.slot_ok);
+        } else {
+            qv_dense_dispatch<NS, false>(a, kind, M, 0xffffu);
+        }
+        return;
+    }
+    // diagonal with a scattered index (QV_UF_GENERIC)
+    const QvSegList* sl = reinterpret_cast<const QvSegList*>(blob + u.segs);
+    const uint32_t idx = qv_gather32(g, sl->segs, sl->n);
+    const uint32_t gate = (kind - QV_K_DIAG_BASE) % 5u, space = (kind - QV_K_DIAG_BASE) / 5u;
+    qvc t;
+    const qvc* tab = nullptr;
+    if (space == 0) t = slices[h.data + idx];
+    else if (space == 1) t = tables[h.data + idx];
+    else if (space == 2) tab = slices + h.data + (idx << qv_slot_field<NS>(gate));
+    else if (space == 3) tab = tables + h.data + (idx << qv_slot_field<NS>(gate));
+    else tab = reinterpret_cast<const qvc*>(blob + h.data);
+    if (space < 2 && (flags & QV_UF_SCALE)) t = qv_cmul(t, slices[u.scale]);
+    switch (gate) {
+        case 0: if (space < 2) qv_diag1<NS, 0>(a, t); else qv_diagr<NS, 0>(a, tab); break;
+        case 1: if (space < 2) qv_diag1<NS, 1>(a, t); else qv_diagr<NS, 1>(a, tab); break;
+        case 2: if (space < 2) qv_diag1<NS, 2>(a, t); else qv_diagr<NS, 2>(a, tab); break;
+        case 3: if (space < 2) qv_diag1<NS, 3>(a, t); else qv_diagr<NS, 3>(a, tab); break;
+        default:
+            if (NS > 8) {
+                if (space < 2) qv_diag1<NS, (NS > 8 ? 4 : 0)>(a, t);
+                else qv_diagr<NS, (NS > 8 ? 4 : 0)>(a, tab);
+            }
+            break;
+    }
+}
+
+// Apply one micro-op to a register group: ONE flat jump on the kind, every operand already resolved.
 //   tables : the pass's global-memory table pool        slices : the per-tile slice area (shared memory)
 //   s_pred : per-tile control predicates (QvPred)
 template <int NS>
-QV_HD void qv_run_uop(qvc (&a)[NS], const QvUop& u, uint32_t g, const uint8_t* blob, const qvc* tables,
-                      const qvc* slices, const uint8_t* s_pred) {
-    const uint32_t kind = u.kind;
-    if (kind < QV_K_DIAG_BASE) {
-        const uint32_t flags = u.flags;
-        const qvc* M = reinterpret_cast<const qvc*>(blob + u.data);
-        if (flags) {
-            if ((flags & QV_UF_PRED) && !s_pred[u.pred]) return;
-            if (flags & QV_UF_CTRL) {
-                if ((g & u.cm) != u.cv) return;
-                qv_dense_dispatch<NS, true>(a, kind, M, u.slot_ok);
-                return;
-            }
-        }
-        qv_dense_dispatch<NS, false>(a, kind, M, 0xffffu);
+QV_HD void qv_run_uop(qvc (&a)[NS], const QvUopHead& h, const QvUop& u, uint32_t g, const uint8_t* blob,
+                      const qvc* tables, const qvc* slices, const uint8_t* s_pred) {
+    const uint32_t kind = h.w0 & 0xffu;
+    if (h.w0 & ((QV_UF_CTRL | QV_UF_PRED | QV_UF_GENERIC) << 8)) {
+        qv_run_uop_slow<NS>(a, h, u, g, blob, tables, slices, s_pred);
         return;
     }
-    uint32_t idx;
-    if (u.flags & QV_UF_GENERIC) {
-        const QvSegList* sl = reinterpret_cast<const QvSegList*>(blob + u.segs);
-        idx = qv_gather32(g, sl->segs, sl->n);
-    } else {
-        idx = ((g >> (u.cm & 0xffu)) & (u.cm >> 8)) | ((g >> (u.cv & 0xffu)) & (u.cv >> 8));
-    }
-    if (kind < QV_K_DIAGR_S) {
-        qvc t;
-        uint32_t gate;
-        if (kind < QV_K_DIAG1_G) {
-            gate = kind - QV_K_DIAG1_S;
-            t = slices[u.data + idx];
-        } else {
-            gate = kind - QV_K_DIAG1_G;
-            t = tables[u.data + idx];
+    const qvc* M = reinterpret_cast<const qvc*>(blob + h.data);
+    const uint32_t idx = ((g >> (h.cm & 0xffu)) & (h.cm >> 8)) | ((g >> (h.cv & 0xffu)) & (h.cv >> 8));
+#define QV_D1(RB) \
+    case QV_K_DENSE1 + 2 * RB: qv_dense1<NS, RB, true, false>(a, M, 0xffffu); break; \
+    case QV_K_DENSE1 + 2 * RB + 1: qv_dense1<NS, RB, false, false>(a, M, 0xffffu); break;
+#define QV_D2(P, RB0, RB1) \
+    case QV_K_DENSE2 + 2 * P: qv_dense2<NS, RB0, RB1, true, false>(a, M, 0xffffu); break; \
+    case QV_K_DENSE2 + 2 * P + 1: qv_dense2<NS, RB0, RB1, false, false>(a, M, 0xffffu); break;
+#define QV_DG(G) \
+    case QV_K_DIAG1_S + G: { \
+        qvc t = slices[h.data + idx]; \
+        if (h.w0 & (QV_UF_SCALE << 8)) t = qv_cmul(t, slices[u.scale]); \
+        qv_diag1<NS, G>(a, t); \
+        break; \
+    } \
+    case QV_K_DIAG1_G + G: { \
+        qvc t = tables[h.data + idx]; \
+        if (h.w0 & (QV_UF_SCALE << 8)) t = qv_cmul(t, slices[u.scale]); \
+        qv_diag1<NS, G>(a, t); \
+        break; \
+    } \
+    case QV_K_DIAGR_S + G: qv_diagr<NS, G>(a, slices + h.data + (idx << qv_slot_field<NS>(G))); break; \
+    case QV_K_DIAGR_G + G: qv_diagr<NS, G>(a, tables + h.data + (idx << qv_slot_field<NS>(G))); break; \
+    case QV_K_DIAGR_C + G: qv_diagr<NS, G>(a, M); break;
+    if (NS == 16) {
+        switch (kind) {
+            QV_D1(0) QV_D1(1) QV_D1(2) QV_D1(3)
+            QV_D2(0, 0, 1) QV_D2(1, 0, 2) QV_D2(2, 1, 2) QV_D2(3, 0, 3) QV_D2(4, 1, 3) QV_D2(5, 2, 3)
+            QV_DG(0) QV_DG(1) QV_DG(2) QV_DG(3) QV_DG(4)
+            default: break;
         }
-        if (u.flags & QV_UF_SCALE) t = qv_cmul(t, slices[u.scale]);
-        qv_diag1_dispatch<NS>(a, gate, t);
-    } else if (kind < QV_K_DIAGR_G) {
-        const uint32_t gate = kind - QV_K_DIAGR_S;
-        qv_diagr_dispatch<NS>(a, gate, slices + u.data + (idx << qv_slot_field<NS>(gate)));
-    } else if (kind < QV_K_DIAGR_C) {
-        const uint32_t gate = kind - QV_K_DIAGR_G;
-        qv_diagr_dispatch<NS>(a, gate, tables + u.data + (idx << qv_slot_field<NS>(gate)));
     } else {
-        qv_diagr_dispatch<NS>(a, kind - QV_K_DIAGR_C, reinterpret_cast<const qvc*>(blob + u.data));
+        switch (kind) {
+            QV_D1(0) QV_D1(1) QV_D1(2)
+            QV_D2(0, 0, 1) QV_D2(1, 0, 2) QV_D2(2, 1, 2)
+            QV_DG(0) QV_DG(1) QV_DG(2) QV_DG(3)
+            default: break;
+        }
     }
+#undef QV_D1
+#undef QV_D2
+#undef QV_DG
 }
 
 // Entry x of a slice for the tile at hand: the product of its sources (src_ext[s] = the source's

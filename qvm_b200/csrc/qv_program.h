@@ -60,7 +60,8 @@ enum QvUopKind : uint32_t {
     QV_K_DIAGR_S = 30,       // + GATE
     QV_K_DIAGR_G = 35,       // + GATE
     QV_K_DIAGR_C = 40,       // + GATE   (index has register bits only, no per-tile part)
-    QV_K_COUNT = 45,
+    QV_K_END = 45,           // terminates the micro-op list of a round (the kernel loops on the kind alone)
+    QV_K_COUNT = 46,
 };
 
 enum QvUopFlags : uint32_t {

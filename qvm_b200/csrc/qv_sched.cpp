@@ -619,6 +619,11 @@ void emit_round(BlobWriter& w, const std::vector<RoundOp>& rops, const std::vect
         if (getenv("QV_SCHED_DEBUG")) fprintf(stderr, "  DIAG group: %zu factors -> %zu chunks (slice entries so far %zu, build %zu)\n", nf, plan.size(), w.slice_entries, w.slice_build);
     }
     rd.n_uops = (uint32_t)w.uops.size() - rd.first_uop;
+    {
+        QvUop end{};
+        end.kind = QV_K_END;        // the kernel's micro-op loop stops on it
+        w.uops.push_back(end);
+    }
     w.rounds.push_back(rd);
     if (getenv("QV_SCHED_DEBUG")) {
         fprintf(stderr, " ROUND regpos:");
@@ -700,15 +705,13 @@ struct Geometry {
     int reg_bits;       // 0 = choose per pass (4 for passes that carry many gates, else 3)
 };
 
-// Work estimate of a pass: dense atoms and diagonal atoms it carries.  Passes with many gates run on the
-// 128-thread / 16-amplitudes-per-thread kernel (micro-op decode amortised over twice the amplitudes, fewer
-// rounds); light passes keep the 256-thread kernel, which is the better HBM streamer.
-int choose_reg_bits(const std::vector<const Atom*>& atoms, const Geometry& geo) {
-    if (geo.reg_bits) return geo.reg_bits;
-    if (geo.T != QV_MAX_TILE_BITS) return 3;
-    size_t dense = 0, diag = 0;
-    for (const Atom* a : atoms) (a->kind == Atom::DENSE ? dense : diag)++;
-    return (dense >= 4 || dense + diag >= 12) ? 4 : 3;
+// Amplitudes per thread per round.  Measured on B200 (gpurun_out/configs_j_m{3,4}.jsonl, QFT-30 launch lists):
+// the 256-thread / 8-amplitude kernel beats the 128-thread / 16-amplitude one on every configuration (QFT-30
+// heavy passes 14.4 vs 16.3 ms, random layers 25q 9.6 vs 12.6 ms) although it executes 35 % more instructions:
+// the interpreter is latency-bound, and 24 resident warps per SM hide more of it than 12.  The 16-amplitude
+// format stays available (CompileOptions::reg_bits = 4, QVMCUDA_REG_BITS=4) and tested.
+int choose_reg_bits(const std::vector<const Atom*>&, const Geometry& geo) {
+    return geo.reg_bits ? geo.reg_bits : 3;
 }
 
 // tile_targets: physical bits that must be inside the tile.
@@ -902,6 +905,7 @@ Step build_tile_step(const std::vector<const Atom*>& atoms_in, uint64_t tile_tar
     h.blob_bytes = (uint32_t)off;
     if (off > QV_PROG_LARGE_BYTES) throw std::length_error("pass control program too large");
     for (QvUop& u : w.uops) {
+        if (u.kind == QV_K_END) continue;
         if (u.kind < QV_K_DIAG_BASE || u.kind >= QV_K_DIAGR_C) u.data += h.off_matrices;
         if (u.kind >= QV_K_DIAG_BASE && (u.flags & QV_UF_GENERIC)) u.segs = (uint16_t)(off_seglists + u.segs * sizeof(QvSegList));
     }

@@ -56,6 +56,7 @@ void run_tile_step(qvc* const* peers, const qv::Step& st) {
         for (uint32_t r = 0; r < h.n_rounds; r++) {
             const QvRound& rd = rounds[r];
             if (rd.m > h.reg_bits) throw std::runtime_error("emulator: round uses more register bits than the pass declares");
+            if (uops[rd.first_uop + rd.n_uops].kind != QV_K_END) throw std::runtime_error("emulator: round without an end sentinel");
             const uint32_t ngroups = tile_n >> rd.m;
             for (uint32_t g = 0; g < ngroups; g++) {
                 uint32_t e0 = g;
@@ -67,8 +68,11 @@ void run_tile_step(qvc* const* peers, const qv::Step& st) {
                         if (s < (1u << rd.m)) a[s] = smem[se0 ^ rd.slot_xor[s]];
                         else { a[s].x = 0.0; a[s].y = 0.0; }
                     }
-                    for (uint32_t u = rd.first_uop; u < rd.first_uop + rd.n_uops; u++)
-                        qv_run_uop<8>(a, uops[u], g, blob, tables, s_slice.data(), s_pred.data());
+                    for (uint32_t u = rd.first_uop; uops[u].kind != QV_K_END; u++) {   // sentinel-terminated, as in the kernel
+                        QvUopHead hd;
+                        std::memcpy(&hd, &uops[u], sizeof(hd));
+                        qv_run_uop<8>(a, hd, uops[u], g, blob, tables, s_slice.data(), s_pred.data());
+                    }
                     for (uint32_t s = 0; s < (1u << rd.m); s++) smem[se0 ^ rd.slot_xor[s]] = a[s];
                 } else {                    // the 16-slot instantiation, as the 128-thread kernel
                     qvc a[16];
@@ -76,8 +80,11 @@ void run_tile_step(qvc* const* peers, const qv::Step& st) {
                         if (s < (1u << rd.m)) a[s] = smem[se0 ^ rd.slot_xor[s]];
                         else { a[s].x = 0.0; a[s].y = 0.0; }
                     }
-                    for (uint32_t u = rd.first_uop; u < rd.first_uop + rd.n_uops; u++)
-                        qv_run_uop<16>(a, uops[u], g, blob, tables, s_slice.data(), s_pred.data());
+                    for (uint32_t u = rd.first_uop; uops[u].kind != QV_K_END; u++) {   // sentinel-terminated, as in the kernel
+                        QvUopHead hd;
+                        std::memcpy(&hd, &uops[u], sizeof(hd));
+                        qv_run_uop<16>(a, hd, uops[u], g, blob, tables, s_slice.data(), s_pred.data());
+                    }
                     for (uint32_t s = 0; s < (1u << rd.m); s++) smem[se0 ^ rd.slot_xor[s]] = a[s];
                 }
             }
