@@ -75,6 +75,10 @@ struct qvmcuda_state {
     qvc* d_alt = nullptr;
     QvPeers peers_alt{};
     bool remap_pull = false;       // every rank has attached every rank's alternate buffer
+    // sampler scratch: block sums (two levels) + top prefix; per-shot uniforms / results
+    double* d_sample_tree = nullptr;
+    void* d_shots = nullptr;
+    uint64_t shot_cap = 0;
     // immediate-mode program upload
     uint8_t* d_scratch = nullptr;
     uint8_t* h_scratch = nullptr;  // pinned
@@ -420,6 +424,8 @@ int qvmcuda_state_destroy(qvmcuda_state* s) {
         cudaFree(s->d_partial);
         if (s->d_scratch) cudaFree(s->d_scratch);
         if (s->h_scratch) cudaFreeHost(s->h_scratch);
+        if (s->d_sample_tree) cudaFree(s->d_sample_tree);
+        if (s->d_shots) cudaFree(s->d_shots);
         if (s->upload_done) cudaEventDestroy(s->upload_done);
         if (s->own_stream && s->stream) cudaStreamDestroy(s->stream);
         s->d_amps = nullptr;
@@ -734,13 +740,23 @@ int qvmcuda_sample(qvmcuda_state* s, const double* uniforms, uint64_t n_shots, u
     if (int rc = canonicalize_locked(s)) return rc;
     const uint64_t n1 = (s->n_amps + QV_SB - 1) / QV_SB;
     const uint64_t n2 = (n1 + QV_SB - 1) / QV_SB;
-    double *d_l1 = nullptr, *d_l2 = nullptr, *d_top = nullptr, *d_u = nullptr;
-    uint64_t* d_out = nullptr;
-    CK(cudaMallocAsync((void**)&d_l1, n1 * sizeof(double), s->stream));
-    CK(cudaMallocAsync((void**)&d_l2, n2 * sizeof(double), s->stream));
-    CK(cudaMallocAsync((void**)&d_top, n2 * sizeof(double), s->stream));
-    CK(cudaMallocAsync((void**)&d_u, n_shots * sizeof(double), s->stream));
-    CK(cudaMallocAsync((void**)&d_out, n_shots * sizeof(uint64_t), s->stream));
+    // Persistent scratch (no allocation on the measurement path): the two summation levels + top prefix live
+    // with the state, the per-shot buffers grow on demand.
+    if (!s->d_sample_tree) CK(cudaMalloc((void**)&s->d_sample_tree, (n1 + 2 * n2) * sizeof(double)));
+    if (n_shots > s->shot_cap) {
+        CK(cudaStreamSynchronize(s->stream));
+        if (s->d_shots) cudaFree(s->d_shots);
+        s->d_shots = nullptr;
+        s->shot_cap = 0;
+        const uint64_t cap = n_shots < 4096 ? 4096 : n_shots + n_shots / 2;
+        CK(cudaMalloc((void**)&s->d_shots, cap * (sizeof(double) + sizeof(uint64_t))));
+        s->shot_cap = cap;
+    }
+    double* d_l1 = s->d_sample_tree;
+    double* d_l2 = d_l1 + n1;
+    double* d_top = d_l2 + n2;
+    uint64_t* d_out = reinterpret_cast<uint64_t*>(s->d_shots);
+    double* d_u = reinterpret_cast<double*>(d_out + s->shot_cap);
     CK(cudaMemcpyAsync(d_u, uniforms, n_shots * sizeof(double), cudaMemcpyHostToDevice, s->stream));
     auto warps_grid = [&](uint64_t blocks) {
         uint64_t g = (blocks * 32 + QV_THREADS - 1) / QV_THREADS;
@@ -755,11 +771,6 @@ int qvmcuda_sample(qvmcuda_state* s, const double* uniforms, uint64_t n_shots, u
     g_launches += 4;
     CK(cudaGetLastError());
     CK(cudaMemcpyAsync(out, d_out, n_shots * sizeof(uint64_t), cudaMemcpyDeviceToHost, s->stream));
-    cudaFreeAsync(d_l1, s->stream);
-    cudaFreeAsync(d_l2, s->stream);
-    cudaFreeAsync(d_top, s->stream);
-    cudaFreeAsync(d_u, s->stream);
-    cudaFreeAsync(d_out, s->stream);
     CK(cudaStreamSynchronize(s->stream));
     return 0;
 }

@@ -25,6 +25,11 @@ METRICS = [
     ("smsp__average_warps_issue_stalled_barrier_per_issue_active.ratio", "stall barrier"),
     ("smsp__average_warps_issue_stalled_mio_throttle_per_issue_active.ratio", "stall mio_throttle"),
     ("smsp__average_warps_issue_stalled_lg_throttle_per_issue_active.ratio", "stall lg_throttle"),
+    ("smsp__average_warps_issue_stalled_wait_per_issue_active.ratio", "stall wait (fixed latency)"),
+    ("smsp__average_warps_issue_stalled_no_instruction_per_issue_active.ratio", "stall no_instruction"),
+    ("smsp__average_warps_issue_stalled_math_pipe_throttle_per_issue_active.ratio", "stall math_pipe_throttle"),
+    ("smsp__inst_executed.sum", "warp instructions"),
+    ("sm__inst_executed.avg.per_cycle_active", "IPC per SM"),
     ("l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum", "smem bank conflicts"),
     ("l1tex__data_pipe_lsu_wavefronts_mem_shared.sum", "smem wavefronts"),
 ]
@@ -32,14 +37,19 @@ METRICS = [
 lines = [f"# {title}", ""]
 rows = [r for r in csv.reader(open(launches)) if len(r) > 5]
 hdr = rows[0]
-ik, iv, iu = hdr.index("Kernel Name"), hdr.index("Metric Value"), hdr.index("Metric Unit")
-lines += ["## Launch list (`ncu --metrics gpu__time_duration.sum --clock-control none`; cold-cache, serialised: compare shares)", "",
-          "| # | kernel | duration |", "|---|---|---|"]
+ik, iv, im, ii = hdr.index("Kernel Name"), hdr.index("Metric Value"), hdr.index("Metric Name"), hdr.index("ID")
+byid = {}
+for r in rows[1:]:
+    d = byid.setdefault(r[ii], {"name": r[ik].split("(")[0].replace("void ", "")[:60]})
+    d[r[im]] = float(r[iv].replace(",", ""))
+lines += ["## Launch list (`ncu --metrics gpu__time_duration.sum,smsp__inst_executed.sum --clock-control none`; cold-cache, "
+          "serialised: compare shares)", "", "| # | kernel | duration | warp instructions |", "|---|---|---|---|"]
 tot = {}
-for i, r in enumerate(rows[1:]):
-    name = r[ik].split("(")[0].replace("void ", "")[:60]
-    lines.append(f"| {i} | `{name}` | {float(r[iv]) / 1e6:.3f} ms |")
-    tot[name] = tot.get(name, 0.0) + float(r[iv])
+for i, d in byid.items():
+    t = d.get("gpu__time_duration.sum", 0.0)
+    n = d.get("smsp__inst_executed.sum")
+    lines.append(f"| {i} | `{d['name']}` | {t / 1e6:.3f} ms | {'' if n is None else f'{n / 1e9:.3f} G'} |")
+    tot[d["name"]] = tot.get(d["name"], 0.0) + t
 all_t = sum(tot.values())
 lines += ["", "| kernel | total | share |", "|---|---|---|"]
 for k, v in sorted(tot.items(), key=lambda kv: -kv[1]):
