@@ -129,6 +129,19 @@ struct QvRound {
                                         // shared-memory slot of (e0 | dep) is qv_swz(e0) ^ slot_xor[r]
 };                                  // 64 bytes
 
+// Pull remap (multi-GPU): every rank gathers the amplitudes it will own AFTER the physical bit swaps
+// (local_bit[i] <-> global_bit[i]) from the current buffers of all ranks into its alternate buffer; then all
+// ranks flip buffers.  Each amplitude crosses NVLink exactly once (an in-place exchange through the tile
+// kernel moves it twice: pulled by the rank that handles the tile and pushed back).
+struct QvRemap {
+    uint32_t n_pairs;
+    uint32_t n_local_bits;
+    uint32_t rank;
+    uint32_t pad;
+    uint32_t local_bit[8];
+    uint32_t global_bit[8];
+};
+
 struct QvPassHeader {
     uint32_t T;                     // tile bits
     uint32_t reg_bits;              // 3: 256-thread kernel, 8 amplitudes per thread; 4: 128-thread kernel, 16 per thread
@@ -157,19 +170,15 @@ struct QvPassHeader {
     uint16_t st_const;              // qv_swz(b)
     uint16_t st_pad;
     uint16_t st_hi[32];             // qv_swz(A ((block size)*i))
-};
-
-// Pull remap (multi-GPU): every rank gathers the amplitudes it will own AFTER the physical bit swaps
-// (local_bit[i] <-> global_bit[i]) from the current buffers of all ranks into its alternate buffer; then all
-// ranks flip buffers.  Each amplitude crosses NVLink exactly once (an in-place exchange through the tile
-// kernel moves it twice: pulled by the rank that handles the tile and pushed back).
-struct QvRemap {
-    uint32_t n_pairs;
-    uint32_t n_local_bits;
-    uint32_t rank;
-    uint32_t pad;
-    uint32_t local_bit[8];
-    uint32_t global_bit[8];
+    // Fused pull remap (multi-GPU): the pass READS through a pending qubit remap -- element p of this rank's
+    // new shard is amplitude S(rank, p) of the ranks' CURRENT buffers, S = the index with every
+    // (local_bit, global_bit) pair exchanged -- and WRITES its results into the alternate buffer; all ranks
+    // flip buffers afterwards.  The exchange costs no pass of its own.  S is GF(2)-linear, so
+    // S(pbase | hi_off[i]) = S(pbase) ^ hi_src[i] with hi_src host-precomputed.
+    uint32_t pull;                  // 0: in place
+    uint32_t pull_pad;
+    QvRemap pull_remap;
+    uint64_t hi_src[32];            // S(hi_off[i])
 };
 
 // A k>=3 dense gate runs as its own pass through the generic kernel.

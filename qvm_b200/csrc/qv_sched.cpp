@@ -947,6 +947,40 @@ Step build_big_step(const Atom& a, const Geometry& geo, const Layout& lay) {
     return st;
 }
 
+// A pull remap followed by a local tile pass becomes ONE pass that loads through the remap (from every rank's
+// current buffer, over NVLink where the source is remote) and stores into the alternate buffer.
+void fuse_pulls(Tape& tape, const CompileOptions& opt) {
+    if (!opt.remap_pull || !opt.fuse_pull) return;
+    std::vector<Step> out;
+    for (size_t i = 0; i < tape.steps.size(); i++) {
+        Step& st = tape.steps[i];
+        if (st.kind == Step::REMAP && i + 1 < tape.steps.size() && tape.steps[i + 1].kind == Step::TILE &&
+            !tape.steps[i + 1].uses_peers) {
+            Step nx = std::move(tape.steps[i + 1]);
+            QvPassHeader h;
+            std::memcpy(&h, nx.blob.data(), sizeof(h));
+            h.pull = 1;
+            h.pull_remap = st.remap;
+            for (int k = 0; k < 32; k++) {
+                uint64_t S = h.hi_off[k];
+                for (uint32_t p = 0; p < st.remap.n_pairs; p++) {
+                    const uint64_t x = ((h.hi_off[k] >> st.remap.local_bit[p]) ^ (h.hi_off[k] >> st.remap.global_bit[p])) & 1ull;
+                    S ^= (x << st.remap.local_bit[p]) | (x << st.remap.global_bit[p]);
+                }
+                h.hi_src[k] = S;
+            }
+            std::memcpy(nx.blob.data(), &h, sizeof(h));
+            nx.uses_peers = true;       // reads peer shards: the host barriers around it
+            nx.is_remap = true;
+            out.push_back(std::move(nx));
+            i++;
+            continue;
+        }
+        out.push_back(std::move(st));
+    }
+    tape.steps.swap(out);
+}
+
 }  // namespace
 
 Tape compile(const std::vector<Gate>& gates, int n_bits, const CompileOptions& opt,
@@ -1122,6 +1156,7 @@ Tape compile(const std::vector<Gate>& gates, int n_bits, const CompileOptions& o
         }
         tape.l2p.resize(n_bits);
         for (int q = 0; q < n_bits; q++) tape.l2p[q] = w2p[wire_of[q]];
+        fuse_pulls(tape, opt);
         return tape;
     }
 
@@ -1205,6 +1240,7 @@ Tape compile(const std::vector<Gate>& gates, int n_bits, const CompileOptions& o
     }
     tape.l2p.resize(n_bits);
     for (int q = 0; q < n_bits; q++) tape.l2p[q] = w2p[wire_of[q]];
+    fuse_pulls(tape, opt);
     return tape;
 }
 
@@ -1226,7 +1262,7 @@ std::string describe(const Tape& t) {
         }
         QvPassHeader h;
         std::memcpy(&h, s.blob.data(), sizeof(h));
-        os << "  [" << i << "] " << (s.is_remap ? "REMAP" : (s.uses_peers ? "PEER" : "TILE")) << " T=" << h.T
+        os << "  [" << i << "] " << (h.pull ? "PULL+TILE" : s.is_remap ? "REMAP" : (s.uses_peers ? "PEER" : "TILE")) << " T=" << h.T
            << " m=" << h.reg_bits << " atoms=" << s.n_gates << " rounds=" << h.n_rounds << " uops=" << h.n_uops << " diag_uops=" << h.n_diag_uops
            << " slices=" << h.n_slices << " sources=" << h.n_sources << " slice_entries=" << h.n_slice_entries
            << (h.store_perm ? " store_perm" : "") << " bytes=" << h.blob_bytes << " tables=" << h.n_table_entries << " tilebits=";

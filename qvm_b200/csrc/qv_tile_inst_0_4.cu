@@ -1,0 +1,4 @@
+// tile kernel, mode 0 (local), 16 amplitudes per thread
+#define QV_INST_MODE 0
+#define QV_INST_M 4
+#include "qv_tile_inst.cuh"

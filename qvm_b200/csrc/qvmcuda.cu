@@ -12,6 +12,7 @@
 
 #include "../../include/qvmcuda.h"
 #include "qv_kernels.cuh"
+#include "qv_tile_launch.h"
 #include "qv_sched.h"
 
 namespace {
@@ -120,43 +121,52 @@ int tile_grid(const qvmcuda_state* s, uint64_t n_tiles) {
     return (int)(n_tiles < cap ? n_tiles : cap);
 }
 
-template <typename PROG, bool PEERS, bool FULL, int M>
-int launch_tile_t(qvmcuda_state* s, const qv::Step& st, const QvPassHeader& h, const uint8_t* d_tables) {
-    static std::atomic<bool> attr_set{false};
-    if (!attr_set.exchange(true)) {
-        CK(cudaFuncSetAttribute(qv_tile_kernel<PROG, PEERS, FULL, M>, cudaFuncAttributeMaxDynamicSharedMemorySize, 65536));
-        CK(cudaFuncSetAttribute(qv_tile_kernel<PROG, PEERS, FULL, M>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
-    }
-    static thread_local PROG prog;   // 28 KiB: keep it off the stack
-    std::memcpy(prog.bytes, st.blob.data(), st.blob.size());
-    const size_t smem = (size_t)sizeof(qvc) << h.T;
-    const int threads = M == 4 ? QV_THREADS_WIDE : QV_THREADS;
-    qv_tile_kernel<PROG, PEERS, FULL, M><<<tile_grid(s, h.n_tiles), threads, smem, s->stream>>>(prog, s->peers, (const qvc*)d_tables);
-    g_launches++;
-    CK(cudaGetLastError());
-    return 0;
-}
-
-template <typename PROG>
+// The tile-kernel instantiations are compiled in their own translation units (qv_tile_inst_*.cu), one per
+// (mode, register bits), so that the build runs in parallel; each exports one launcher.
 int launch_tile_p(qvmcuda_state* s, const qv::Step& st, const QvPassHeader& h, const uint8_t* d_tables) {
     const bool full = h.T == QV_MAX_TILE_BITS;
-    if (h.reg_bits == 4) {
-        // the 16-amplitudes-per-thread kernel exists for full tiles only (the scheduler never asks otherwise)
-        if (!full || h.threads_log2 != 7) return fail("4 register bits need a full 12-bit tile");
-        return h.uses_peers ? launch_tile_t<PROG, true, true, 4>(s, st, h, d_tables) : launch_tile_t<PROG, false, true, 4>(s, st, h, d_tables);
+    int mode = 0;
+    if (h.pull) {
+        if (!s->remap_pull || !s->d_alt) return fail("pull pass without an attached alternate buffer");
+        if (h.uses_peers) return fail("malformed pass header: pull pass whose tile spans rank bits");
+        mode = 2;
+    } else if (h.uses_peers) {
+        mode = 1;
     }
-    if (h.reg_bits != 3 || h.threads_log2 != 8) return fail("malformed pass header");
-    if (h.uses_peers) return full ? launch_tile_t<PROG, true, true, 3>(s, st, h, d_tables) : launch_tile_t<PROG, true, false, 3>(s, st, h, d_tables);
-    return full ? launch_tile_t<PROG, false, true, 3>(s, st, h, d_tables) : launch_tile_t<PROG, false, false, 3>(s, st, h, d_tables);
+    QvTileLaunch L;
+    L.blob = st.blob.data();
+    L.blob_bytes = st.blob.size();
+    L.full = full;
+    L.grid = tile_grid(s, h.n_tiles);
+    L.smem = (size_t)sizeof(qvc) << h.T;
+    L.stream = s->stream;
+    L.peers = &s->peers;
+    L.tables = (const qvc*)d_tables;
+    L.alt_own = s->d_alt;
+    const char* err = nullptr;
+    if (h.reg_bits == 4) {
+        // the 16-amplitudes-per-thread kernel exists for full local tiles only (the scheduler never asks otherwise)
+        if (!full || h.threads_log2 != 7 || mode != 0) return fail("4 register bits need a full 12-bit local tile");
+        err = qv_launch_tile_0_4(L);
+    } else {
+        if (h.reg_bits != 3 || h.threads_log2 != 8) return fail("malformed pass header");
+        err = mode == 0 ? qv_launch_tile_0_3(L) : mode == 1 ? qv_launch_tile_1_3(L) : qv_launch_tile_2_3(L);
+    }
+    if (err) return fail(std::string("tile kernel launch: ") + err);
+    g_launches++;
+    if (mode == 2) {    // pull pass: results sit in the alternate buffers; every rank flips after the same step
+        std::swap(s->d_amps, s->d_alt);
+        std::swap(s->peers, s->peers_alt);
+    }
+    return 0;
 }
 
 int launch_tile(qvmcuda_state* s, const qv::Step& st, const uint8_t* d_tables) {
     QvPassHeader h;
     std::memcpy(&h, st.blob.data(), sizeof(h));
     if (st.blob.size() > QV_PROG_LARGE_BYTES) return fail("pass control program too large");
-    if (h.uses_peers && s->world < 2) return fail("peer pass on a state without attached peers");
-    return st.blob.size() <= QV_PROG_SMALL_BYTES ? launch_tile_p<QvProgSmall>(s, st, h, d_tables)
-                                                 : launch_tile_p<QvProgLarge>(s, st, h, d_tables);
+    if ((h.uses_peers || h.pull) && s->world < 2) return fail("peer pass on a state without attached peers");
+    return launch_tile_p(s, st, h, d_tables);
 }
 
 int launch_big(qvmcuda_state* s, const qv::Step& st, const uint8_t* d_mat) {

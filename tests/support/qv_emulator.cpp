@@ -17,7 +17,8 @@
 namespace {
 
 // peers[r] = base pointer of rank r's shard (peers[0] for a single device)
-void run_tile_step(qvc* const* peers, const qv::Step& st) {
+// pull passes (header.pull): loads go through the remap from the current buffers, stores into alt_own
+void run_tile_step(qvc* const* peers, const qv::Step& st, qvc* alt_own = nullptr) {
     const uint8_t* blob = st.blob.data();
     QvPassHeader h;
     std::memcpy(&h, blob, sizeof(h));
@@ -39,6 +40,17 @@ void run_tile_step(qvc* const* peers, const qv::Step& st) {
         h.n_slices > QV_MAX_SLICES)
         throw std::runtime_error("emulator: per-tile table limits exceeded");
     auto addr = [&](uint64_t p) { return peers[p >> h.n_local_bits] + (p & local_mask); };
+    if (h.pull && !alt_own) throw std::runtime_error("emulator: pull pass without an alternate buffer");
+    // the kernel's split source index: S(base | gather(tid)) ^ hi_src[i]
+    auto src_index = [&](uint64_t base, uint32_t e) {
+        const uint64_t P = base | qv_gather(e & (threads - 1), h.tile_segs, h.n_tile_segs);
+        uint64_t S = P;
+        for (uint32_t i = 0; i < h.pull_remap.n_pairs; i++) {
+            const uint64_t x = ((P >> h.pull_remap.local_bit[i]) ^ (P >> h.pull_remap.global_bit[i])) & 1ull;
+            S ^= (x << h.pull_remap.local_bit[i]) | (x << h.pull_remap.global_bit[i]);
+        }
+        return S ^ h.hi_src[e >> h.threads_log2];
+    };
     // the split address computation of the kernel: (base | gather(tid)) | hi_off[i] for e = tid + threads*i
     auto phys = [&](uint64_t base, uint32_t e) {
         return base | qv_gather(e & (threads - 1), h.tile_segs, h.n_tile_segs) | h.hi_off[e >> h.threads_log2];
@@ -52,7 +64,7 @@ void run_tile_step(qvc* const* peers, const qv::Step& st) {
             const QvSlice& sl = slices[slice_of[f]];
             s_slice[f] = qv_slice_entry(sl, sources, s_srcext.data(), tables, f - sl.off);
         }
-        for (uint32_t e = 0; e < tile_n; e++) smem[qv_swz(e)] = *addr(phys(base, e));
+        for (uint32_t e = 0; e < tile_n; e++) smem[qv_swz(e)] = h.pull ? *addr(src_index(base, e)) : *addr(phys(base, e));
         for (uint32_t r = 0; r < h.n_rounds; r++) {
             const QvRound& rd = rounds[r];
             if (rd.m > h.reg_bits) throw std::runtime_error("emulator: round uses more register bits than the pass declares");
@@ -97,7 +109,8 @@ void run_tile_step(qvc* const* peers, const qv::Step& st) {
                     if ((e & (threads - 1)) >> k & 1) slot ^= h.st_col[k];
                 slot ^= h.st_hi[e >> h.threads_log2];
             }
-            *addr(phys(base, e)) = smem[slot];
+            if (h.pull) alt_own[phys(base, e) & local_mask] = smem[slot];
+            else *addr(phys(base, e)) = smem[slot];
         }
     }
 }
@@ -257,13 +270,20 @@ extern "C" int qvtest_run_sharded(double* psi, int n_bits, int world, int n_gate
                 peer_steps++;
                 continue;
             }
+            bool pull = false;
             for (int r = 0; r < world; r++) {
                 const qv::Step& st = tapes[r].steps[i];
                 if (st.kind != tapes[0].steps[i].kind || st.uses_peers != tapes[0].steps[i].uses_peers)
                     throw std::runtime_error("ranks disagree on a step");
-                if (st.kind == qv::Step::TILE) run_tile_step(peers.data(), st);
-                else run_big_step(peers[r], n_local, st);
+                if (st.kind == qv::Step::TILE) {
+                    QvPassHeader hh;
+                    std::memcpy(&hh, st.blob.data(), sizeof(hh));
+                    if (r == 0) pull = hh.pull != 0;
+                    else if (pull != (hh.pull != 0)) throw std::runtime_error("ranks disagree on a pull pass");
+                    run_tile_step(peers.data(), st, pull ? alts[r] : nullptr);
+                } else run_big_step(peers[r], n_local, st);
             }
+            if (pull) std::swap(peers, alts);   // every rank flips after the same step
             if (tapes[0].steps[i].uses_peers) peer_steps++;
         }
         if (peers[0] != (qvc*)psi)   // an odd number of flips: the result sits in the alternate buffers

@@ -49,7 +49,7 @@ def test_index_tracer_through_remaps(pull):
     psi = np.arange(1 << n).astype(np.complex128)
     ref = run_oracle(psi.copy(), circ)
     _, peer_steps, desc, l2p = run_emulator_sharded(psi, n, world, circ, fuse=True, tile_bits=6, remap_pull=pull)
-    assert peer_steps >= 1 and (("REMAP(pull)" in desc) == pull), desc
+    assert peer_steps >= 1 and ((("REMAP(pull)" in desc) or ("PULL+TILE" in desc)) == pull), desc
     assert np.array_equal(unpermute(psi, l2p), ref)
 
 
