@@ -91,6 +91,9 @@ int qvmcuda_prob_excited(qvmcuda_state *s, int qubit, double *p);
 int qvmcuda_prob_ground(qvmcuda_state *s, int qubit, double *p);
 /* NORM / NORMALIZE-WAVEFUNCTION src/wavefunction.lisp:333-364 */
 int qvmcuda_norm2(qvmcuda_state *s, double *sum_of_squares);
+/* <a|b> = sum conj(a_i) b_i: the INNER-PRODUCT of PURE-STATE-EXPECTATION (app/src/api/expectation.lisp:78-91),
+ * out[0] = real part, out[1] = imaginary part.  Both states on the same device, same length. */
+int qvmcuda_inner_product(qvmcuda_state *a, qvmcuda_state *b, double out[2]);
 int qvmcuda_scale(qvmcuda_state *s, double factor);
 int qvmcuda_normalize(qvmcuda_state *s);
 /* FORCE-MEASUREMENT (pure-state) src/measurement.lisp:10-41: amplitudes whose QUBIT bit differs from

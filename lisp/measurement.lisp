@@ -64,3 +64,17 @@ uniforms are drawn here, the prefix structure and the searches run on the GPU."
       (sample (device-handle state) u num-samples out 0)
       (dotimes (i num-samples samples)
         (setf (aref samples i) (cffi:mem-aref out :uint64 i))))))
+
+(defun pure-state-expectation/cuda (qvm prepared-state op &optional first-time)
+  "PURE-STATE-EXPECTATION (app/src/api/expectation.lisp:78-91) with both wavefunctions on the device:
+PREPARED-STATE is a DEVICE-PURE-STATE holding a copy of the prepared wavefunction; OP is run on QVM's own
+state and <prepared | OP prepared> is reduced on the GPU instead of the host LOOP :sum."
+  (unless first-time
+    (copy-state (device-handle (qvm::state qvm)) (device-handle prepared-state))
+    (setf (device-newer-p (qvm::state qvm)) t))
+  (qvm:load-program qvm op)
+  (qvm:run qvm)
+  (flush-gate-tape (qvm::state qvm))
+  (cffi:with-foreign-object (out :double 2)
+    (inner-product (device-handle prepared-state) (device-handle (qvm::state qvm)) out)
+    (complex (cffi:mem-aref out :double 0) (cffi:mem-aref out :double 1))))

@@ -12,4 +12,5 @@
            #:*cuda-device*
            #:*cuda-lazy-mirror*
            #:flush-gate-tape
-           #:sample-wavefunction-multiple-times/cuda))
+           #:sample-wavefunction-multiple-times/cuda
+           #:pure-state-expectation/cuda))

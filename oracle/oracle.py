@@ -49,6 +49,7 @@ def lib():
             getattr(L, f).restype = dbl; getattr(L, f).argtypes = [vp, u64, i32]
         for f in ("orc_norm2", "orc_norm"):
             getattr(L, f).restype = dbl; getattr(L, f).argtypes = [vp, u64]
+        L.orc_inner_product.restype = None; L.orc_inner_product.argtypes = [vp, vp, u64, vp]
         L.orc_scale.restype = None; L.orc_scale.argtypes = [vp, u64, dbl]
         L.orc_normalize.restype = None; L.orc_normalize.argtypes = [vp, u64]
         L.orc_force_measurement.restype = None; L.orc_force_measurement.argtypes = [vp, u64, i32, i32, dbl]
@@ -130,6 +131,13 @@ def prob_excited(psi, q): return float(lib().orc_prob_excited(_p(_state(psi)), p
 def prob_ground(psi, q): return float(lib().orc_prob_ground(_p(_state(psi)), psi.size, q))
 def norm2(psi): return float(lib().orc_norm2(_p(_state(psi)), psi.size))
 def norm(psi): return float(lib().orc_norm(_p(_state(psi)), psi.size))
+
+
+def inner_product(a, b) -> complex:
+    """<a|b> as PURE-STATE-EXPECTATION sums it (app/src/api/expectation.lisp:79-84)."""
+    out = np.zeros(2, dtype=np.float64)
+    lib().orc_inner_product(_p(_state(a)), _p(_state(b)), a.size, _p(out))
+    return complex(out[0], out[1])
 def scale(psi, a): lib().orc_scale(_p(_state(psi)), psi.size, a); return psi
 def normalize(psi): lib().orc_normalize(_p(_state(psi)), psi.size); return psi
 

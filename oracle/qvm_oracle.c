@@ -222,6 +222,19 @@ double orc_norm2(const double *psi_, uint64_t n_amps) {
 }
 double orc_norm(const double *psi_, uint64_t n_amps) { return sqrt(orc_norm2(psi_, n_amps)); }
 
+/* INNER-PRODUCT inside PURE-STATE-EXPECTATION app/src/api/expectation.lisp:79-84:
+ * (loop :for ai :across a :for bi :across b :sum (* (conjugate ai) bi)), sequential, out = (re, im). */
+void orc_inner_product(const double *a_, const double *b_, uint64_t n_amps, double *out) {
+    const cplx *a = (const cplx *)a_, *b = (const cplx *)b_;
+    double re = 0.0, im = 0.0;
+    for (uint64_t i = 0; i < n_amps; i++) {
+        re += a[i].re * b[i].re + a[i].im * b[i].im;
+        im += a[i].re * b[i].im - a[i].im * b[i].re;
+    }
+    out[0] = re;
+    out[1] = im;
+}
+
 /* NORMALIZE-WAVEFUNCTION src/wavefunction.lisp:349-364: psi *= 1/norm.
  * (* real complex) in SBCL scales both components. */
 void orc_scale(double *psi_, uint64_t n_amps, double inv) {

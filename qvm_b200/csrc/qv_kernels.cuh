@@ -126,6 +126,49 @@ qv_reduce_kernel(const qvc* __restrict__ psi, uint64_t count, int mode, uint32_t
     if (threadIdx.x == 0) partial[blockIdx.x] = tot;
 }
 
+// <a|b> = sum conj(a_i) b_i (PURE-STATE-EXPECTATION's INNER-PRODUCT, app/src/api/expectation.lisp:79-84): per-CTA partial
+// sums of the real and the imaginary part (partial[2*blockIdx], partial[2*blockIdx + 1]); reads 32*count bytes.
+__global__ void __launch_bounds__(QV_THREADS)
+qv_inner_kernel(const qvc* __restrict__ a, const qvc* __restrict__ b, uint64_t count, double* __restrict__ partial) {
+    double re0 = 0.0, im0 = 0.0, re1 = 0.0, im1 = 0.0;
+    const uint64_t stride = (uint64_t)gridDim.x * QV_THREADS;
+    uint64_t i = (uint64_t)blockIdx.x * QV_THREADS + threadIdx.x;
+    for (; i + stride < count; i += 2 * stride) {
+        const qvc x0 = qv_ld_stream(a + i), y0 = qv_ld_stream(b + i);
+        const qvc x1 = qv_ld_stream(a + i + stride), y1 = qv_ld_stream(b + i + stride);
+        re0 += x0.x * y0.x + x0.y * y0.y;
+        im0 += x0.x * y0.y - x0.y * y0.x;
+        re1 += x1.x * y1.x + x1.y * y1.y;
+        im1 += x1.x * y1.y - x1.y * y1.x;
+    }
+    for (; i < count; i += stride) {
+        const qvc x0 = qv_ld_stream(a + i), y0 = qv_ld_stream(b + i);
+        re0 += x0.x * y0.x + x0.y * y0.y;
+        im0 += x0.x * y0.y - x0.y * y0.x;
+    }
+    const double re = qv_block_sum(re0 + re1);
+    const double im = qv_block_sum(im0 + im1);
+    if (threadIdx.x == 0) {
+        partial[2 * blockIdx.x] = re;
+        partial[2 * blockIdx.x + 1] = im;
+    }
+}
+
+// out[0] = sum partial[2k], out[1] = sum partial[2k+1], fixed order
+__global__ void __launch_bounds__(QV_THREADS) qv_final_sum2_kernel(const double* __restrict__ partial, uint32_t n, double* out) {
+    double re = 0.0, im = 0.0;
+    for (uint32_t i = threadIdx.x; i < n; i += QV_THREADS) {
+        re += partial[2 * i];
+        im += partial[2 * i + 1];
+    }
+    const double tre = qv_block_sum(re);
+    const double tim = qv_block_sum(im);
+    if (threadIdx.x == 0) {
+        out[0] = tre;
+        out[1] = tim;
+    }
+}
+
 __global__ void __launch_bounds__(QV_THREADS) qv_final_sum_kernel(const double* __restrict__ partial, uint32_t n, double* out) {
     double s = 0.0;
     for (uint32_t i = threadIdx.x; i < n; i += QV_THREADS) s += partial[i];

@@ -713,6 +713,38 @@ int qvmcuda_norm2(qvmcuda_state* s, double* out) {
     return reduce_locked(s, s->n_amps, 0, 0, 0, out);
 }
 
+int qvmcuda_inner_product(qvmcuda_state* a, qvmcuda_state* b, double out[2]) {
+    if (!a || !b || !out) return fail("null argument");
+    if (a->n_amps != b->n_amps) return fail("inner product of states of different length");
+    if (a->device != b->device) return fail("inner product of states on different devices");
+    if (a == b) {
+        std::lock_guard<std::mutex> lk(a->mu);
+        DeviceGuard dg(a->device);
+        out[1] = 0.0;
+        return reduce_locked(a, a->n_amps, 0, 0, 0, out);
+    }
+    std::lock(a->mu, b->mu);
+    std::lock_guard<std::mutex> l1(a->mu, std::adopt_lock), l2(b->mu, std::adopt_lock);
+    DeviceGuard dg(a->device);
+    if (a->world > 1 || b->world > 1) {
+        if (a->l2p != b->l2p) return fail("inner product of shards with different qubit layouts");
+    } else {
+        if (int rc = canonicalize_locked(a)) return rc;
+        if (int rc = canonicalize_locked(b)) return rc;
+    }
+    CK(cudaStreamSynchronize(b->stream));      // b's pending work runs on its own stream
+    uint64_t blocks = (a->n_amps + QV_THREADS - 1) / QV_THREADS;
+    if (blocks > (kReduceBlocks - 2) / 2) blocks = (kReduceBlocks - 2) / 2;      // d_partial holds kReduceBlocks + 1 doubles: partials + the two results
+    if (blocks == 0) blocks = 1;
+    qv_inner_kernel<<<(int)blocks, QV_THREADS, 0, a->stream>>>(a->d_amps, b->d_amps, a->n_amps, a->d_partial);
+    qv_final_sum2_kernel<<<1, QV_THREADS, 0, a->stream>>>(a->d_partial, (uint32_t)blocks, a->d_partial + 2 * blocks);
+    g_launches += 2;
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(out, a->d_partial + 2 * blocks, 2 * sizeof(double), cudaMemcpyDeviceToHost, a->stream));
+    CK(cudaStreamSynchronize(a->stream));
+    return 0;
+}
+
 int qvmcuda_scale(qvmcuda_state* s, double factor) {
     if (!s) return fail("null argument");
     std::lock_guard<std::mutex> lk(s->mu);

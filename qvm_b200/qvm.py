@@ -100,6 +100,12 @@ class DeviceVector:
         L.check(L.lib().qvmcuda_norm2(self.handle, C.byref(p)))
         return p.value
 
+    def inner_product(self, other: "DeviceVector") -> complex:
+        """<self|other> = sum conj(self_i) other_i (app/src/api/expectation.lisp:79-84)."""
+        out = np.zeros(2, dtype=np.float64)
+        L.check(L.lib().qvmcuda_inner_product(self.handle, other.handle, L.ptr(out)))
+        return complex(out[0], out[1])
+
     def scale(self, f: float): L.check(L.lib().qvmcuda_scale(self.handle, float(f)))
     def normalize(self): L.check(L.lib().qvmcuda_normalize(self.handle))
 
@@ -488,6 +494,38 @@ class DensityQVM(BaseQVM):
             elif isinstance(x, Halt):
                 break
         return self
+
+
+def pure_state_expectation(qvm: "PureStateQVM", prepared: DeviceVector, op, first_time: bool = False) -> complex:
+    """PURE-STATE-EXPECTATION (app/src/api/expectation.lisp:78-91): restore the prepared state, run the operator
+    program OP on it and return <prepared | OP prepared>.  Everything stays on the device."""
+    if not first_time:
+        qvm.state.vec.copy_from(prepared)
+    qvm.load_program(op)
+    qvm.run()
+    return prepared.inner_product(qvm.state.vec)
+
+
+def perform_expectation(state_prep, operators, num_qubits: int, device: int = 0, seed: Optional[int] = None) -> List[float]:
+    """PERFORM-EXPECTATION on a pure state (app/src/api/expectation.lisp:38-76): run STATE-PREP once, keep a device copy
+    of the prepared wavefunction, then one expectation value per operator program.  The imaginary part must vanish
+    to 1e-14 like in the reference (:73)."""
+    qvm = make_qvm(num_qubits, device=device, seed=seed)
+    qvm.load_program(state_prep)
+    qvm.run()
+    prepared = DeviceVector(1 << num_qubits, device)
+    prepared.copy_from(qvm.state.vec)
+    out = []
+    first = True
+    for op in operators:
+        e = pure_state_expectation(qvm, prepared, op, first_time=first)
+        first = False
+        if abs(e.imag) >= 1e-14:
+            raise ValueError(f"expectation value has an imaginary part: {e}")
+        out.append(e.real)
+    prepared.close()
+    qvm.state.vec.close()
+    return out
 
 
 def make_qvm(num_qubits: int, device: int = 0, seed: Optional[int] = None) -> PureStateQVM:

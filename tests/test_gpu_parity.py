@@ -379,3 +379,81 @@ def test_stochastic_kraus_on_pure_state(Q, O):
         qvm.load_program("DECLARE R0 BIT\nI 0\nMEASURE 0 R0").run()
         ones += int(qvm.registers["R0"][0])
     assert 0 < ones < 60
+
+
+def test_sixteen_amplitude_kernel_variant(tmp_path):
+    """The 128-thread / 16-amplitudes-per-thread instantiation (QVMCUDA_REG_BITS=4, read once per process, hence
+    the subprocess) must give the oracle's amplitudes too; the default runs use the 8-amplitude kernel."""
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    script = tmp_path / "m4.py"
+    script.write_text(
+        "import sys, numpy as np\n"
+        f"sys.path.insert(0, {root!r}); sys.path.insert(0, {os.path.join(root, 'tests')!r})\n"
+        "import helpers\n"
+        "from qvm_b200 import qvm, circuits as CC\n"
+        "n = 16\n"
+        "rng = np.random.default_rng(4)\n"
+        "circ = CC.qft_circuit(range(n)) + helpers.random_circuit(n, 80, rng, max_dense=3) + CC.random_layer_circuit(n, 3, 2)\n"
+        "psi = helpers.rand_state(n, 9)\n"
+        "ref = helpers.run_oracle(psi.copy(), circ)\n"
+        "tape = qvm.Tape(n, circ, fuse=True)\n"
+        "assert ' m=4 ' in tape.describe(), tape.describe()\n"
+        "vec = qvm.DeviceVector(1 << n)\n"
+        "vec.upload(psi)\n"
+        "vec.run_tape(tape)\n"
+        "helpers.assert_close(vec.download(), ref)\n"
+        "print('m4 ok')\n")
+    env = dict(os.environ, QVMCUDA_REG_BITS="4")
+    out = subprocess.run([sys.executable, str(script)], env=env, capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0 and "m4 ok" in out.stdout, out.stdout + out.stderr
+
+
+def test_permutation_tail_is_folded_and_exact(Q, O):
+    """entangle-style circuits: the CNOT chain is folded into the write-back addressing; permutation-only circuits
+    move integer labels exactly (dqvm's index-tracer idea, dqvm/tests/program-tests.lisp:14-19)."""
+    n = 18
+    circ = [(G.gate_matrix("H"), (0,))] + [(G.gate_matrix("CNOT"), (q, q + 1)) for q in range(n - 1)]
+    tape = Q.Tape(n, circ, fuse=True)
+    assert "store_perm" in tape.describe()
+    psi = rand_state(n, 3)
+    assert_close(gpu_run(Q, psi, circ), run_oracle(psi.copy(), circ))
+    rng = np.random.default_rng(8)
+    perm = []
+    for _ in range(60):
+        a, b, c = (int(x) for x in rng.choice(n, 3, replace=False))
+        perm.append([(G.gate_matrix("SWAP"), (a, b)), (G.gate_matrix("CNOT"), (a, b)), (G.gate_matrix("X"), (a,)),
+                     (G.gate_matrix("CCNOT"), (a, b, c))][int(rng.integers(0, 4))])
+    labels = np.arange(1 << n).astype(np.complex128)
+    assert np.array_equal(gpu_run(Q, labels, perm), run_oracle(labels.copy(), perm))
+
+
+def test_inner_product_and_expectation(Q, O):
+    """PURE-STATE-EXPECTATION (app/src/api/expectation.lisp:78-91) on the device: <prepared | OP prepared>."""
+    n = 14
+    a, b = rand_state(n, 1), rand_state(n, 2)
+    va, vb = Q.DeviceVector(1 << n), Q.DeviceVector(1 << n)
+    va.upload(a)
+    vb.upload(b)
+    got = va.inner_product(vb)
+    ref = O.inner_product(a, b)
+    assert abs(got - ref) < 1e-13
+    assert abs(va.inner_product(va) - 1.0) < 1e-13
+    va.close()
+    vb.close()
+    # <Z0>, <X1>, <Z0 Z3> on a prepared state, against the oracle run of the same programs
+    prep = "H 0\nCNOT 0 1\nRX(0.3) 2\nRY(1.1) 3\nCZ 2 3\nH 4"
+    ops = ["Z 0", "X 1", "Z 0\nZ 3", "I 0"]
+    got = Q.perform_expectation(prep, ops, 5)
+    from qvm_b200.quil import parse_quil
+    psi = O.zero_state(5)
+    for ins in parse_quil(prep).instructions:
+        O.apply_matrix(psi, G.gate_matrix(ins.name, ins.params), tuple(ins.qubits))
+    for op, g in zip(ops, got):
+        phi = psi.copy()
+        for ins in parse_quil(op).instructions:
+            O.apply_matrix(phi, G.gate_matrix(ins.name, ins.params), tuple(ins.qubits))
+        assert abs(g - O.inner_product(psi, phi).real) < 1e-13
+    assert abs(got[3] - 1.0) < 1e-13

@@ -242,3 +242,19 @@ def test_multithreaded_baseline_equals_serial():
         O.apply_matrix(a, m, q)
         O.apply_matrix(b, m, q, threads=4)
     assert np.array_equal(a, b)
+
+
+def test_inner_product_is_the_reference_loop():
+    """app/src/api/expectation.lisp:79-84: sum of (conjugate a_i) * b_i; <psi|Z0|psi> of a Bell pair is 0 and
+    <psi|psi> = 1 (the expectation API asserts a vanishing imaginary part, :73)."""
+    from oracle import oracle as O
+    rng = np.random.default_rng(5)
+    a = rng.standard_normal(64) + 1j * rng.standard_normal(64)
+    b = rng.standard_normal(64) + 1j * rng.standard_normal(64)
+    assert abs(O.inner_product(a, b) - np.vdot(a, b)) < 1e-13
+    bell = np.zeros(4, dtype=np.complex128)
+    bell[0] = bell[3] = math.sqrt(0.5)
+    z0 = bell.copy()
+    z0[3] = -z0[3]
+    assert abs(O.inner_product(bell, z0)) < 1e-15
+    assert abs(O.inner_product(bell, bell) - 1.0) < 1e-15
