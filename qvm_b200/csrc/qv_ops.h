@@ -237,7 +237,7 @@ QV_HD constexpr uint32_t qv_slot_field(uint32_t gate) {
 
 // The first 16 bytes of a micro-op (kind | flags << 8 | pred << 16, data, cm, cv): the kernel fetches the
 // NEXT micro-op's header while the current one runs, so that the decode latency is off the critical path.
-struct QvUopHead {
+struct alignas(16) QvUopHead {
     uint32_t w0, data, cm, cv;
 };
 
@@ -295,7 +295,8 @@ QV_HD void qv_run_uop(qvc (&a)[NS], const QvUopHead& h, const QvUop& u, uint32_t
         return;
     }
     const qvc* M = reinterpret_cast<const qvc*>(blob + h.data);
-    const uint32_t idx = ((g >> (h.cm & 0xffu)) & (h.cm >> 8)) | ((g >> (h.cv & 0xffu)) & (h.cv >> 8));
+    // table index of a diagonal micro-op: two fields of the group counter (evaluated in the diagonal cases only)
+#define QV_IDX (((g >> (h.cm & 0xffu)) & (h.cm >> 8)) | ((g >> (h.cv & 0xffu)) & (h.cv >> 8)))
 #define QV_D1(RB) \
     case QV_K_DENSE1 + 2 * RB: qv_dense1<NS, RB, true, false>(a, M, 0xffffu); break; \
     case QV_K_DENSE1 + 2 * RB + 1: qv_dense1<NS, RB, false, false>(a, M, 0xffffu); break;
@@ -304,19 +305,19 @@ QV_HD void qv_run_uop(qvc (&a)[NS], const QvUopHead& h, const QvUop& u, uint32_t
     case QV_K_DENSE2 + 2 * P + 1: qv_dense2<NS, RB0, RB1, false, false>(a, M, 0xffffu); break;
 #define QV_DG(G) \
     case QV_K_DIAG1_S + G: { \
-        qvc t = slices[h.data + idx]; \
+        qvc t = slices[h.data + QV_IDX]; \
         if (h.w0 & (QV_UF_SCALE << 8)) t = qv_cmul(t, slices[u.scale]); \
         qv_diag1<NS, G>(a, t); \
         break; \
     } \
     case QV_K_DIAG1_G + G: { \
-        qvc t = tables[h.data + idx]; \
+        qvc t = tables[h.data + QV_IDX]; \
         if (h.w0 & (QV_UF_SCALE << 8)) t = qv_cmul(t, slices[u.scale]); \
         qv_diag1<NS, G>(a, t); \
         break; \
     } \
-    case QV_K_DIAGR_S + G: qv_diagr<NS, G>(a, slices + h.data + (idx << qv_slot_field<NS>(G))); break; \
-    case QV_K_DIAGR_G + G: qv_diagr<NS, G>(a, tables + h.data + (idx << qv_slot_field<NS>(G))); break; \
+    case QV_K_DIAGR_S + G: qv_diagr<NS, G>(a, slices + h.data + (QV_IDX << qv_slot_field<NS>(G))); break; \
+    case QV_K_DIAGR_G + G: qv_diagr<NS, G>(a, tables + h.data + (QV_IDX << qv_slot_field<NS>(G))); break; \
     case QV_K_DIAGR_C + G: qv_diagr<NS, G>(a, M); break;
     if (NS == 16) {
         switch (kind) {
@@ -336,6 +337,7 @@ QV_HD void qv_run_uop(qvc (&a)[NS], const QvUopHead& h, const QvUop& u, uint32_t
 #undef QV_D1
 #undef QV_D2
 #undef QV_DG
+#undef QV_IDX
 }
 
 // Entry x of a slice for the tile at hand: the product of its sources (src_ext[s] = the source's

@@ -154,7 +154,11 @@ qv_tile_kernel(const __grid_constant__ PROG prog, const __grid_constant__ QvPeer
             const uint32_t m = FULL ? (uint32_t)M : rd.m;
             const uint32_t nslots = 1u << m;
             const uint32_t ngroups = tile_n >> m;
-            for (uint32_t g = tid; g < ngroups; g += THREADS) {
+            for (uint32_t g_ = tid; g_ < ngroups; g_ += THREADS) {
+                // keep the group counter in a register: ptxas otherwise re-derives it from SR_TID.X (a 20-cycle S2R)
+                // in front of every micro-op
+                uint32_t g = g_;
+                asm volatile("" : "+r"(g));
                 uint32_t e0 = g;
                 if (m > 0) e0 = qv_insert_zero(e0, rd.regpos[0]);
                 if (m > 1) e0 = qv_insert_zero(e0, rd.regpos[1]);
