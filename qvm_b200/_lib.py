@@ -12,7 +12,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libqvmcuda.so")
+LIB_PATH = os.environ.get("QVMCUDA_LIB") or os.path.join(_HERE, "libqvmcuda.so")   # QVMCUDA_LIB: A/B builds when profiling
 
 FUSE = 1
 ABSORB_SWAPS = 2

@@ -138,6 +138,21 @@ QV_HD void qv_dense1(qvc (&a)[NS], const qvc* M, uint32_t slot_ok) {
     }
 }
 
+// The unscaled butterfly (a0, a1) <- (a0 + a1, a0 - a1) on register bit RB, in place and without temporaries:
+// a0 += a1, then a1 = a0 - 2 a1.
+template <int NS, int RB>
+QV_HD void qv_bfly(qvc (&a)[NS]) {
+#pragma unroll
+    for (int r = 0; r < NS; r++) {
+        if (r & (1 << RB)) continue;
+        const int r1 = r | (1 << RB);
+        qv_add_ip(a[r].x, a[r1].x);
+        qv_add_ip(a[r].y, a[r1].y);
+        qv_fma_self(a[r1].x, -2.0, a[r].x);
+        qv_fma_self(a[r1].y, -2.0, a[r].y);
+    }
+}
+
 template <int NS, int RB0, int RB1, bool REAL, bool CTRL>
 QV_HD void qv_dense2(qvc (&a)[NS], const qvc* M, uint32_t slot_ok) {
 #pragma unroll
@@ -321,6 +336,10 @@ QV_HD void qv_run_uop(qvc (&a)[NS], const QvUopHead& h, const QvUop& u, uint32_t
     case QV_K_DIAGR_C + G: qv_diagr<NS, G>(a, M); break;
     if (NS == 16) {
         switch (kind) {
+            case QV_K_BFLY + 0: qv_bfly<NS, 0>(a); break;
+            case QV_K_BFLY + 1: qv_bfly<NS, 1>(a); break;
+            case QV_K_BFLY + 2: qv_bfly<NS, 2>(a); break;
+            case QV_K_BFLY + 3: qv_bfly<NS, (NS > 8 ? 3 : 0)>(a); break;
             QV_D1(0) QV_D1(1) QV_D1(2) QV_D1(3)
             QV_D2(0, 0, 1) QV_D2(1, 0, 2) QV_D2(2, 1, 2) QV_D2(3, 0, 3) QV_D2(4, 1, 3) QV_D2(5, 2, 3)
             QV_DG(0) QV_DG(1) QV_DG(2) QV_DG(3) QV_DG(4)
@@ -328,6 +347,9 @@ QV_HD void qv_run_uop(qvc (&a)[NS], const QvUopHead& h, const QvUop& u, uint32_t
         }
     } else {
         switch (kind) {
+            case QV_K_BFLY + 0: qv_bfly<NS, 0>(a); break;
+            case QV_K_BFLY + 1: qv_bfly<NS, 1>(a); break;
+            case QV_K_BFLY + 2: qv_bfly<NS, 2>(a); break;
             QV_D1(0) QV_D1(1) QV_D1(2)
             QV_D2(0, 0, 1) QV_D2(1, 0, 2) QV_D2(2, 1, 2)
             QV_DG(0) QV_DG(1) QV_DG(2) QV_DG(3)

@@ -61,7 +61,9 @@ enum QvUopKind : uint32_t {
     QV_K_DIAGR_G = 35,       // + GATE
     QV_K_DIAGR_C = 40,       // + GATE   (index has register bits only, no per-tile part)
     QV_K_END = 45,           // terminates the micro-op list of a round (the kernel loops on the kind alone)
-    QV_K_COUNT = 46,
+    QV_K_BFLY = 46,          // + RB: the unscaled butterfly [[1,1],[1,-1]] on register bit RB (Hadamard-like gates; their
+                             //       common scale factor is folded into the pass's write-back scale)
+    QV_K_COUNT = 50,
 };
 
 enum QvUopFlags : uint32_t {
@@ -162,6 +164,7 @@ struct QvPassHeader {
     uint32_t uses_peers;            // tile bits include a physical bit >= n_local_bits
     uint32_t n_diag_uops;           // statistics for describe()
     uint64_t hi_off[32];            // physical-index bits of tile-local index (block size)*i (host-precomputed gather)
+    uint64_t hi_byte[32];           // 16 * hi_off[i]: byte offsets for the local-pass fast path (one 64-bit add per element)
     // Store permutation: the trailing X / CNOT / SWAP gates of a pass are GF(2)-affine maps of the tile-local
     // index, so they cost no arithmetic at all: the element written to tile-local position e is read from
     // shared-memory slot qv_swz(A e ^ b) = st_lo(tid) ^ st_hi[i] for e = tid + (block size)*i.
@@ -175,6 +178,11 @@ struct QvPassHeader {
     // (local_bit, global_bit) pair exchanged -- and WRITES its results into the alternate buffer; all ranks
     // flip buffers afterwards.  The exchange costs no pass of its own.  S is GF(2)-linear, so
     // S(pbase | hi_off[i]) = S(pbase) ^ hi_src[i] with hi_src host-precomputed.
+    // Write-back scale: uncontrolled gates of the form s*[[1,1],[1,-1]] (H) run as unscaled butterflies (2 FP64 ops per
+    // amplitude instead of 4); the product of their factors is applied once, while the tile is written back.
+    double out_scale;
+    uint32_t has_scale;
+    uint32_t scale_pad;
     uint32_t pull;                  // 0: in place
     uint32_t pull_pad;
     QvRemap pull_remap;

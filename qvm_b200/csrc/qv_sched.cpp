@@ -186,6 +186,8 @@ struct BlobWriter {
     std::vector<QvSegList> seglists;
     std::vector<cd> mats;
     std::vector<cd> tables;
+    double out_scale = 1.0;             // product of the factors of the gates that run as unscaled butterflies
+    bool has_scale = false;
     size_t slice_entries = 0;
     size_t slice_build = 0;             // sum of 2^nl * n_src: per-tile construction work
     size_t n_diag_uops = 0;
@@ -243,7 +245,7 @@ struct PlanChunk {
 };
 
 void emit_round(BlobWriter& w, const std::vector<RoundOp>& rops, const std::vector<int>& regpos_local,
-                const TileMap& tm, const Layout& lay, int reg_bits) {
+                const TileMap& tm, const Layout& lay, int reg_bits, bool butterflies) {
     const int m = (int)regpos_local.size();
     QvRound rd{};
     rd.m = (uint32_t)m;
@@ -297,6 +299,15 @@ void emit_round(BlobWriter& w, const std::vector<RoundOp>& rops, const std::vect
             for (const cd& e : mat)
                 if (e.imag() != 0.0) real = false;
             u.kind = (uint8_t)(r1 < 0 ? QV_K_DENSE1 + 2 * r0 + (real ? 0 : 1) : QV_K_DENSE2 + 2 * pair_index[r0][r1] + (real ? 0 : 1));
+            // s * [[1,1],[1,-1]] without controls (Hadamard): unscaled butterfly, s goes into the write-back scale
+            if (butterflies && r1 < 0 && real && a.cmask == 0 && mat[0].real() != 0.0 && mat[0] == mat[1] && mat[0] == mat[2] &&
+                mat[3] == -mat[0]) {
+                u.kind = (uint8_t)(QV_K_BFLY + r0);
+                w.out_scale *= mat[0].real();
+                w.has_scale = true;
+                w.uops.push_back(u);
+                continue;
+            }
             uint32_t slot_ok = 0xffffu;
             QvPred pred{};
             for (int wq = 0; wq < 64; wq++) {
@@ -634,7 +645,8 @@ void emit_round(BlobWriter& w, const std::vector<RoundOp>& rops, const std::vect
 
 // Split the ordered atoms of one pass into register rounds (same greedy + commutation look-ahead
 // as the pass level, one level down: <= reg_bits target bits per round).
-void build_rounds(BlobWriter& w, const std::vector<const Atom*>& atoms, const TileMap& tm, const Layout& lay, int reg_bits) {
+void build_rounds(BlobWriter& w, const std::vector<const Atom*>& atoms, const TileMap& tm, const Layout& lay, int reg_bits,
+                  bool butterflies) {
     const int m_max = std::min(reg_bits, tm.T);
     std::vector<const Atom*> pending = atoms;
     while (!pending.empty()) {
@@ -694,7 +706,7 @@ void build_rounds(BlobWriter& w, const std::vector<const Atom*>& atoms, const Ti
         for (int lp = tm.T - 1; lp >= 0 && (int)regpos.size() < m_max; lp--)
             if (std::find(regpos.begin(), regpos.end(), lp) == regpos.end()) regpos.push_back(lp);
         std::sort(regpos.begin(), regpos.end());
-        emit_round(w, rops, regpos, tm, lay, reg_bits);
+        emit_round(w, rops, regpos, tm, lay, reg_bits, butterflies);
         pending.swap(deferred);
     }
 }
@@ -702,6 +714,7 @@ void build_rounds(BlobWriter& w, const std::vector<const Atom*>& atoms, const Ti
 struct Geometry {
     int n_bits, n_local, T, lmin, rank;
     bool store_perm;    // fold trailing X / CNOT / SWAP gates into the write-back addressing
+    bool butterflies;   // run s*[[1,1],[1,-1]] gates as unscaled butterflies, s folded into the write-back scale
     int reg_bits;       // 0 = choose per pass (4 for passes that carry many gates, else 3)
 };
 
@@ -802,7 +815,7 @@ Step build_tile_step(const std::vector<const Atom*>& atoms_in, uint64_t tile_tar
     const int reg_bits = choose_reg_bits(atoms, geo);
     const int threads_log2 = reg_bits == 4 ? 7 : 8;
     BlobWriter w;
-    build_rounds(w, atoms, tm, lay, reg_bits);
+    build_rounds(w, atoms, tm, lay, reg_bits, geo.butterflies);
 
     QvPassHeader h{};
     h.T = (uint32_t)tm.T;
@@ -855,6 +868,7 @@ Step build_tile_step(const std::vector<const Atom*>& atoms_in, uint64_t tile_tar
         for (int t = 0; t < tm.T; t++)
             if (e >> t & 1) off |= 1ull << tm.tilebits[t];
         h.hi_off[i] = off;
+        h.hi_byte[i] = off * 16;
     }
     if (!stripped.empty()) {
         auto image = [&](uint32_t e) {      // A e (no constant)
@@ -876,6 +890,8 @@ Step build_tile_step(const std::vector<const Atom*>& atoms_in, uint64_t tile_tar
     h.n_rounds = (uint32_t)w.rounds.size();
     h.n_uops = (uint32_t)w.uops.size();
     h.n_diag_uops = (uint32_t)w.n_diag_uops;
+    h.out_scale = w.out_scale;
+    h.has_scale = w.has_scale ? 1u : 0u;
     h.n_sources = (uint32_t)w.sources.size();
     h.n_slices = (uint32_t)w.slices.size();
     h.n_slice_entries = (uint32_t)w.slice_entries;
@@ -905,7 +921,7 @@ Step build_tile_step(const std::vector<const Atom*>& atoms_in, uint64_t tile_tar
     h.blob_bytes = (uint32_t)off;
     if (off > QV_PROG_LARGE_BYTES) throw std::length_error("pass control program too large");
     for (QvUop& u : w.uops) {
-        if (u.kind == QV_K_END) continue;
+        if (u.kind == QV_K_END || u.kind >= QV_K_BFLY) continue;
         if (u.kind < QV_K_DIAG_BASE || u.kind >= QV_K_DIAGR_C) u.data += h.off_matrices;
         if (u.kind >= QV_K_DIAG_BASE && (u.flags & QV_UF_GENERIC)) u.segs = (uint16_t)(off_seglists + u.segs * sizeof(QvSegList));
     }
@@ -1003,6 +1019,7 @@ Tape compile(const std::vector<Gate>& gates, int n_bits, const CompileOptions& o
     geo.rank = opt.rank;
     geo.reg_bits = opt.reg_bits;
     geo.store_perm = opt.store_perm;
+    geo.butterflies = opt.butterflies;
     if (opt.reg_bits != 0 && opt.reg_bits != 3 && opt.reg_bits != 4) throw std::runtime_error("reg_bits must be 0 (auto), 3 or 4");
     geo.T = std::min(opt.tile_bits, geo.n_local);
     if (geo.n_local > n_bits) throw std::runtime_error("n_local_bits exceeds the qubit count");
@@ -1265,7 +1282,7 @@ std::string describe(const Tape& t) {
         os << "  [" << i << "] " << (h.pull ? "PULL+TILE" : s.is_remap ? "REMAP" : (s.uses_peers ? "PEER" : "TILE")) << " T=" << h.T
            << " m=" << h.reg_bits << " atoms=" << s.n_gates << " rounds=" << h.n_rounds << " uops=" << h.n_uops << " diag_uops=" << h.n_diag_uops
            << " slices=" << h.n_slices << " sources=" << h.n_sources << " slice_entries=" << h.n_slice_entries
-           << (h.store_perm ? " store_perm" : "") << " bytes=" << h.blob_bytes << " tables=" << h.n_table_entries << " tilebits=";
+           << (h.store_perm ? " store_perm" : "") << (h.has_scale ? " out_scale" : "") << " bytes=" << h.blob_bytes << " tables=" << h.n_table_entries << " tilebits=";
         for (uint32_t k = 0; k < h.n_tile_segs; k++)
             os << (int)h.tile_segs[k].dst << "+" << (int)h.tile_segs[k].len << (k + 1 < h.n_tile_segs ? "," : "");
         os << "\n";

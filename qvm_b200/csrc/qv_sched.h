@@ -33,6 +33,7 @@ struct CompileOptions {
     int n_local_bits = 0;        // log2(amplitudes on this device); 0 = n_bits (single device)
     int rank = 0;                // value of the physical bits >= n_local_bits on this device
     int reg_bits = 0;            // amplitudes per thread per round = 2^reg_bits: 3, 4, or 0 = chosen per pass
+    bool butterflies = true;     // Hadamard-like gates as unscaled butterflies + one write-back scale per pass
     bool store_perm = true;      // fold trailing X / CNOT / SWAP gates of a pass into its write-back addressing
     bool fuse_pull = true;       // with remap_pull: merge a pull remap into the tile pass that follows it
     bool remap_pull = false;     // remaps as out-of-place pulls into the alternate buffer (needs 2x shard memory)

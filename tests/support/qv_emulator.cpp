@@ -109,8 +109,13 @@ void run_tile_step(qvc* const* peers, const qv::Step& st, qvc* alt_own = nullptr
                     if ((e & (threads - 1)) >> k & 1) slot ^= h.st_col[k];
                 slot ^= h.st_hi[e >> h.threads_log2];
             }
-            if (h.pull) alt_own[phys(base, e) & local_mask] = smem[slot];
-            else *addr(phys(base, e)) = smem[slot];
+            qvc v = smem[slot];
+            if (h.has_scale) {
+                v.x *= h.out_scale;
+                v.y *= h.out_scale;
+            }
+            if (h.pull) alt_own[phys(base, e) & local_mask] = v;
+            else *addr(phys(base, e)) = v;
         }
     }
 }
