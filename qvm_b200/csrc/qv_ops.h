@@ -318,6 +318,21 @@ QV_HD void qv_run_uop(qvc (&a)[NS], const QvUopHead& h, const QvUop& u, uint32_t
 #define QV_D2(P, RB0, RB1) \
     case QV_K_DENSE2 + 2 * P: qv_dense2<NS, RB0, RB1, true, false>(a, M, 0xffffu); break; \
     case QV_K_DENSE2 + 2 * P + 1: qv_dense2<NS, RB0, RB1, false, false>(a, M, 0xffffu); break;
+#define QV_BD(LBL, RB) \
+    case QV_K_BFLY_DIAG1_S + LBL: { \
+        qv_bfly<NS, RB>(a); \
+        qvc t = slices[h.data + QV_IDX]; \
+        if (h.w0 & (QV_UF_SCALE << 8)) t = qv_cmul(t, slices[u.scale]); \
+        qv_diag1<NS, RB + 1>(a, t); \
+        break; \
+    } \
+    case QV_K_BFLY_DIAG1_G + LBL: { \
+        qv_bfly<NS, RB>(a); \
+        qvc t = tables[h.data + QV_IDX]; \
+        if (h.w0 & (QV_UF_SCALE << 8)) t = qv_cmul(t, slices[u.scale]); \
+        qv_diag1<NS, RB + 1>(a, t); \
+        break; \
+    }
 #define QV_DG(G) \
     case QV_K_DIAG1_S + G: { \
         qvc t = slices[h.data + QV_IDX]; \
@@ -340,6 +355,7 @@ QV_HD void qv_run_uop(qvc (&a)[NS], const QvUopHead& h, const QvUop& u, uint32_t
             case QV_K_BFLY + 1: qv_bfly<NS, 1>(a); break;
             case QV_K_BFLY + 2: qv_bfly<NS, 2>(a); break;
             case QV_K_BFLY + 3: qv_bfly<NS, (NS > 8 ? 3 : 0)>(a); break;
+            QV_BD(0, 0) QV_BD(1, 1) QV_BD(2, 2) QV_BD(3, (NS > 8 ? 3 : 0))
             QV_D1(0) QV_D1(1) QV_D1(2) QV_D1(3)
             QV_D2(0, 0, 1) QV_D2(1, 0, 2) QV_D2(2, 1, 2) QV_D2(3, 0, 3) QV_D2(4, 1, 3) QV_D2(5, 2, 3)
             QV_DG(0) QV_DG(1) QV_DG(2) QV_DG(3) QV_DG(4)
@@ -350,6 +366,7 @@ QV_HD void qv_run_uop(qvc (&a)[NS], const QvUopHead& h, const QvUop& u, uint32_t
             case QV_K_BFLY + 0: qv_bfly<NS, 0>(a); break;
             case QV_K_BFLY + 1: qv_bfly<NS, 1>(a); break;
             case QV_K_BFLY + 2: qv_bfly<NS, 2>(a); break;
+            QV_BD(0, 0) QV_BD(1, 1) QV_BD(2, 2)
             QV_D1(0) QV_D1(1) QV_D1(2)
             QV_D2(0, 0, 1) QV_D2(1, 0, 2) QV_D2(2, 1, 2)
             QV_DG(0) QV_DG(1) QV_DG(2) QV_DG(3)
@@ -359,6 +376,7 @@ QV_HD void qv_run_uop(qvc (&a)[NS], const QvUopHead& h, const QvUop& u, uint32_t
 #undef QV_D1
 #undef QV_D2
 #undef QV_DG
+#undef QV_BD
 #undef QV_IDX
 }
 

@@ -63,7 +63,9 @@ enum QvUopKind : uint32_t {
     QV_K_END = 45,           // terminates the micro-op list of a round (the kernel loops on the kind alone)
     QV_K_BFLY = 46,          // + RB: the unscaled butterfly [[1,1],[1,-1]] on register bit RB (Hadamard-like gates; their
                              //       common scale factor is folded into the pass's write-back scale)
-    QV_K_COUNT = 50,
+    QV_K_BFLY_DIAG1_S = 50,  // + RB: butterfly on RB, then the DIAG1 (slice table) gated by RB: one dispatch for the QFT's
+    QV_K_BFLY_DIAG1_G = 54,  // + RB: "H, then the controlled phases hanging off that qubit"; same with a global table
+    QV_K_COUNT = 58,
 };
 
 enum QvUopFlags : uint32_t {

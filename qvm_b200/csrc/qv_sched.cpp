@@ -629,6 +629,42 @@ void emit_round(BlobWriter& w, const std::vector<RoundOp>& rops, const std::vect
         }
         if (getenv("QV_SCHED_DEBUG")) fprintf(stderr, "  DIAG group: %zu factors -> %zu chunks (slice entries so far %zu, build %zu)\n", nf, plan.size(), w.slice_entries, w.slice_build);
     }
+    // Peephole: a DIAG1 gated by register bit r commutes with every micro-op that is diagonal or acts on other
+    // register bits, so it can move back to the last dense micro-op on r; if that one is an unscaled butterfly, the
+    // pair becomes ONE micro-op ("H, then the controlled phases hanging off that qubit": the QFT's inner step).
+    if (butterflies) {
+        for (size_t i = rd.first_uop; i < w.uops.size(); i++) {
+            const QvUop& d = w.uops[i];
+            int space = -1;
+            if (d.kind > QV_K_DIAG1_S && d.kind < QV_K_DIAG1_S + 5) space = 0;
+            else if (d.kind > QV_K_DIAG1_G && d.kind < QV_K_DIAG1_G + 5) space = 1;
+            if (space < 0 || (d.flags & QV_UF_GENERIC)) continue;
+            const int r = d.kind - (space == 0 ? QV_K_DIAG1_S : QV_K_DIAG1_G) - 1;
+            // last micro-op before i that mixes register bit r
+            int j = (int)i - 1;
+            for (; j >= (int)rd.first_uop; j--) {
+                const QvUop& e = w.uops[j];
+                bool mixes = false;
+                if (e.kind >= QV_K_BFLY && e.kind < QV_K_BFLY + 4) mixes = (e.kind - QV_K_BFLY) == r;
+                else if (e.kind >= QV_K_BFLY_DIAG1_S && e.kind < QV_K_COUNT) mixes = ((e.kind - QV_K_BFLY_DIAG1_S) & 3) == r;
+                else if (e.kind < QV_K_DENSE2) mixes = (e.kind - QV_K_DENSE1) / 2 == r;
+                else if (e.kind < QV_K_DIAG_BASE) {
+                    static const int pr[6][2] = {{0, 1}, {0, 2}, {1, 2}, {0, 3}, {1, 3}, {2, 3}};
+                    const int p = (e.kind - QV_K_DENSE2) / 2;
+                    mixes = pr[p][0] == r || pr[p][1] == r;
+                }
+                if (mixes) break;
+            }
+            if (j < (int)rd.first_uop) continue;
+            QvUop& b = w.uops[j];
+            if (!(b.kind >= QV_K_BFLY && b.kind < QV_K_BFLY + 4)) continue;
+            QvUop fused = d;
+            fused.kind = (uint8_t)((space == 0 ? QV_K_BFLY_DIAG1_S : QV_K_BFLY_DIAG1_G) + r);
+            b = fused;
+            w.uops.erase(w.uops.begin() + i);
+            i--;
+        }
+    }
     rd.n_uops = (uint32_t)w.uops.size() - rd.first_uop;
     {
         QvUop end{};
@@ -921,7 +957,7 @@ Step build_tile_step(const std::vector<const Atom*>& atoms_in, uint64_t tile_tar
     h.blob_bytes = (uint32_t)off;
     if (off > QV_PROG_LARGE_BYTES) throw std::length_error("pass control program too large");
     for (QvUop& u : w.uops) {
-        if (u.kind == QV_K_END || u.kind >= QV_K_BFLY) continue;
+        if (u.kind == QV_K_END || u.kind >= QV_K_BFLY) continue;      // no blob-relative operands
         if (u.kind < QV_K_DIAG_BASE || u.kind >= QV_K_DIAGR_C) u.data += h.off_matrices;
         if (u.kind >= QV_K_DIAG_BASE && (u.flags & QV_UF_GENERIC)) u.segs = (uint16_t)(off_seglists + u.segs * sizeof(QvSegList));
     }
