@@ -213,7 +213,7 @@ def run_ours(args):
     roofline = {"bound": "hbm", "achieved": bytes_per_pass / pass_s / 1e9, "peak": peak, "unit": "GB/s",
                 "frac": bytes_per_pass / pass_s / 1e9 / peak,
                 "traffic": traffic.get("fused_pass_dram_bytes", 0) * scale or None,
-                "kernel": "qv_tile_kernel, fused passes of the timed region (4-212 gates per launch; the 84-212-gate passes are issue-bound, see profiles/r01_f_microops.md)",
+                "kernel": "qv_tile_kernel, fused passes of the timed region (4-212 gates per launch; the 84-212-gate passes are issue-bound, see profiles/r01_g_butterfly.md)",
                 "peak_source": peak_src, "traffic_source": traffic.get("source"),
                 "bytes_per_launch": bytes_per_pass, "launches_per_step": info["passes"]}
 
