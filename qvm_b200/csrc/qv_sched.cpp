@@ -1171,12 +1171,28 @@ Tape compile(const std::vector<Gate>& gates, int n_bits, const CompileOptions& o
     std::vector<const Atom*> pending;
     for (const Atom& a : atoms) pending.push_back(&a);
 
+    // Sharded states never return to the canonical layout (the host maps indices through the layout), so an exact
+    // SWAP gate with an operand on a rank bit is a pure relabeling: the two wires exchange their physical bits
+    // and nothing crosses NVLink.  Only the atom at the head of the queue may do this (every earlier atom has been
+    // scheduled with the old mapping).
+    auto relabels = [&](const Atom& a) {
+        if (!opt.relabel_global_swaps || g_bits == 0) return false;
+        if (!(a.kind == Atom::DENSE && a.tw.size() == 2 && a.cmask == 0 && is_linear_perm(a))) return false;
+        return w2p[a.tw[0]] >= geo.n_local || w2p[a.tw[1]] >= geo.n_local;
+    };
+
     if (!opt.fuse) {
         // every gate is its own pass (its controlled blocks share it when they fit)
         size_t i = 0;
         while (i < atoms.size()) {
             size_t j = i;
             while (j < atoms.size() && gate_of[j] == gate_of[i]) j++;
+            if (j == i + 1 && relabels(atoms[i])) {
+                std::swap(w2p[atoms[i].tw[0]], w2p[atoms[i].tw[1]]);
+                tape.n_relabeled++;
+                i = j;
+                continue;
+            }
             uint64_t need = 0;
             for (size_t a = i; a < j; a++) need |= atoms[a].mix;
             if (phys_mask(need) & ~local_mask) {
@@ -1215,6 +1231,13 @@ Tape compile(const std::vector<Gate>& gates, int n_bits, const CompileOptions& o
 
     // 2. greedy pass formation with commutation look-ahead.
     while (!pending.empty()) {
+        if (relabels(*pending.front())) {
+            const Atom& a = *pending.front();
+            std::swap(w2p[a.tw[0]], w2p[a.tw[1]]);
+            tape.n_relabeled++;
+            pending.erase(pending.begin());
+            continue;
+        }
         if (pending.front()->kind == Atom::BIG) {
             if (phys_mask(pending.front()->mix) & ~local_mask) {
                 remap(pending.front()->mix, pending);
@@ -1300,7 +1323,7 @@ Tape compile(const std::vector<Gate>& gates, int n_bits, const CompileOptions& o
 std::string describe(const Tape& t) {
     std::ostringstream os;
     os << "tape: n_bits=" << t.n_bits << " gates=" << t.n_gates << " atoms=" << t.n_atoms
-       << " steps=" << t.steps.size() << "\n";
+       << " steps=" << t.steps.size() << (t.n_relabeled ? " relabeled_swaps=" + std::to_string(t.n_relabeled) : std::string()) << "\n";
     for (size_t i = 0; i < t.steps.size(); i++) {
         const Step& s = t.steps[i];
         if (s.kind == Step::BIG) {

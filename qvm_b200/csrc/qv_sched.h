@@ -36,6 +36,7 @@ struct CompileOptions {
     bool butterflies = true;     // Hadamard-like gates as unscaled butterflies + one write-back scale per pass
     bool store_perm = true;      // fold trailing X / CNOT / SWAP gates of a pass into its write-back addressing
     bool fuse_pull = true;       // with remap_pull: merge a pull remap into the tile pass that follows it
+    bool relabel_global_swaps = true;   // sharded: an exact SWAP touching a rank bit only exchanges the two wires' physical bits
     bool remap_pull = false;     // remaps as out-of-place pulls into the alternate buffer (needs 2x shard memory)
 };
 
@@ -57,6 +58,7 @@ struct Tape {
     std::vector<int> l2p;        // logical -> physical qubit map after the tape ran
     int n_gates = 0;
     int n_atoms = 0;
+    int n_relabeled = 0;         // SWAP gates on rank bits executed as relabelings (sharded)
 };
 
 // l2p_in: current logical->physical map (empty = identity).

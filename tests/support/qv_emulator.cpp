@@ -340,6 +340,7 @@ extern "C" void* qvtest_shard_compile(int n_bits, int world, int rank, int n_gat
         opt.reg_bits = g_reg_bits;
         opt.n_local_bits = n_bits - gb;
         opt.rank = rank;
+        opt.remap_pull = g_remap_pull;      // schedule inspection only: the step-wise engine runs in-place schedules
         std::vector<int> l2p(l2p_in, l2p_in + n_bits);
         EmuTape* t = new EmuTape();
         t->n_local = n_bits - gb;
