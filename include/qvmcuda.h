@@ -94,6 +94,10 @@ int qvmcuda_norm2(qvmcuda_state *s, double *sum_of_squares);
 /* <a|b> = sum conj(a_i) b_i: the INNER-PRODUCT of PURE-STATE-EXPECTATION (app/src/api/expectation.lisp:78-91),
  * out[0] = real part, out[1] = imaginary part.  Both states on the same device, same length. */
 int qvmcuda_inner_product(qvmcuda_state *a, qvmcuda_state *b, double out[2]);
+/* probabilities of COUNT basis states starting at OFFSET (|psi_i|^2, PROBABILITY src/wavefunction.lisp:44-50) straight to a
+ * host buffer: the :probabilities request of the app (app/src/api/probabilities.lisp; handle-request.lisp:155-176 streams
+ * them as big-endian doubles).  Half the bytes of a wavefunction download. */
+int qvmcuda_probabilities(qvmcuda_state *s, double *out, uint64_t offset, uint64_t count);
 int qvmcuda_scale(qvmcuda_state *s, double factor);
 int qvmcuda_normalize(qvmcuda_state *s);
 /* FORCE-MEASUREMENT (pure-state) src/measurement.lisp:10-41: amplitudes whose QUBIT bit differs from

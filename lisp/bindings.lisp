@@ -42,6 +42,7 @@
 (defcuda prob-ground "qvmcuda_prob_ground" (state :pointer) (qubit :int) (p :pointer))
 (defcuda norm2 "qvmcuda_norm2" (state :pointer) (p :pointer))
 (defcuda inner-product "qvmcuda_inner_product" (a :pointer) (b :pointer) (out :pointer))
+(defcuda probabilities "qvmcuda_probabilities" (state :pointer) (out :pointer) (offset :uint64) (count :uint64))
 (defcuda scale "qvmcuda_scale" (state :pointer) (factor :double))
 (defcuda collapse "qvmcuda_collapse" (state :pointer) (qubit :int) (keep-bit :int) (inv-norm :double))
 (defcuda sample "qvmcuda_sample" (state :pointer) (uniforms :pointer) (n-shots :uint64) (out :pointer) (strict :int))

@@ -78,3 +78,13 @@ state and <prepared | OP prepared> is reduced on the GPU instead of the host LOO
   (cffi:with-foreign-object (out :double 2)
     (inner-product (device-handle prepared-state) (device-handle (qvm::state qvm)) out)
     (complex (cffi:mem-aref out :double 0) (cffi:mem-aref out :double 1))))
+
+(defun probabilities/cuda (state)
+  "What PERFORM-PROBABILITIES collects (app/src/api/probabilities.lisp): the probability of every basis state of a
+DEVICE-PURE-STATE as a vector of double-floats, reduced to 8 bytes per basis state on the device."
+  (flush-gate-tape state)
+  (let* ((n (expt 2 (qvm::num-qubits state)))
+         (probs (make-array n :element-type 'double-float)))
+    (cffi:with-pointer-to-vector-data (p probs)
+      (probabilities (device-handle state) p 0 n))
+    probs))

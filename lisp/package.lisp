@@ -13,4 +13,5 @@
            #:*cuda-lazy-mirror*
            #:flush-gate-tape
            #:sample-wavefunction-multiple-times/cuda
-           #:pure-state-expectation/cuda))
+           #:pure-state-expectation/cuda
+           #:probabilities/cuda))

@@ -49,6 +49,7 @@ def lib():
             getattr(L, f).restype = dbl; getattr(L, f).argtypes = [vp, u64, i32]
         for f in ("orc_norm2", "orc_norm"):
             getattr(L, f).restype = dbl; getattr(L, f).argtypes = [vp, u64]
+        L.orc_probabilities.restype = None; L.orc_probabilities.argtypes = [vp, u64, vp]
         L.orc_inner_product.restype = None; L.orc_inner_product.argtypes = [vp, vp, u64, vp]
         L.orc_scale.restype = None; L.orc_scale.argtypes = [vp, u64, dbl]
         L.orc_normalize.restype = None; L.orc_normalize.argtypes = [vp, u64]
@@ -131,6 +132,13 @@ def prob_excited(psi, q): return float(lib().orc_prob_excited(_p(_state(psi)), p
 def prob_ground(psi, q): return float(lib().orc_prob_ground(_p(_state(psi)), psi.size, q))
 def norm2(psi): return float(lib().orc_norm2(_p(_state(psi)), psi.size))
 def norm(psi): return float(lib().orc_norm(_p(_state(psi)), psi.size))
+
+
+def probabilities(psi) -> np.ndarray:
+    """|psi_i|^2 for every basis state (PROBABILITY, src/wavefunction.lisp:44-50)."""
+    out = np.zeros(psi.size, dtype=np.float64)
+    lib().orc_probabilities(_p(_state(psi)), psi.size, _p(out))
+    return out
 
 
 def inner_product(a, b) -> complex:

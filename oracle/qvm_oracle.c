@@ -222,6 +222,13 @@ double orc_norm2(const double *psi_, uint64_t n_amps) {
 }
 double orc_norm(const double *psi_, uint64_t n_amps) { return sqrt(orc_norm2(psi_, n_amps)); }
 
+/* PROBABILITY src/wavefunction.lisp:44-50 over every amplitude (what PERFORM-PROBABILITIES collects,
+ * app/src/api/probabilities.lisp): out[i] = re^2 + im^2. */
+void orc_probabilities(const double *psi_, uint64_t n_amps, double *out) {
+    const cplx *psi = (const cplx *)psi_;
+    for (uint64_t i = 0; i < n_amps; i++) out[i] = prob(psi[i]);
+}
+
 /* INNER-PRODUCT inside PURE-STATE-EXPECTATION app/src/api/expectation.lisp:79-84:
  * (loop :for ai :across a :for bi :across b :sum (* (conjugate ai) bi)), sequential, out = (re, im). */
 void orc_inner_product(const double *a_, const double *b_, uint64_t n_amps, double *out) {

@@ -48,6 +48,7 @@ _SIGS = {
     "qvmcuda_prob_ground": [C.c_void_p, C.c_int, C.POINTER(C.c_double)],
     "qvmcuda_norm2": [C.c_void_p, C.POINTER(C.c_double)],
     "qvmcuda_inner_product": [C.c_void_p, C.c_void_p, C.c_void_p],
+    "qvmcuda_probabilities": [C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint64],
     "qvmcuda_scale": [C.c_void_p, C.c_double],
     "qvmcuda_normalize": [C.c_void_p],
     "qvmcuda_collapse": [C.c_void_p, C.c_int, C.c_int, C.c_double],

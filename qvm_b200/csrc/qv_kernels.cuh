@@ -236,6 +236,18 @@ qv_elementwise_kernel(qvc* __restrict__ psi, uint64_t count, int mode, uint32_t 
     }
 }
 
+// out[i] = |psi[first + i]|^2, the PROBABILITY of every basis state (src/wavefunction.lisp:44-50) for the
+// :probabilities export path (app/src/api/probabilities.lisp, handle-request.lisp:155-176): 8 instead of 16 bytes
+// per amplitude leave the device.  Explicitly rounded products and sum: bit-exact against the oracle.
+__global__ void __launch_bounds__(QV_THREADS)
+qv_probs_kernel(const qvc* __restrict__ psi, uint64_t first, uint64_t count, double* __restrict__ out) {
+    const uint64_t stride = (uint64_t)gridDim.x * QV_THREADS;
+    for (uint64_t i = (uint64_t)blockIdx.x * QV_THREADS + threadIdx.x; i < count; i += stride) {
+        const qvc a = qv_ld_stream(psi + first + i);
+        out[i] = __dadd_rn(__dmul_rn(a.x, a.x), __dmul_rn(a.y, a.y));
+    }
+}
+
 __global__ void qv_set_one_kernel(qvc* psi, uint64_t index) {
     psi[index].x = 1.0;
     psi[index].y = 0.0;

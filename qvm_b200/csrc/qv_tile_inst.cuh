@@ -10,13 +10,16 @@ namespace {
 template <typename PROG, bool FULL>
 const char* qv_launch_one(const QvTileLaunch& L) {
     constexpr int MODE = QV_INST_MODE, M = QV_INST_M;
-    static std::atomic<bool> attr_set{false};
-    if (!attr_set.exchange(true)) {
+    // function attributes are per device: one flag per (instantiation, device ordinal)
+    static std::atomic<bool> attr_set[64];
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return "cannot identify the current device";
+    if (!attr_set[dev].exchange(true)) {
         cudaError_t e = cudaFuncSetAttribute(qv_tile_kernel<PROG, MODE, FULL, M>, cudaFuncAttributeMaxDynamicSharedMemorySize, 65536);
         if (e == cudaSuccess)
             e = cudaFuncSetAttribute(qv_tile_kernel<PROG, MODE, FULL, M>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
         if (e != cudaSuccess) {
-            attr_set = false;
+            attr_set[dev] = false;
             return cudaGetErrorString(e);
         }
     }

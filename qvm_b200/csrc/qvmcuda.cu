@@ -745,6 +745,34 @@ int qvmcuda_inner_product(qvmcuda_state* a, qvmcuda_state* b, double out[2]) {
     return 0;
 }
 
+int qvmcuda_probabilities(qvmcuda_state* s, double* out, uint64_t offset, uint64_t count) {
+    if (!s || (count && !out)) return fail("null argument");
+    if (offset > s->n_amps || count > s->n_amps - offset) return fail("range outside the state");
+    if (count == 0) return 0;
+    std::lock_guard<std::mutex> lk(s->mu);
+    DeviceGuard dg(s->device);
+    if (int rc = canonicalize_locked(s)) return rc;
+    // chunks of at most 2^24 basis states through one temporary device buffer (128 MiB)
+    const uint64_t chunk = count < (1ull << 24) ? count : (1ull << 24);
+    double* d_tmp = nullptr;
+    CK(cudaMalloc((void**)&d_tmp, chunk * sizeof(double)));
+    int rc = 0;
+    for (uint64_t done = 0; done < count && !rc; done += chunk) {
+        const uint64_t n = count - done < chunk ? count - done : chunk;
+        uint64_t blocks = (n + QV_THREADS - 1) / QV_THREADS;
+        const uint64_t cap = (uint64_t)s->sm_count * 8 * 4;
+        if (blocks > cap) blocks = cap;
+        qv_probs_kernel<<<(int)blocks, QV_THREADS, 0, s->stream>>>(s->d_amps, offset + done, n, d_tmp);
+        g_launches++;
+        cudaError_t e = cudaGetLastError();
+        if (e == cudaSuccess) e = cudaMemcpyAsync(out + done, d_tmp, n * sizeof(double), cudaMemcpyDeviceToHost, s->stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(s->stream);
+        if (e != cudaSuccess) rc = fail(std::string("probabilities: ") + cudaGetErrorString(e));
+    }
+    cudaFree(d_tmp);
+    return rc;
+}
+
 int qvmcuda_scale(qvmcuda_state* s, double factor) {
     if (!s) return fail("null argument");
     std::lock_guard<std::mutex> lk(s->mu);

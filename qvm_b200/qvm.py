@@ -100,6 +100,14 @@ class DeviceVector:
         L.check(L.lib().qvmcuda_norm2(self.handle, C.byref(p)))
         return p.value
 
+    def probabilities(self, offset: int = 0, count: Optional[int] = None) -> np.ndarray:
+        """|psi_i|^2 of COUNT basis states from OFFSET, computed on the device (PERFORM-PROBABILITIES,
+        app/src/api/probabilities.lisp): 8 bytes per basis state cross PCIe instead of 16."""
+        count = self.length - offset if count is None else count
+        out = np.zeros(count, dtype=np.float64)
+        L.check(L.lib().qvmcuda_probabilities(self.handle, L.ptr(out), int(offset), int(count)))
+        return out
+
     def inner_product(self, other: "DeviceVector") -> complex:
         """<self|other> = sum conj(self_i) other_i (app/src/api/expectation.lisp:79-84)."""
         out = np.zeros(2, dtype=np.float64)
@@ -494,6 +502,19 @@ class DensityQVM(BaseQVM):
             elif isinstance(x, Halt):
                 break
         return self
+
+
+def wavefunction_octets(amplitudes) -> bytes:
+    """The :wavefunction reply body (app/src/handle-request.lisp:135-153, WRITE-COMPLEX-DOUBLE-FLOAT-AS-BINARY
+    app/src/utilities.lisp:64-78): every amplitude as two big-endian IEEE-754 doubles, 16 octets each."""
+    a = np.ascontiguousarray(amplitudes, dtype=np.complex128)
+    return a.view(np.float64).astype(">f8").tobytes()
+
+
+def probabilities_octets(probabilities) -> bytes:
+    """The :probabilities reply body (app/src/handle-request.lisp:155-176, WRITE-DOUBLE-FLOAT-AS-BINARY
+    app/src/utilities.lisp:80-87): big-endian doubles, 8 octets each."""
+    return np.ascontiguousarray(probabilities, dtype=np.float64).astype(">f8").tobytes()
 
 
 def pure_state_expectation(qvm: "PureStateQVM", prepared: DeviceVector, op, first_time: bool = False) -> complex:

@@ -457,3 +457,16 @@ def test_inner_product_and_expectation(Q, O):
             O.apply_matrix(phi, G.gate_matrix(ins.name, ins.params), tuple(ins.qubits))
         assert abs(g - O.inner_product(psi, phi).real) < 1e-13
     assert abs(got[3] - 1.0) < 1e-13
+
+
+def test_probabilities_export(Q, O):
+    """PERFORM-PROBABILITIES on the device: |psi_i|^2 bit for bit as the oracle's PROBABILITY (explicitly rounded)."""
+    n = 15
+    psi = rand_state(n, 6)
+    vec = Q.DeviceVector(1 << n)
+    vec.upload(psi)
+    ref = O.probabilities(psi)
+    assert np.array_equal(vec.probabilities(), ref)
+    assert np.array_equal(vec.probabilities(1000, 777), ref[1000:1777])
+    assert Q.probabilities_octets(vec.probabilities(0, 4)) == Q.probabilities_octets(ref[:4])
+    vec.close()

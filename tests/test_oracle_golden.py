@@ -258,3 +258,24 @@ def test_inner_product_is_the_reference_loop():
     z0[3] = -z0[3]
     assert abs(O.inner_product(bell, z0)) < 1e-15
     assert abs(O.inner_product(bell, bell) - 1.0) < 1e-15
+
+
+def test_probabilities_and_wire_formats():
+    """:wavefunction / :probabilities replies (app/src/handle-request.lisp:135-176) are streams of big-endian IEEE
+    doubles (WRITE-64-BE, app/src/utilities.lisp:40-87); the Bell pair of tests/state-representation-tests.lisp:30-41."""
+    import struct
+    from oracle import oracle as O
+    from qvm_b200 import qvm as Q
+    bell = np.zeros(4, dtype=np.complex128)
+    bell[0] = bell[3] = math.sqrt(0.5)
+    p = O.probabilities(bell)
+    assert np.allclose(p, [0.5, 0, 0, 0.5], atol=1e-15)
+    wf = Q.wavefunction_octets(bell)
+    assert len(wf) == 16 * 4
+    assert wf[:8] == struct.pack(">d", math.sqrt(0.5)) and wf[8:16] == struct.pack(">d", 0.0)
+    assert wf[48:56] == struct.pack(">d", math.sqrt(0.5))
+    po = Q.probabilities_octets(p)
+    assert po == b"".join(struct.pack(">d", x) for x in p)
+    rng = np.random.default_rng(3)
+    a = rng.standard_normal(32) + 1j * rng.standard_normal(32)
+    assert np.array_equal(O.probabilities(a), a.real * a.real + a.imag * a.imag)

@@ -64,3 +64,35 @@ def test_diagonal_gates_on_global_qubits_need_no_exchange():
     steps, peer_steps, desc, l2p = run_emulator_sharded(a, n, world, circ, fuse=True, tile_bits=6)
     assert peer_steps == 0, desc
     assert_close(unpermute(a, l2p), ref)
+
+
+@pytest.mark.parametrize("world", [2, 8])
+@pytest.mark.parametrize("pull", [False, True])
+def test_repeated_application_carries_the_layout(world, pull):
+    """bench.py's sharded step applies the same circuit again and again on whatever layout the previous run left
+    behind (SWAPs on rank bits are relabelings, remaps move qubits): three QFTs in a row, layout carried over,
+    must equal three oracle QFTs."""
+    n = 13
+    circ = CC.qft_circuit(range(n))
+    a = rand_state(n, 11)
+    ref = a.copy()
+    l2p = np.arange(n, dtype=np.int32)
+    relabeled = 0
+    for it in range(3):
+        ref = run_oracle(ref, circ)
+        # the shards hold the state in PHYSICAL order; hand the emulator the current layout and take the new one back
+        import ctypes as C
+        from helpers import emulator, flatten_circuit
+        ks, qf, mf = flatten_circuit(circ)
+        desc = C.create_string_buffer(1 << 16)
+        emu = emulator()
+        emu.qvtest_run_sharded.restype = C.c_int
+        emu.qvtest_set_remap_pull(int(pull))
+        emu.qvtest_set_reg_bits(0)
+        p = lambda x: x.ctypes.data_as(C.c_void_p)
+        rc = emu.qvtest_run_sharded(p(a), n, world, len(circ), p(ks), p(qf), p(mf), 1, 7, 0, p(l2p), desc, len(desc))
+        assert rc >= 0, desc.value.decode()
+        relabeled += desc.value.decode().count("relabeled_swaps")
+        assert_close(unpermute(a, l2p), ref)
+    assert relabeled >= 1      # at least one run met a SWAP on a rank bit
+    assert not (l2p == np.arange(n)).all()
