@@ -1063,7 +1063,8 @@ Tape compile(const std::vector<Gate>& gates, int n_bits, const CompileOptions& o
     if (geo.T < 1 || geo.T > QV_MAX_TILE_BITS || (geo.T < geo.n_local && geo.T < 2))
         throw std::runtime_error("tile_bits out of range");
     // keep room for a 2-target gate above the always-resident low bits
-    geo.lmin = (geo.T < geo.n_local) ? std::max(0, std::min(opt.min_low_bits, geo.T - 2)) : geo.T;
+    // (a shard that fits one tile still needs room for rank bits in a peer pass, hence the g_bits test)
+    geo.lmin = (geo.T < geo.n_local || g_bits > 0) ? std::max(0, std::min(opt.min_low_bits, geo.T - 2)) : geo.T;
     if (g_bits > 0 && geo.T - geo.lmin < 2)
         throw std::runtime_error("shard too small for the requested number of ranks");
     const uint64_t lowmask = (1ull << geo.lmin) - 1;
@@ -1126,6 +1127,17 @@ Tape compile(const std::vector<Gate>& gates, int n_bits, const CompileOptions& o
             if (next_use[a] != next_use[b]) return next_use[a] > next_use[b];
             return w2p[a] > w2p[b];     // prefer high local bits: longer contiguous runs stay put
         });
+        if (cand.size() < globals.size()) {
+            // tiny shards: fall back to the always-resident low bits as well (correct, only shorter contiguous runs)
+            std::vector<int> low;
+            for (int wq = 0; wq < n_bits; wq++)
+                if (w2p[wq] < geo.lmin && !(need_wires >> wq & 1)) low.push_back(wq);
+            std::stable_sort(low.begin(), low.end(), [&](int a, int b) {
+                if (next_use[a] != next_use[b]) return next_use[a] > next_use[b];
+                return w2p[a] > w2p[b];
+            });
+            cand.insert(cand.end(), low.begin(), low.end());
+        }
         if (cand.size() < globals.size()) throw std::runtime_error("scheduler: no local bit available for a remap");
         if (opt.remap_pull) {
             // one out-of-place pull moves every needed pair at once
