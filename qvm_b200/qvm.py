@@ -517,6 +517,55 @@ def probabilities_octets(probabilities) -> bytes:
     return np.ascontiguousarray(probabilities, dtype=np.float64).astype(">f8").tobytes()
 
 
+UNUSED_QUBIT = None      # the reference's :unused-qubit marker (app/src/api/multishot-measure.lisp:66-69)
+
+
+def relabel_multishot_qubits(qubits: Sequence[int], num_qubits: int, relabeling: Optional[Sequence[int]]):
+    """The relabeling step of %PERFORM-MULTISHOT-MEASURE (app/src/api/multishot-measure.lisp:62-77): qubit q becomes
+    its position in RELABELING (or :unused-qubit when absent), and the register grows to hold the largest one."""
+    qubits = list(qubits)
+    if any((not isinstance(q, (int, np.integer))) or q < 0 for q in qubits):
+        raise ValueError("qubits must be non-negative integers")
+    if relabeling is not None:
+        rel = [int(x) for x in relabeling]
+        qubits = [rel.index(q) if q in rel else UNUSED_QUBIT for q in qubits]
+        used = [q for q in qubits if q is not UNUSED_QUBIT]
+        num_qubits = max(num_qubits, 1 + max(used, default=-1))
+    return qubits, num_qubits
+
+
+def multishot_bits(basis_states, qubits: Sequence[Optional[int]]) -> List[List[int]]:
+    """What PARALLEL-MEASURE collects per trial (app/src/api/multishot-measure.lisp:13-38): bit q of the measured basis
+    state for every requested qubit, 0 for :unused-qubit, in the order of QUBITS."""
+    b = np.asarray(basis_states, dtype=np.uint64)
+    cols = [np.zeros(b.size, dtype=np.int64) if q is UNUSED_QUBIT else ((b >> np.uint64(q)) & np.uint64(1)).astype(np.int64)
+            for q in qubits]
+    return np.stack(cols, axis=1).tolist() if cols else [[] for _ in range(b.size)]
+
+
+def perform_multishot_measure(quil, num_qubits: int, qubits: Sequence[int], num_trials: int,
+                              relabeling: Optional[Sequence[int]] = None, device: int = 0, seed: Optional[int] = None):
+    """%PERFORM-MULTISHOT-MEASURE on a pure state (app/src/api/multishot-measure.lisp:50-110).  The reference prepares
+    the state once and then, PER TRIAL, restores a 2^n copy and collapses it with MEASURE-ALL (or qubit by qubit);
+    here the prepared state never leaves the device and all NUM-TRIALS outcomes are drawn from it in ONE sampler call
+    (one read of the state + NUM-TRIALS descents) with MEASURE-ALL's decision rule (strict, src/measurement.lisp:128-143).
+    Measuring a subset of the qubits is the marginal of the same draw (the alternative the reference's own XXX comment
+    debates, :27-31)."""
+    if not qubits or num_trials == 0:
+        return []
+    qubits, num_qubits = relabel_multishot_qubits(qubits, num_qubits, relabeling)
+    if any(q is not UNUSED_QUBIT and q >= num_qubits for q in qubits):
+        raise ValueError(f"The provided qubits {qubits} to a multishot measure are out of range for the given QVM, "
+                         f"which only has {num_qubits} qubits.")
+    qvm = make_qvm(num_qubits, device=device, seed=seed)
+    qvm.load_program(quil)
+    qvm.run()
+    u = qvm.rng.random_sample(num_trials)
+    outcomes = qvm.state.vec.sample(u, strict=True)
+    qvm.state.vec.close()
+    return multishot_bits(outcomes, qubits)
+
+
 def pure_state_expectation(qvm: "PureStateQVM", prepared: DeviceVector, op, first_time: bool = False) -> complex:
     """PURE-STATE-EXPECTATION (app/src/api/expectation.lisp:78-91): restore the prepared state, run the operator
     program OP on it and return <prepared | OP prepared>.  Everything stays on the device."""

@@ -105,3 +105,27 @@ def test_qft_circuit_shape():
     assert abs(np.angle(c[3][0][3, 3]) - math.pi / 4) < 1e-15 and c[3][1] == (27, 29)
     assert c[-15][1] == (0, 29) and c[-1][1] == (14, 15)
     assert CC.qft_circuit([5]) == [] or len(CC.qft_circuit([5])) == 1
+
+
+def test_multishot_relabeling_and_bit_extraction():
+    """app/src/api/multishot-measure.lisp:13-38,62-77: relabeled qubits, :unused-qubit reads 0, bits in request order;
+    the sampled basis states come from the oracle's MEASURE-ALL sampler here (the GPU sampler is pinned to it bit for bit)."""
+    from oracle import oracle as O
+    from qvm_b200 import qvm as Q
+    qs, n = Q.relabel_multishot_qubits([0, 2, 5], 2, [2, 0])
+    assert qs == [1, 0, Q.UNUSED_QUBIT] and n == 2
+    qs, n = Q.relabel_multishot_qubits([3], 1, [9, 8, 7, 3])
+    assert qs == [3] and n == 4
+    assert Q.relabel_multishot_qubits([1, 0], 2, None) == ([1, 0], 2)
+    with pytest.raises(ValueError):
+        Q.relabel_multishot_qubits([-1], 2, None)
+    # GHZ on 3 qubits: every trial reads 000 or 111 whatever the request order; unused qubits read 0
+    psi = np.zeros(8, dtype=np.complex128)
+    psi[0] = psi[7] = math.sqrt(0.5)
+    u = np.random.default_rng(1).random(200)
+    states = O.sample_tree(psi, u, True)
+    bits = Q.multishot_bits(states, [2, Q.UNUSED_QUBIT, 0, 1])
+    assert len(bits) == 200 and all(b in ([0, 0, 0, 0], [1, 0, 1, 1]) for b in bits)
+    assert 60 < sum(b[0] for b in bits) < 140
+    assert Q.multishot_bits([5, 2], [0, 1, 2]) == [[1, 0, 1], [0, 1, 0]]
+    assert Q.perform_multishot_measure("H 0", 1, [], 10) == [] and Q.perform_multishot_measure("H 0", 1, [0], 0) == []
