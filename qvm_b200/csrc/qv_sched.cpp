@@ -645,9 +645,9 @@ void emit_round(BlobWriter& w, const std::vector<RoundOp>& rops, const std::vect
             for (; j >= (int)rd.first_uop; j--) {
                 const QvUop& e = w.uops[j];
                 bool mixes = false;
-                if (e.kind >= QV_K_BFLY && e.kind < QV_K_BFLY + 4) mixes = (e.kind - QV_K_BFLY) == r;
-                else if (e.kind >= QV_K_BFLY_DIAG1_S && e.kind < QV_K_COUNT) mixes = ((e.kind - QV_K_BFLY_DIAG1_S) & 3) == r;
-                else if (e.kind < QV_K_DENSE2) mixes = (e.kind - QV_K_DENSE1) / 2 == r;
+                if (e.kind >= QV_K_BFLY && e.kind < QV_K_BFLY + 4) mixes = (int)(e.kind - QV_K_BFLY) == r;
+                else if (e.kind >= QV_K_BFLY_DIAG1_S && e.kind < QV_K_COUNT) mixes = (int)((e.kind - QV_K_BFLY_DIAG1_S) & 3) == r;
+                else if (e.kind < QV_K_DENSE2) mixes = (int)((e.kind - QV_K_DENSE1) / 2) == r;
                 else if (e.kind < QV_K_DIAG_BASE) {
                     static const int pr[6][2] = {{0, 1}, {0, 2}, {1, 2}, {0, 3}, {1, 3}, {2, 3}};
                     const int p = (e.kind - QV_K_DENSE2) / 2;
