@@ -129,3 +129,12 @@ def test_multishot_relabeling_and_bit_extraction():
     assert 60 < sum(b[0] for b in bits) < 140
     assert Q.multishot_bits([5, 2], [0, 1, 2]) == [[1, 0, 1], [0, 1, 0]]
     assert Q.perform_multishot_measure("H 0", 1, [], 10) == [] and Q.perform_multishot_measure("H 0", 1, [0], 0) == []
+
+
+def test_header_is_plain_c(tmp_path):
+    """The boundary is a C ABI: include/qvmcuda.h must compile as C99 (no C++ / torch types in the signatures)."""
+    import subprocess
+    src = tmp_path / "hdr.c"
+    src.write_text('#include "qvmcuda.h"\nint main(void) { return 0; }\n')
+    subprocess.check_call(["gcc", "-std=c99", "-Wall", "-Wextra", "-pedantic", "-fsyntax-only",
+                           "-I", os.path.join(ROOT, "include"), str(src)])
