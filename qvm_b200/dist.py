@@ -241,6 +241,46 @@ class ShardedState:
 
 
 # --------------------------------------------------------------------------------------- bench (N > 1)
+def _main_attr(name):
+    """bench.py runs as __main__ under torchrun: borrow its helpers (ClockSampler, measured_peaks) when present."""
+    import sys
+    return getattr(sys.modules.get("__main__"), name, None)
+
+
+def _start_clock_sampler(rank: int, local_rank: int):
+    try:
+        cls = _main_attr("ClockSampler")
+        return cls(local_rank) if (rank == 0 and cls is not None) else None
+    except Exception:
+        return None
+
+
+def _stop_clock_sampler(sampler):
+    try:
+        return sampler.stop() if sampler is not None else None
+    except Exception:
+        return None
+
+
+def _sharded_roofline(local_qubits: int, step_seconds: float, passes_per_step: float, peer_passes_per_step: float):
+    """Per-GPU figure for the sharded run: every pass reads and writes the rank's whole shard (32 B per amplitude,
+    SURVEY 8d), so achieved = 32 * 2^local_qubits * passes / step time.  Pull passes are bounded by NVLink ingress,
+    not by HBM: their count is reported beside it."""
+    try:
+        peaks = _main_attr("measured_peaks")
+        peak, src = peaks() if peaks is not None else (6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)")
+        bytes_per_pass = 32.0 * float(1 << local_qubits)
+        achieved = bytes_per_pass * passes_per_step / step_seconds / 1e9 if step_seconds > 0 else None
+        return {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                "frac": (achieved / peak) if achieved else None, "traffic": None,
+                "kernel": "qv_tile_kernel per GPU, average over the passes of a step (pull passes are NVLink-ingress-bound)",
+                "peak_source": src, "bytes_per_launch": bytes_per_pass, "launches_per_step": passes_per_step,
+                "pull_passes_per_step": peer_passes_per_step}
+    except Exception:
+        return None
+
+
+
 def bench_sharded(args, rank: int, world: int, local_rank: int):
     """Weak scaling: every rank keeps a 2^args.qubits shard; the circuit is the QFT on
     args.qubits + log2(world) qubits.  value = 30-qubit-equivalent gates/s = gates * 2^(n - args.qubits) / s,
@@ -271,6 +311,7 @@ def bench_sharded(args, rank: int, world: int, local_rank: int):
     torch.cuda.synchronize()
     l0 = _lib.launch_count()
     p0, s0 = st.peer_steps, st.steps
+    sampler = _start_clock_sampler(rank, local_rank)     # nvidia-smi clocks during the timed region (rank 0)
     t0 = time.perf_counter()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ev0.record()
@@ -284,6 +325,7 @@ def bench_sharded(args, rank: int, world: int, local_rank: int):
     dist.all_reduce(t, op=dist.ReduceOp.MAX)
     dt = float(t.item())
     launches = _lib.launch_count() - l0
+    clocks = _stop_clock_sampler(sampler)
     norm2 = st.norm2()
     if rank == 0:
         scale = 2.0 ** (n - args.qubits)
@@ -299,6 +341,8 @@ def bench_sharded(args, rank: int, world: int, local_rank: int):
                        "hbm_passes_per_step": (st.steps - s0) / args.steps, "peer_passes_per_step": peer_per_step,
                        "exchange": "tile kernel P2P loads/stores over NVLink (IPC-mapped shards); torch.distributed barriers only",
                        "timing": "host wall clock bracketed by barrier + cudaDeviceSynchronize, max over ranks"},
+            "roofline": _sharded_roofline(args.qubits, dt / args.steps, (st.steps - s0) / args.steps, peer_per_step),
+            "clocks": clocks,
             "gpu_launches": int(launches), "norm2": norm2,
             "e2e": {"value": value, "unit": "gates/s", "h2d_bytes_per_step": int(sum(np.asarray(m).nbytes for m, _ in gates)),
                     "d2h_bytes_per_step": 0, "what": "apply_gates from host gate arrays (scheduled, uploaded and run inside the timed region)"},
