@@ -83,6 +83,18 @@ int qvmcuda_tape_run(qvmcuda_state *s, qvmcuda_tape *t);
 int qvmcuda_tape_info(qvmcuda_tape *t, int64_t info[8]);
 int qvmcuda_tape_describe(qvmcuda_tape *t, char *buf, uint64_t buflen);
 int qvmcuda_tape_destroy(qvmcuda_tape *t);
+/* The pass compiler (the device-side counterpart of the reference's run-time COMPILE of gate lambdas and their cache,
+ * src/compile-gate.lisp:156-209, 315-361): every fused pass of a tape that carries enough work is turned into its own
+ * straight-line sm_100a kernel (NVRTC), cached in memory and on disk by structure; gate angles and qubit positions stay
+ * data.  QVMCUDA_JIT = sync (default) | async | off; passes without a compiled kernel run through the interpreter kernel.
+ * stats: [0] kernels compiled, [1] in-memory cache hits, [2] disk cache hits, [3] failures, [4] compiled-pass launches,
+ * [5] compile time in ms, [6] policy (0 off, 1 sync, 2 async), [7] micro-op threshold. */
+int qvmcuda_jit_stats(int64_t stats[8]);
+/* generated CUDA source of one step (diagnostics, tests) and its cache key */
+int qvmcuda_tape_jit_source(qvmcuda_tape *t, int step, char *buf, uint64_t buflen, uint64_t *signature);
+/* compile every eligible step of the tape into the on-disk kernel cache without touching a device (build-time
+ * prewarming; needs no GPU).  log receives the compiler output (register counts, spills). */
+int qvmcuda_tape_jit_precompile(qvmcuda_tape *t, int *n_eligible, int *n_compiled, char *log, uint64_t loglen);
 
 /* ---- measurement protocol (src/measurement.lisp:7-150) */
 /* WAVEFUNCTION-EXCITED-STATE-PROBABILITY src/wavefunction.lisp:64-70 */

@@ -44,6 +44,9 @@ _SIGS = {
     "qvmcuda_tape_info": [C.c_void_p, C.c_void_p],
     "qvmcuda_tape_describe": [C.c_void_p, C.c_char_p, C.c_uint64],
     "qvmcuda_tape_destroy": [C.c_void_p],
+    "qvmcuda_jit_stats": [C.c_void_p],
+    "qvmcuda_tape_jit_source": [C.c_void_p, C.c_int, C.c_char_p, C.c_uint64, C.POINTER(C.c_uint64)],
+    "qvmcuda_tape_jit_precompile": [C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_int), C.c_char_p, C.c_uint64],
     "qvmcuda_prob_excited": [C.c_void_p, C.c_int, C.POINTER(C.c_double)],
     "qvmcuda_prob_ground": [C.c_void_p, C.c_int, C.POINTER(C.c_double)],
     "qvmcuda_norm2": [C.c_void_p, C.POINTER(C.c_double)],
@@ -111,6 +114,15 @@ def flatten_gates(gates):
         if np.asarray(m).shape != (1 << int(k), 1 << int(k)):
             raise ValueError("gate matrix does not match its qubit count")
     return ks, qf, np.ascontiguousarray(mf)
+
+
+def jit_stats() -> dict:
+    """Counters of the pass compiler (qvmcuda_jit_stats)."""
+    a = np.zeros(8, dtype=np.int64)
+    check(lib().qvmcuda_jit_stats(ptr(a)))
+    return {"compiled": int(a[0]), "cache_hits": int(a[1]), "disk_hits": int(a[2]), "failed": int(a[3]),
+            "launches": int(a[4]), "compile_ms": int(a[5]), "policy": ["off", "sync", "async"][int(a[6])],
+            "min_uops": int(a[7])}
 
 
 def launch_count() -> int:

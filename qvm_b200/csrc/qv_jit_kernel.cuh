@@ -1,0 +1,122 @@
+// qv_jit_kernel.cuh -- skeleton of a COMPILED gate pass.
+//
+// The pass compiler (qv_jit_gen.cpp) turns one tile program (qv_program.h) into CUDA C++ in which everything the
+// interpreter kernel (qv_tile_kernel.cuh) decodes at run time is a literal: the rounds are unrolled, every
+// micro-op is a direct call of its qv_ops.h template with compile-time register bits, control masks, index fields and
+// blob / table offsets, and the matrices are read from the constant bank at fixed addresses (they reach the FP64 pipe
+// as c[bank][offset] operands).  Gate matrices, diagonal tables and tile geometry stay DATA (the kernel parameter and
+// the table pool), so passes with the same structure but other angles or qubit positions share one cubin.  This is the
+// device-side analogue of the reference's per-gate compiled lambdas and their cache
+// (src/compile-gate.lisp:156-209, 315-334), one level up: one compiled function per fused pass.
+//
+// The generated translation unit defines, before including this file:
+//   QVJ_M, QVJ_THREADS, QVJ_MODE (0 local, 2 pull), QVJ_PROG_BYTES, QVJ_HAS_SCALE, QVJ_STORE_PERM, QVJ_HAS_TABLES,
+//   the round functions qvj_round_<r>() and QVJ_RUN_ROUNDS (the sequence of rounds with barriers in between).
+// With QVJ_HOST defined the same text compiles as plain C++ (tests/support: the round functions are run by the CPU
+// emulator in place of its interpreter, which checks the generator without a GPU).
+#pragma once
+
+#if !defined(QVJ_HOST)
+
+struct QvjProg { uint8_t bytes[QVJ_PROG_BYTES]; };
+
+extern "C" __global__ void __launch_bounds__(QVJ_THREADS, QVJ_MIN_CTAS)
+qvj_kernel(const __grid_constant__ QvjProg prog, const __grid_constant__ QvPeers peers,
+           const qvc* __restrict__ tables, qvc* __restrict__ alt_own) {
+    constexpr bool PULL = QVJ_MODE == 2;
+    constexpr int THREADS = QVJ_THREADS;
+    constexpr int ITERS = 4096 / THREADS;
+    extern __shared__ __align__(16) uint8_t qv_smem_raw[];
+    qvc* tile = reinterpret_cast<qvc*>(qv_smem_raw);
+#if QVJ_HAS_TABLES
+    __shared__ qvc s_slice[QV_SLICE_ENTRIES];
+    __shared__ uint32_t s_srcext[QV_MAX_SOURCES];
+    __shared__ uint8_t s_pred[QV_MAX_PREDS];
+#else
+    const qvc* s_slice = nullptr;
+    const uint8_t* s_pred = nullptr;
+#endif
+    const uint8_t* blob = prog.bytes;
+    const QvPassHeader* h = reinterpret_cast<const QvPassHeader*>(blob);
+    const uint64_t fixed_bits = h->fixed_bits;
+    const uint64_t n_tiles = h->n_tiles;
+    const uint32_t n_local = h->n_local_bits;
+    const uint64_t local_mask = (1ull << n_local) - 1ull;
+    const uint32_t tid = threadIdx.x;
+    const uint64_t glo = qv_gather((uint64_t)tid, h->tile_segs, h->n_tile_segs);
+    qvc* const my_tile = tile + qv_swz(tid);
+    qvc* const own = PULL ? alt_own : peers.base[(fixed_bits >> n_local) & (QV_MAX_PEERS - 1)];
+#if QVJ_STORE_PERM
+    uint32_t st_lo = h->st_const;
+#pragma unroll
+    for (uint32_t k = 0; k < 12; k++)
+        if (tid >> k & 1) st_lo ^= h->st_col[k];
+#endif
+#if QVJ_HAS_SCALE
+    const double out_scale = h->out_scale;
+#endif
+
+    for (uint64_t t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+        const uint64_t base = qv_gather(t, h->base_segs, h->n_base_segs) | fixed_bits;
+        const uint64_t pbase = (base | glo) & local_mask;
+
+        // ---- HBM -> shared memory (asynchronous 16-byte copies, all in flight at once)
+        if (!PULL) {
+            const char* tsrc = reinterpret_cast<const char*>(own + pbase);
+#pragma unroll
+            for (int i = 0; i < ITERS; i++) qv_cp_async16(my_tile + i * THREADS, reinterpret_cast<const qvc*>(tsrc + h->hi_byte[i]));
+        } else {
+            const uint64_t sbase = qv_remap_index(base | glo, h->pull_remap);
+#pragma unroll
+            for (int i = 0; i < ITERS; i++) {
+                const uint64_t p = sbase ^ h->hi_src[i];
+                qv_cp_async16(my_tile + i * THREADS, peers.base[(p >> n_local) & (QV_MAX_PEERS - 1)] + (p & local_mask));
+            }
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+
+#if QVJ_HAS_TABLES
+        {   // per-tile tables, built while the copies fly (same construction as the interpreter kernel)
+            const QvSource* sources = reinterpret_cast<const QvSource*>(blob + h->off_sources);
+            const QvSlice* slices = reinterpret_cast<const QvSlice*>(blob + h->off_slices);
+            const uint8_t* slice_of = blob + h->off_slice_of;
+            const QvPred* preds = reinterpret_cast<const QvPred*>(blob + h->off_preds);
+            for (uint32_t i = tid; i < h->n_sources; i += THREADS)
+                s_srcext[i] = (uint32_t)qv_gather(base, sources[i].esegs, sources[i].n_esegs) << sources[i].nl;
+            for (uint32_t i = tid; i < h->n_preds; i += THREADS)
+                s_pred[i] = (base & preds[i].mask) == preds[i].val ? 1 : 0;
+            __syncthreads();
+            for (uint32_t f = tid; f < h->n_slice_entries; f += THREADS) {
+                const QvSlice& sl = slices[slice_of[f]];
+                s_slice[f] = qv_slice_entry(sl, sources, s_srcext, tables, f - sl.off);
+            }
+        }
+#endif
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
+        __syncthreads();
+
+        // ---- the rounds: straight-line code emitted by the pass compiler
+        QVJ_RUN_ROUNDS(tile, tid, blob, tables, s_slice, s_pred)
+
+        // ---- shared memory -> HBM
+        {
+            char* tdst = reinterpret_cast<char*>(own + pbase);
+#pragma unroll
+            for (int i = 0; i < ITERS; i++) {
+#if QVJ_STORE_PERM
+                qvc v = tile[st_lo ^ h->st_hi[i]];
+#else
+                qvc v = my_tile[i * THREADS];
+#endif
+#if QVJ_HAS_SCALE
+                v.x *= out_scale;
+                v.y *= out_scale;
+#endif
+                qv_st_stream(reinterpret_cast<qvc*>(tdst + h->hi_byte[i]), v);
+            }
+        }
+        __syncthreads();
+    }
+}
+
+#endif  // !QVJ_HOST

@@ -1,0 +1,16 @@
+// qv_jit_prelude.cuh -- first include of every generated pass (qv_jit_gen.cpp): the micro-op templates and the
+// handful of macros that let the same text compile for the device (NVRTC) and, under QVJ_HOST, for the test emulator.
+#pragma once
+#if defined(QVJ_HOST)
+#include "qv_ops.h"
+#define QVJ_FN static inline
+#define QVJ_RESTRICT
+#define QVJ_UNROLL
+#define QVJ_SYNC() do { } while (0)
+#else
+#include "qv_tile_common.cuh"
+#define QVJ_FN __device__ __forceinline__
+#define QVJ_RESTRICT __restrict__
+#define QVJ_UNROLL _Pragma("unroll")
+#define QVJ_SYNC() __syncthreads()
+#endif

@@ -19,7 +19,17 @@
 // translated logical qubits into physical index bits.  All structs are PODs
 // copied verbatim to the device.
 #pragma once
+#if defined(__CUDACC_RTC__)
+// NVRTC (the pass compiler, qv_jit.cpp) has no system headers: the fixed-width types come from the compiler's own
+typedef unsigned char uint8_t;
+typedef unsigned short uint16_t;
+typedef unsigned int uint32_t;
+typedef unsigned long long uint64_t;
+typedef int int32_t;
+typedef long long int64_t;
+#else
 #include <stdint.h>
+#endif
 
 #define QV_MAX_TILE_BITS 12      // 2^12 amplitudes * 16 B = 64 KiB of shared memory per CTA
 #define QV_MIN_LOW_BITS 4        // low bits always inside the tile: 256-byte HBM runs at worst

@@ -14,6 +14,7 @@
 #include "qv_kernels.cuh"
 #include "qv_tile_launch.h"
 #include "qv_sched.h"
+#include "qv_jit.h"
 
 namespace {
 
@@ -95,6 +96,10 @@ struct qvmcuda_tape {
     std::vector<size_t> offsets;          // per step offset into the buffer
     size_t total_bytes = 0;
     int n_local = 0, rank = 0, world = 1; // geometry the tape was compiled for
+    // compiled passes (qv_jit.h) per device: jit[dev][step] = kernel or nullptr (interpreter); complete = no step is
+    // still waiting for the asynchronous compiler
+    std::map<int, std::vector<qv::JitKernel*>> jit;
+    std::map<int, bool> jit_complete;
 };
 
 namespace {
@@ -123,7 +128,7 @@ int tile_grid(const qvmcuda_state* s, uint64_t n_tiles) {
 
 // The tile-kernel instantiations are compiled in their own translation units (qv_tile_inst_*.cu), one per
 // (mode, register bits), so that the build runs in parallel; each exports one launcher.
-int launch_tile_p(qvmcuda_state* s, const qv::Step& st, const QvPassHeader& h, const uint8_t* d_tables) {
+int launch_tile_p(qvmcuda_state* s, const qv::Step& st, const QvPassHeader& h, const uint8_t* d_tables, qv::JitKernel* jk) {
     const bool full = h.T == QV_MAX_TILE_BITS;
     int mode = 0;
     if (h.pull) {
@@ -144,7 +149,19 @@ int launch_tile_p(qvmcuda_state* s, const qv::Step& st, const QvPassHeader& h, c
     L.tables = (const qvc*)d_tables;
     L.alt_own = s->d_alt;
     const char* err = nullptr;
-    if (h.reg_bits == 4) {
+    if (jk && full && mode != 1) {
+        // compiled pass: the same tile program, executed by its own straight-line kernel
+        qv::JitLaunch J;
+        J.blob = L.blob;
+        J.blob_bytes = L.blob_bytes;
+        J.grid = L.grid;
+        J.smem = L.smem;
+        J.stream = (void*)s->stream;
+        J.peers = L.peers;
+        J.tables = L.tables;
+        J.alt_own = L.alt_own;
+        err = qv::jit_launch(jk, J);
+    } else if (h.reg_bits == 4) {
         // the 16-amplitudes-per-thread kernel exists for full local tiles only (the scheduler never asks otherwise)
         if (!full || h.threads_log2 != 7 || mode != 0) return fail("4 register bits need a full 12-bit local tile");
         err = qv_launch_tile_0_4(L);
@@ -161,12 +178,12 @@ int launch_tile_p(qvmcuda_state* s, const qv::Step& st, const QvPassHeader& h, c
     return 0;
 }
 
-int launch_tile(qvmcuda_state* s, const qv::Step& st, const uint8_t* d_tables) {
+int launch_tile(qvmcuda_state* s, const qv::Step& st, const uint8_t* d_tables, qv::JitKernel* jk) {
     QvPassHeader h;
     std::memcpy(&h, st.blob.data(), sizeof(h));
     if (st.blob.size() > QV_PROG_LARGE_BYTES) return fail("pass control program too large");
     if ((h.uses_peers || h.pull) && s->world < 2) return fail("peer pass on a state without attached peers");
-    return launch_tile_p(s, st, h, d_tables);
+    return launch_tile_p(s, st, h, d_tables, jk);
 }
 
 int launch_big(qvmcuda_state* s, const qv::Step& st, const uint8_t* d_mat) {
@@ -198,15 +215,38 @@ int launch_remap(qvmcuda_state* s, const qv::Step& st) {
     return 0;
 }
 
-int launch_step(qvmcuda_state* s, const qv::Step& st, const uint8_t* d_data) {
-    if (st.kind == qv::Step::TILE) return launch_tile(s, st, d_data);
+int launch_step(qvmcuda_state* s, const qv::Step& st, const uint8_t* d_data, qv::JitKernel* jk = nullptr) {
+    if (st.kind == qv::Step::TILE) return launch_tile(s, st, d_data, jk);
     if (st.kind == qv::Step::BIG) return launch_big(s, st, d_data);
     return launch_remap(s, st);
 }
 
-int run_steps(qvmcuda_state* s, const qv::Tape& tape, const std::vector<size_t>& offsets, const uint8_t* d_buf) {
+// kernels of the compiled passes of a tape on the state's device (nullptr entries run through the interpreter kernel)
+void prepare_jit(qvmcuda_state* s, const qv::Tape& tape, std::vector<qv::JitKernel*>& out) {
+    std::vector<const qv::Step*> ptrs;
+    for (const qv::Step& st : tape.steps) ptrs.push_back(&st);
+    qv::jit_prepare(ptrs, s->device, out);
+}
+
+const std::vector<qv::JitKernel*>& tape_jit(qvmcuda_state* s, qvmcuda_tape* t) {
+    std::vector<qv::JitKernel*>& v = t->jit[s->device];
+    if (v.size() != t->tape.steps.size() || !t->jit_complete[s->device]) {
+        prepare_jit(s, t->tape, v);
+        // in asynchronous mode kernels arrive later: ask again on the next run until every eligible step has one
+        t->jit_complete[s->device] = qv::jit_policy() != qv::JitPolicy::ASYNC;
+    }
+    return v;
+}
+
+int run_steps(qvmcuda_state* s, const qv::Tape& tape, const std::vector<size_t>& offsets, const uint8_t* d_buf,
+              const std::vector<qv::JitKernel*>* jit = nullptr) {
+    std::vector<qv::JitKernel*> local;
+    if (!jit) {
+        prepare_jit(s, tape, local);
+        jit = &local;
+    }
     for (size_t i = 0; i < tape.steps.size(); i++) {
-        int rc = launch_step(s, tape.steps[i], d_buf + offsets[i]);
+        int rc = launch_step(s, tape.steps[i], d_buf + offsets[i], (*jit)[i]);
         if (rc) return rc;
     }
     return 0;
@@ -622,7 +662,7 @@ int qvmcuda_tape_run_step(qvmcuda_state* s, qvmcuda_tape* t, int step) {
     uint8_t* d_buf = nullptr;
     if (int rc = tape_device_buffer(s, t, &d_buf)) return rc;
     const qv::Step& st = t->tape.steps[step];
-    return launch_step(s, st, d_buf + t->offsets[step]);
+    return launch_step(s, st, d_buf + t->offsets[step], tape_jit(s, t)[step]);
 }
 
 int qvmcuda_tape_commit(qvmcuda_state* s, qvmcuda_tape* t) {
@@ -656,8 +696,50 @@ int qvmcuda_tape_run(qvmcuda_state* s, qvmcuda_tape* t) {
     }
     uint8_t* d_buf = nullptr;
     if (int rc = tape_device_buffer(s, t, &d_buf)) return rc;
-    if (int rc = run_steps(s, t->tape, t->offsets, d_buf)) return rc;
+    if (int rc = run_steps(s, t->tape, t->offsets, d_buf, &tape_jit(s, t))) return rc;
     s->l2p = t->tape.l2p;
+    return 0;
+}
+
+int qvmcuda_jit_stats(int64_t out[8]) {
+    if (!out) return fail("null argument");
+    const qv::JitStats st = qv::jit_stats();
+    std::memset(out, 0, 8 * sizeof(int64_t));
+    out[0] = (int64_t)st.compiled;
+    out[1] = (int64_t)st.cache_hits;
+    out[2] = (int64_t)st.disk_hits;
+    out[3] = (int64_t)st.failed;
+    out[4] = (int64_t)st.launches;
+    out[5] = (int64_t)(st.compile_seconds * 1e3);
+    out[6] = (int64_t)qv::jit_policy();
+    out[7] = (int64_t)qv::jit_min_uops();
+    return 0;
+}
+
+int qvmcuda_tape_jit_source(qvmcuda_tape* t, int step, char* buf, uint64_t buflen, uint64_t* sig) {
+    if (!t || !buf || buflen == 0) return fail("null argument");
+    if (step < 0 || step >= (int)t->tape.steps.size()) return fail("step out of range");
+    const qv::JitSource src = qv::jit_generate(t->tape.steps[step]);
+    if (!src.ok) return fail("step has no compiled form: " + src.why_not);
+    if (src.text.size() + 1 > buflen) return fail("buffer too small for the generated source");
+    std::memcpy(buf, src.text.c_str(), src.text.size() + 1);
+    if (sig) *sig = src.sig;
+    return 0;
+}
+
+int qvmcuda_tape_jit_precompile(qvmcuda_tape* t, int* n_eligible, int* n_ok, char* log, uint64_t loglen) {
+    if (!t) return fail("null argument");
+    std::vector<const qv::Step*> ptrs;
+    for (const qv::Step& st : t->tape.steps) ptrs.push_back(&st);
+    std::string text;
+    int ne = 0, nk = 0;
+    qv::jit_precompile(ptrs, ne, nk, text);
+    if (n_eligible) *n_eligible = ne;
+    if (n_ok) *n_ok = nk;
+    if (log && loglen) {
+        std::strncpy(log, text.c_str(), loglen - 1);
+        log[loglen - 1] = 0;
+    }
     return 0;
 }
 

@@ -31,14 +31,23 @@ def emulator():
     global _EMU
     if _EMU is None:
         so = os.path.join(SUPPORT, "libqvemu.so")
-        srcs = [os.path.join(SUPPORT, "qv_emulator.cpp"), os.path.join(ROOT, "qvm_b200", "csrc", "qv_sched.cpp")]
-        deps = srcs + [os.path.join(ROOT, "qvm_b200", "csrc", f) for f in ("qv_ops.h", "qv_program.h", "qv_sched.h")]
+        srcs = [os.path.join(SUPPORT, "qv_emulator.cpp"), os.path.join(ROOT, "qvm_b200", "csrc", "qv_sched.cpp"),
+                os.path.join(ROOT, "qvm_b200", "csrc", "qv_jit_gen.cpp")]
+        deps = srcs + [os.path.join(ROOT, "qvm_b200", "csrc", f) for f in ("qv_ops.h", "qv_program.h", "qv_sched.h", "qv_jit.h")]
         if not os.path.exists(so) or any(os.path.getmtime(d) > os.path.getmtime(so) for d in deps):
             subprocess.check_call(["/usr/bin/g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-Wno-unknown-pragmas",
-                                   "-o", so] + srcs)
+                                   "-o", so] + srcs + ["-ldl"])
         _EMU = C.CDLL(so)
         _EMU.qvtest_run.restype = C.c_int
     return _EMU
+
+
+def emulator_jit_host(on: bool) -> int:
+    """Switch the emulator between interpreting the micro-ops and running the pass compiler's generated C++
+    (compiled for the host with g++ -DQVJ_HOST).  Returns the number of passes run compiled so far."""
+    emu = emulator()
+    emu.qvtest_set_jit_host.restype = C.c_int
+    return emu.qvtest_set_jit_host(int(on), os.path.join(ROOT, "qvm_b200", "csrc").encode())
 
 
 def flatten_circuit(circ):

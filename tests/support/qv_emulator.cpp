@@ -11,10 +11,52 @@
 #include <string>
 #include <vector>
 
+#include <dlfcn.h>
+#include <unistd.h>
+
+#include <cstdio>
+#include <cstdlib>
+#include <map>
+
+#include "../../qvm_b200/csrc/qv_jit.h"
 #include "../../qvm_b200/csrc/qv_ops.h"
 #include "../../qvm_b200/csrc/qv_sched.h"
 
 namespace {
+
+// ---- compiled passes on the host: the text the pass compiler (qv_jit_gen.cpp) would hand to NVRTC is compiled with
+// g++ (-DQVJ_HOST) and its round functions replace the interpreter loop below.  This checks the generator -- literal
+// offsets, index expressions, slot addressing, template arguments -- against the oracle without a GPU.
+bool g_jit_host = false;
+int g_jit_host_used = 0;
+std::string g_csrc_dir;
+typedef void (*qvj_round_fn)(int, qvc*, uint32_t, const uint8_t*, const qvc*, const qvc*, const uint8_t*);
+std::map<uint64_t, qvj_round_fn> g_jit_fns;
+
+qvj_round_fn host_compiled_rounds(const qv::Step& st) {
+    const qv::JitSource src = qv::jit_generate(st);
+    if (!src.ok) return nullptr;
+    auto it = g_jit_fns.find(src.sig);
+    if (it != g_jit_fns.end()) return it->second;
+    char base[128];
+    snprintf(base, sizeof(base), "/tmp/qvj_host_%ld_%016llx", (long)getpid(), (unsigned long long)src.sig);
+    const std::string cu = std::string(base) + ".cpp", so = std::string(base) + ".so";
+    FILE* f = fopen(cu.c_str(), "w");
+    if (!f) throw std::runtime_error("emulator: cannot write the generated pass");
+    fwrite(src.text.data(), 1, src.text.size(), f);
+    fclose(f);
+    const std::string cmd = "/usr/bin/g++ -O1 -std=c++17 -fPIC -shared -DQVJ_HOST -Wno-unknown-pragmas -I" + g_csrc_dir + " -o " + so + " " + cu + " 2>" + base + ".log";
+    if (system(cmd.c_str()) != 0) throw std::runtime_error("emulator: g++ failed on a generated pass, see " + std::string(base) + ".log");
+    void* lib = dlopen(so.c_str(), RTLD_NOW | RTLD_LOCAL);
+    if (!lib) throw std::runtime_error(std::string("emulator: dlopen of a generated pass: ") + dlerror());
+    qvj_round_fn fn = (qvj_round_fn)dlsym(lib, "qvj_host_round");
+    if (!fn) throw std::runtime_error("emulator: generated pass lacks qvj_host_round");
+    unlink(cu.c_str());
+    unlink(so.c_str());
+    unlink((std::string(base) + ".log").c_str());
+    g_jit_fns[src.sig] = fn;
+    return fn;
+}
 
 // peers[r] = base pointer of rank r's shard (peers[0] for a single device)
 // pull passes (header.pull): loads go through the remap from the current buffers, stores into alt_own
@@ -39,6 +81,11 @@ void run_tile_step(qvc* const* peers, const qv::Step& st, qvc* alt_own = nullptr
     if (h.n_sources > QV_MAX_SOURCES || h.n_preds > QV_MAX_PREDS || h.n_slice_entries > QV_SLICE_ENTRIES ||
         h.n_slices > QV_MAX_SLICES)
         throw std::runtime_error("emulator: per-tile table limits exceeded");
+    qvj_round_fn compiled = nullptr;
+    if (g_jit_host && h.n_rounds > 0) {
+        compiled = host_compiled_rounds(st);
+        if (compiled) g_jit_host_used++;
+    }
     auto addr = [&](uint64_t p) { return peers[p >> h.n_local_bits] + (p & local_mask); };
     if (h.pull && !alt_own) throw std::runtime_error("emulator: pull pass without an alternate buffer");
     // the kernel's split source index: S(base | gather(tid)) ^ hi_src[i]
@@ -65,6 +112,11 @@ void run_tile_step(qvc* const* peers, const qv::Step& st, qvc* alt_own = nullptr
             s_slice[f] = qv_slice_entry(sl, sources, s_srcext.data(), tables, f - sl.off);
         }
         for (uint32_t e = 0; e < tile_n; e++) smem[qv_swz(e)] = h.pull ? *addr(src_index(base, e)) : *addr(phys(base, e));
+        if (compiled) {     // the generated round functions, one virtual thread after the other, round by round
+            for (uint32_t r = 0; r < h.n_rounds; r++)
+                for (uint32_t tid = 0; tid < threads; tid++)
+                    compiled((int)r, smem.data(), tid, blob, tables, s_slice.data(), s_pred.data());
+        } else
         for (uint32_t r = 0; r < h.n_rounds; r++) {
             const QvRound& rd = rounds[r];
             if (rd.m > h.reg_bits) throw std::runtime_error("emulator: round uses more register bits than the pass declares");
@@ -178,6 +230,12 @@ int g_reg_bits = 0;
 
 extern "C" void qvtest_set_remap_pull(int on) { g_remap_pull = on != 0; }
 extern "C" void qvtest_set_reg_bits(int m) { g_reg_bits = m; }
+// compiled-pass mode: csrc_dir = where qv_jit_prelude.cuh & co. live; returns the number of passes run compiled so far
+extern "C" int qvtest_set_jit_host(int on, const char* csrc_dir) {
+    g_jit_host = on != 0;
+    if (csrc_dir) g_csrc_dir = csrc_dir;
+    return g_jit_host_used;
+}
 
 extern "C" int qvtest_run(double* psi, int n_bits, int n_gates, const int* ks, const int* qubits_flat,
                           const double* mats_flat, int fuse, int tile_bits, int absorb_swaps,
