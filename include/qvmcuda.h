@@ -121,6 +121,12 @@ int qvmcuda_collapse(qvmcuda_state *s, int qubit, int keep_bit, double inv_norm)
  * (SAMPLE-WAVEFUNCTION-AS-DISTRIBUTION-IN-PARALLEL-TRULY src/measurement.lisp:179-225, used by MEASURE-ALL :128-143).
  * The CDF is accumulated in the blocked order documented in oracle/qvm_oracle.c (orc_sample_tree). */
 int qvmcuda_sample(qvmcuda_state *s, const double *uniforms, uint64_t n_shots, uint64_t *out, int strict);
+/* The same sampler on ONE SHARD of a sharded state (physical index order, rank-major): every rank asks for its shard's mass
+ * (qvmcuda_sample_total, tree order), the host adds the totals left to right, and the rank that owns a draw resolves it with
+ * the preceding shards' mass as the starting accumulator BASE -- indices are bit-exact against the oracle's
+ * orc_sample_tree_sharded.  Indices returned are local to the shard. */
+int qvmcuda_sample_total(qvmcuda_state *s, double *total);
+int qvmcuda_sample_shard(qvmcuda_state *s, const double *uniforms, uint64_t n_shots, uint64_t *out, int strict, double base);
 /* psi <- |basis> (second half of MEASURE-ALL-STATE src/measurement.lisp:137-141) */
 int qvmcuda_set_basis_state(qvmcuda_state *s, uint64_t basis);
 

@@ -70,6 +70,9 @@ def lib():
         L.orc_density_diag_probs.restype = None; L.orc_density_diag_probs.argtypes = [vp, i32, vp]
         L.orc_evolve_stochastic.restype = i32; L.orc_evolve_stochastic.argtypes = [vp, u64, i32, vp, i32, vp, dbl]
         L.orc_sample_tree.restype = None; L.orc_sample_tree.argtypes = [vp, u64, vp, u64, i32, vp]
+        L.orc_sample_tree_total.restype = dbl; L.orc_sample_tree_total.argtypes = [vp, u64]
+        L.orc_sample_tree_base.restype = None; L.orc_sample_tree_base.argtypes = [vp, u64, vp, u64, i32, dbl, vp]
+        L.orc_sample_tree_sharded.restype = None; L.orc_sample_tree_sharded.argtypes = [vp, u64, i32, vp, u64, i32, vp]
         _lib = L
     return _lib
 
@@ -186,6 +189,25 @@ def sample_tree(psi, u, strict: bool):
     u = np.ascontiguousarray(u, dtype=np.float64)
     out = np.empty(u.size, dtype=np.uint64)
     lib().orc_sample_tree(_p(_state(psi)), psi.size, _p(u), u.size, 1 if strict else 0, _p(out))
+    return out
+
+
+def sample_tree_total(psi) -> float:
+    return float(lib().orc_sample_tree_total(_p(_state(psi)), psi.size))
+
+
+def sample_tree_base(psi, u, strict: bool, base: float):
+    u = np.ascontiguousarray(u, dtype=np.float64)
+    out = np.empty(u.size, dtype=np.uint64)
+    lib().orc_sample_tree_base(_p(_state(psi)), psi.size, _p(u), u.size, 1 if strict else 0, float(base), _p(out))
+    return out
+
+
+def sample_tree_sharded(psi, world: int, u, strict: bool):
+    """The sharded sampler's order: psi = `world` contiguous shards (physical index order, rank-major)."""
+    u = np.ascontiguousarray(u, dtype=np.float64)
+    out = np.empty(u.size, dtype=np.uint64)
+    lib().orc_sample_tree_sharded(_p(_state(psi)), psi.size, int(world), _p(u), u.size, 1 if strict else 0, _p(out))
     return out
 
 

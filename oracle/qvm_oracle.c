@@ -494,9 +494,12 @@ static double tree_sum_1024(const double *v, uint64_t count) {
 
 static inline int rule_hit(double c, double p, int strict) { return strict ? (c > p) : (c >= p); }
 
-void orc_sample_tree(const double *psi_, uint64_t n_amps, const double *u, uint64_t n_shots,
-                     int strict, uint64_t *out) {
-    const cplx *psi = (const cplx *)psi_;
+/* The descent with a starting accumulator BASE (the probability mass that precedes this vector: 0 for a whole state,
+ * the sum of the preceding shards' totals for one shard of a sharded state).  Every comparison adds BASE first, in the
+ * same place the GPU does (qv_sample_descend_kernel); BASE = 0.0 leaves every sum bit-identical.  *total = the vector's
+ * own mass in tree order (last entry of the top prefix). */
+static void sample_tree_base(const cplx *psi, uint64_t n_amps, const double *u, uint64_t n_shots,
+                             int strict, double base, uint64_t *out, double *total) {
     uint64_t n1 = (n_amps + SB - 1) / SB;
     uint64_t n2 = (n1 + SB - 1) / SB;
     double *l1 = (double *)malloc(sizeof(double) * n1);
@@ -514,16 +517,17 @@ void orc_sample_tree(const double *psi_, uint64_t n_amps, const double *u, uint6
     }
     double s = 0.0;
     for (uint64_t c = 0; c < n2; c++) { s += l2[c]; top[c] = s; }
+    if (total) *total = top[n2 - 1];
     for (uint64_t t = 0; t < n_shots; t++) {
         double p = u[t];
         /* chunk: binary search over the monotone top prefix */
         uint64_t lo = 0, hi = n2 - 1;
         while (lo < hi) {
             uint64_t mid = lo + (hi - lo) / 2;
-            if (rule_hit(top[mid], p, strict)) hi = mid; else lo = mid + 1;
+            if (rule_hit(base + top[mid], p, strict)) hi = mid; else lo = mid + 1;
         }
         uint64_t c = lo;
-        double acc = (c == 0) ? 0.0 : top[c - 1];
+        double acc = (c == 0) ? base : base + top[c - 1];
         uint64_t b0 = c * SB, bcnt = n1 - b0; if (bcnt > SB) bcnt = SB;
         double run = 0.0, before = 0.0; uint64_t b = b0 + bcnt - 1; int found = 0;
         for (uint64_t j = 0; j < bcnt; j++) {
@@ -546,6 +550,53 @@ void orc_sample_tree(const double *psi_, uint64_t n_amps, const double *u, uint6
         out[t] = r;
     }
     free(l1); free(l2); free(top);
+}
+
+void orc_sample_tree(const double *psi_, uint64_t n_amps, const double *u, uint64_t n_shots,
+                     int strict, uint64_t *out) {
+    sample_tree_base((const cplx *)psi_, n_amps, u, n_shots, strict, 0.0, out, NULL);
+}
+
+/* one shard's pieces of the sharded order (used by the CPU stand-in engine of the gloo tests) */
+double orc_sample_tree_total(const double *psi_, uint64_t n_amps) {
+    uint64_t dummy_out;
+    double dummy_u = 2.0, tot = 0.0;
+    sample_tree_base((const cplx *)psi_, n_amps, &dummy_u, 0, 0, 0.0, &dummy_out, &tot);
+    return tot;
+}
+void orc_sample_tree_base(const double *psi_, uint64_t n_amps, const double *u, uint64_t n_shots, int strict, double base,
+                          uint64_t *out) {
+    sample_tree_base((const cplx *)psi_, n_amps, u, n_shots, strict, base, out, NULL);
+}
+
+/* The SHARDED sampler's summation order (qvm_b200/dist.py ShardedState.sample): the vector is WORLD contiguous shards
+ * (dqvm's layout: the top index bits select the rank, dqvm/src/global-addresses.lisp:99-151).  Every shard builds its
+ * own tree; the shard totals are added left to right into a prefix; a draw belongs to the first shard whose inclusive
+ * prefix hits it (the tie rule of the single-device sampler) and is resolved there with the exclusive prefix as the
+ * starting accumulator.  Restates SAMPLE-WAVEFUNCTION-MULTIPLE-TIMES / the bisection sampler
+ * (src/measurement.lisp:179-225, 246-288) for a partitioned CDF. */
+void orc_sample_tree_sharded(const double *psi_, uint64_t n_amps, int world, const double *u, uint64_t n_shots,
+                             int strict, uint64_t *out) {
+    const cplx *psi = (const cplx *)psi_;
+    const uint64_t len = n_amps / (uint64_t)world;
+    double *prefix = (double *)malloc(sizeof(double) * ((size_t)world + 1));
+    uint64_t dummy_out;
+    double dummy_u = 2.0;
+    prefix[0] = 0.0;
+    for (int s = 0; s < world; s++) {
+        double tot = 0.0;
+        sample_tree_base(psi + (uint64_t)s * len, len, &dummy_u, 0, strict, 0.0, &dummy_out, &tot);
+        prefix[s + 1] = prefix[s] + tot;
+    }
+    for (uint64_t t = 0; t < n_shots; t++) {
+        int owner = world - 1;
+        for (int s = 0; s < world; s++)
+            if (rule_hit(prefix[s + 1], u[t], strict)) { owner = s; break; }
+        uint64_t local;
+        sample_tree_base(psi + (uint64_t)owner * len, len, u + t, 1, strict, prefix[owner], &local, NULL);
+        out[t] = (uint64_t)owner * len + local;
+    }
+    free(prefix);
 }
 
 /* %EVOLVE-PURE-STATE-STOCHASTICALLY src/apply-gate.lisp:16-39 with the uniform draw r supplied by the

@@ -56,6 +56,8 @@ _SIGS = {
     "qvmcuda_normalize": [C.c_void_p],
     "qvmcuda_collapse": [C.c_void_p, C.c_int, C.c_int, C.c_double],
     "qvmcuda_sample": [C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p, C.c_int],
+    "qvmcuda_sample_total": [C.c_void_p, C.POINTER(C.c_double)],
+    "qvmcuda_sample_shard": [C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p, C.c_int, C.c_double],
     "qvmcuda_density_apply_kraus": [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_uint32],
     "qvmcuda_density_prob_excited": [C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_double)],
     "qvmcuda_density_collapse": [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_double],

@@ -14,7 +14,7 @@
 
 #include "qv_sched.h"
 
-#define QVJIT_VERSION "qvjit-1"
+#define QVJIT_VERSION "qvjit-2"
 
 struct QvPeers;
 struct qvc;

@@ -7,6 +7,7 @@
 #include "qv_jit.h"
 
 #include <cstdarg>
+#include <cstddef>
 #include <cstdio>
 #include <cstring>
 
@@ -101,10 +102,14 @@ JitSource jit_generate(const Step& st, int variant) {
 
     Out o;
     o("// compiled gate pass (qv_jit_gen.cpp); variant %d\n", variant);
-    o("#define QVJ_M %d\n#define QVJ_THREADS %d\n#define QVJ_MIN_CTAS 3\n#define QVJ_MODE %d\n#define QVJ_PROG_BYTES %d\n", M, threads,
-      js.mode, js.prog_bytes);
-    o("#define QVJ_HAS_SCALE %d\n#define QVJ_STORE_PERM %d\n#define QVJ_HAS_TABLES %d\n", h.has_scale ? 1 : 0, h.store_perm ? 1 : 0,
-      (h.n_sources | h.n_preds | h.n_slice_entries) ? 1 : 0);
+    // variant bits (experiments, QVMCUDA_JIT_VARIANT): 1 = keep the two group iterations of a round rolled (fewer live
+    // registers, half the code), 2 = two CTAs per SM (up to 128 registers per thread)
+    const bool rolled = (variant & 1) != 0;
+    const int min_ctas = (variant & 2) ? 2 : 3;
+    const bool fences = (variant & 4) != 0;        // 4 = compiler fence after every micro-op (table loads are not hoisted across micro-ops)
+    o("#define QVJ_M %d\n#define QVJ_THREADS %d\n#define QVJ_MIN_CTAS %d\n#define QVJ_MODE %d\n#define QVJ_PROG_BYTES %d\n", M, threads,
+      min_ctas, js.mode, js.prog_bytes);
+    o("#define QVJ_HAS_SCALE %d\n#define QVJ_HAS_TABLES %d\n", h.has_scale ? 1 : 0, (h.n_sources | h.n_preds | h.n_slice_entries) ? 1 : 0);
     o("#include \"qv_jit_prelude.cuh\"\n\n");
 
     static const int pairs[6][2] = {{0, 1}, {0, 2}, {1, 2}, {0, 3}, {1, 3}, {2, 3}};
@@ -118,7 +123,7 @@ JitSource jit_generate(const Step& st, int variant) {
           "                        const qvc* QVJ_RESTRICT tables, const qvc* QVJ_RESTRICT s_slice, const uint8_t* QVJ_RESTRICT s_pred) {\n",
           r);
         o("    (void)blob; (void)tables; (void)s_slice; (void)s_pred;\n");
-        o("QVJ_UNROLL\n    for (uint32_t it = 0; it < %du; it++) {\n", iters);
+        o("%s\n    for (uint32_t it = 0; it < %du; it++) {\n", rolled ? "QVJ_NOUNROLL" : "QVJ_UNROLL", iters);
         o("        const uint32_t g = tid + %du * it;\n", threads);
         // e0 = g with a zero inserted at every register position (ascending)
         o("        uint32_t e0 = g;\n");
@@ -182,7 +187,17 @@ JitSource jit_generate(const Step& st, int variant) {
                         const uint32_t space = (dk - QV_K_DIAG_BASE) / 5u, gate = (dk - QV_K_DIAG_BASE) % 5u;
                         const std::string idx = index_expr(u, blob);
                         const uint32_t field = (NS == 16 ? 4u : 3u) - (gate ? 1u : 0u);
-                        if (space < 2) {
+                        // table-pool offsets are DATA (read from the micro-op record, a fixed constant-bank address): the pool
+                        // interleaves static tables with slice sources whose sizes depend on the tile geometry
+                        char tdata[64];
+                        snprintf(tdata, sizeof(tdata), "qvj_u32(blob, %uu)", (uint32_t)(h.off_uops + k * sizeof(QvUop) + offsetof(QvUop, data)));
+                        if (space == 1) {
+                            o("            qvc t = tables[%s + %s];\n", tdata, idx.c_str());
+                            if (flags & QV_UF_SCALE) o("            t = qv_cmul(t, s_slice[%uu]);\n", (unsigned)u.scale);
+                            o("            qv_diag1<%d, %u>(a, t);\n", NS, gate);
+                        } else if (space == 3) {
+                            o("            qv_diagr<%d, %u>(a, tables + %s + (%s << %uu));\n", NS, gate, tdata, idx.c_str(), field);
+                        } else if (space < 2) {
                             o("            qvc t = %s[%uu + %s];\n", space == 0 ? "s_slice" : "tables", u.data, idx.c_str());
                             if (flags & QV_UF_SCALE) o("            t = qv_cmul(t, s_slice[%uu]);\n", (unsigned)u.scale);
                             o("            qv_diag1<%d, %u>(a, t);\n", NS, gate);
@@ -194,6 +209,7 @@ JitSource jit_generate(const Step& st, int variant) {
                         }
                     }
                     o("        }\n");
+                    if (fences) o("        QVJ_FENCE();\n");
                 }
             }
             for (int s = 0; s < NS; s++) {

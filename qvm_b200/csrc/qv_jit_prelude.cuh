@@ -6,11 +6,17 @@
 #define QVJ_FN static inline
 #define QVJ_RESTRICT
 #define QVJ_UNROLL
+#define QVJ_NOUNROLL
+#define QVJ_FENCE() do { } while (0)
 #define QVJ_SYNC() do { } while (0)
 #else
 #include "qv_tile_common.cuh"
 #define QVJ_FN __device__ __forceinline__
 #define QVJ_RESTRICT __restrict__
 #define QVJ_UNROLL _Pragma("unroll")
+#define QVJ_NOUNROLL _Pragma("unroll 1")
+#define QVJ_FENCE() asm volatile("" ::: "memory")
 #define QVJ_SYNC() __syncthreads()
 #endif
+// a 32-bit field of the control program at a fixed offset (constant bank on the device)
+QVJ_FN uint32_t qvj_u32(const uint8_t* blob, uint32_t off) { return *reinterpret_cast<const uint32_t*>(blob + off); }

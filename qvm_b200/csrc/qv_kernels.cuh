@@ -303,18 +303,20 @@ __device__ __forceinline__ bool qv_rule_hit(double c, double p, int strict) { re
 __global__ void __launch_bounds__(128)
 qv_sample_descend_kernel(const qvc* __restrict__ psi, uint64_t n_amps, const double* __restrict__ l1, uint64_t n1,
                          const double* __restrict__ top, uint64_t n2, const double* __restrict__ u, uint64_t n_shots,
-                         int strict, uint64_t* __restrict__ out) {
+                         int strict, double base, uint64_t* __restrict__ out) {
+    // base: probability mass in front of this vector (0 for a whole state; the preceding shards' totals for a shard).
+    // Adding 0.0 is exact, so the single-device indices do not depend on it (oracle: sample_tree_base).
     const uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= n_shots) return;
     const double p = u[t];
     uint64_t lo = 0, hi = n2 - 1;
     while (lo < hi) {
         const uint64_t mid = lo + (hi - lo) / 2;
-        if (qv_rule_hit(top[mid], p, strict)) hi = mid;
+        if (qv_rule_hit(__dadd_rn(base, top[mid]), p, strict)) hi = mid;
         else lo = mid + 1;
     }
     const uint64_t c = lo;
-    const double acc = (c == 0) ? 0.0 : top[c - 1];
+    const double acc = (c == 0) ? base : __dadd_rn(base, top[c - 1]);
     const uint64_t b0 = c * QV_SB;
     uint64_t bcnt = n1 - b0;
     if (bcnt > QV_SB) bcnt = QV_SB;

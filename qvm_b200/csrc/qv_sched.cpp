@@ -124,6 +124,138 @@ void analyze(const Gate& g, const std::vector<int>& wire_of, std::vector<Atom>& 
     }
 }
 
+
+// ---------------------------------------------------------------- host-side matrix fusion
+// The reference multiplies the matrices of neighbouring gates on the same qubits before it compiles them
+// (quil::fuse-gates-in-executable-code, called from src/qvm.lisp:166-175).  Same idea at atom level: an uncontrolled
+// dense atom absorbs the dense atoms and 1- or 2-qubit diagonals on a SUBSET of its target wires that sit next to it in the
+// dependency order (RZ.RY.RZ on one qubit becomes one 2x2; U* on the column bit, U on the row bit and the 4x4
+// depolarizing superoperator that follows them on vec(rho) become one 4x4), as long as the merged block stays within two
+// target wires.  X / CNOT / SWAP atoms are left alone (they fold into store permutations or relabelings for free), and so
+// are diagonals that reach outside the block (CZ / CPHASE stay table lookups).  Products are formed in double precision
+// on the host: the result differs from gate-by-gate application by a few ulp per merged gate, inside the 1e-12 parity
+// tolerance.
+bool is_linear_perm(const Atom& a);
+
+std::vector<int> atom_wires(const Atom& a) { return a.kind == Atom::DIAG ? a.dw : a.tw; }
+
+// full matrix of a (dense or diagonal) atom on the wire list U (index bit j <-> U[j])
+std::vector<cd> expand_atom(const Atom& a, const std::vector<int>& U) {
+    const std::vector<int> w = atom_wires(a);
+    const size_t d = (size_t)1 << U.size();
+    std::vector<int> pos(w.size());
+    for (size_t j = 0; j < w.size(); j++) pos[j] = (int)(std::find(U.begin(), U.end(), w[j]) - U.begin());
+    uint32_t own = 0;
+    for (int p : pos) own |= 1u << p;
+    auto sub = [&](size_t x) {
+        uint32_t r = 0;
+        for (size_t j = 0; j < w.size(); j++)
+            if (x >> pos[j] & 1) r |= 1u << j;
+        return r;
+    };
+    const size_t da = (size_t)1 << w.size();
+    std::vector<cd> M(d * d, cd(0.0, 0.0));
+    for (size_t r = 0; r < d; r++)
+        for (size_t c = 0; c < d; c++) {
+            if ((r & ~(size_t)own) != (c & ~(size_t)own)) continue;
+            if (a.kind == Atom::DIAG) {
+                if (r == c) M[r * d + c] = a.mat[sub(r)];
+            } else {
+                M[r * d + c] = a.mat[(size_t)sub(r) * da + sub(c)];
+            }
+        }
+    return M;
+}
+
+bool fusable(const Atom& a) {
+    if (a.kind == Atom::BIG || a.cmask != 0) return false;
+    if (a.kind == Atom::DENSE && is_linear_perm(a)) return false;
+    return atom_wires(a).size() <= 2;
+}
+
+// `later` applied after `earlier`; returns false when the pair should stay apart
+bool fuse_pair(const Atom& earlier, const Atom& later, Atom& out) {
+    if (!fusable(earlier) || !fusable(later)) return false;
+    if (earlier.kind == Atom::DIAG && later.kind == Atom::DIAG) return false;      // diagonals merge into tables later
+    const Atom& dense = earlier.kind == Atom::DENSE ? earlier : later;
+    std::vector<int> U = dense.tw;
+    for (const Atom* x : {&earlier, &later})
+        for (int w : atom_wires(*x))
+            if (std::find(U.begin(), U.end(), w) == U.end()) {
+                if (x->kind == Atom::DIAG) return false;      // a diagonal that reaches outside the dense block stays a lookup
+                U.push_back(w);
+            }
+    if (U.size() > 2) return false;
+    const size_t d = (size_t)1 << U.size();
+    const std::vector<cd> A = expand_atom(earlier, U), B = expand_atom(later, U);
+    std::vector<cd> P(d * d, cd(0.0, 0.0));
+    for (size_t r = 0; r < d; r++)
+        for (size_t k = 0; k < d; k++) {
+            const cd b = B[r * d + k];
+            if (b == cd(0.0, 0.0)) continue;
+            for (size_t c = 0; c < d; c++) P[r * d + c] += b * A[k * d + c];
+        }
+    out = Atom();
+    bool diagonal = true;
+    for (size_t r = 0; r < d; r++)
+        for (size_t c = 0; c < d; c++)
+            if (r != c && P[r * d + c] != cd(0.0, 0.0)) diagonal = false;
+    for (int w : U) out.touch |= 1ull << w;
+    if (diagonal) {
+        out.kind = Atom::DIAG;
+        out.dw = U;
+        out.mat.resize(d);
+        for (size_t r = 0; r < d; r++) out.mat[r] = P[r * d + r];
+    } else {
+        out.kind = Atom::DENSE;
+        out.tw = U;
+        out.mat = std::move(P);
+        out.mix = out.touch;
+    }
+    return true;
+}
+
+// atoms in, atoms out (same order semantics); returns the number of merges
+int fuse_matrices(std::vector<Atom>& atoms) {
+    std::vector<Atom> out;
+    std::vector<char> alive;
+    int merges = 0;
+    for (Atom& b : atoms) {
+        Atom cur = std::move(b);
+        long pos = -1;
+        for (;;) {
+            long k = (pos < 0 ? (long)out.size() : pos) - 1;
+            for (; k >= 0; k--)
+                if (alive[k] && (out[k].touch & cur.touch)) break;
+            Atom merged;
+            if (k < 0 || !fuse_pair(out[k], cur, merged)) break;
+            // the merged atom takes the place of the EARLIER one: everything between the two leaves cur's wires alone
+            if (pos >= 0) alive[pos] = 0;
+            out[k] = std::move(merged);
+            cur = out[k];
+            pos = k;
+            merges++;
+        }
+        if (pos < 0) {
+            out.push_back(std::move(cur));
+            alive.push_back(1);
+        }
+    }
+    atoms.clear();
+    for (size_t i = 0; i < out.size(); i++) {
+        if (!alive[i]) continue;
+        Atom& a = out[i];
+        if (a.kind == Atom::DIAG) {      // drop products that came out as the identity
+            bool ident = true;
+            for (const cd& e : a.mat)
+                if (e != cd(1.0, 0.0)) ident = false;
+            if (ident) continue;
+        }
+        atoms.push_back(std::move(a));
+    }
+    return merges;
+}
+
 // ---------------------------------------------------------------- segments
 std::vector<QvSeg> make_segs(const std::vector<int>& srcpos, const std::vector<int>& dstpos) {
     std::vector<QvSeg> segs;
@@ -936,11 +1068,18 @@ Step build_tile_step(const std::vector<const Atom*>& atoms_in, uint64_t tile_tar
     for (size_t i = 0; i < w.slices.size(); i++)
         for (size_t x = 0; x < ((size_t)1 << w.slices[i].nl); x++) slice_of[w.slices[i].off + x] = (uint8_t)i;
     auto align16 = [](size_t x) { return (x + 15) & ~(size_t)15; };
+    // Layout: header, rounds, micro-ops, matrices first -- their offsets depend only on the STRUCTURE of the pass (round and
+    // micro-op counts, matrix sizes), which lets the pass compiler (qv_jit_gen.cpp) address matrices as literals and still
+    // share one kernel between passes that differ in tile geometry / number of slice sources -- then the per-tile tables.
     size_t off = align16(sizeof(QvPassHeader));
     h.off_rounds = (uint32_t)off;
     off = align16(off + w.rounds.size() * sizeof(QvRound));
     h.off_uops = (uint32_t)off;
     off = align16(off + w.uops.size() * sizeof(QvUop));
+    h.off_matrices = (uint32_t)off;
+    off = align16(off + w.mats.size() * sizeof(cd));
+    const size_t off_seglists = off;
+    off = align16(off + w.seglists.size() * sizeof(QvSegList));
     h.off_sources = (uint32_t)off;
     off = align16(off + w.sources.size() * sizeof(QvSource));
     h.off_slices = (uint32_t)off;
@@ -949,10 +1088,6 @@ Step build_tile_step(const std::vector<const Atom*>& atoms_in, uint64_t tile_tar
     off = align16(off + slice_of.size());
     h.off_preds = (uint32_t)off;
     off = align16(off + w.preds.size() * sizeof(QvPred));
-    const size_t off_seglists = off;
-    off = align16(off + w.seglists.size() * sizeof(QvSegList));
-    h.off_matrices = (uint32_t)off;
-    off = align16(off + w.mats.size() * sizeof(cd));
     h.n_table_entries = (uint32_t)w.tables.size();
     h.blob_bytes = (uint32_t)off;
     if (off > QV_PROG_LARGE_BYTES) throw std::length_error("pass control program too large");
@@ -1087,6 +1222,7 @@ Tape compile(const std::vector<Gate>& gates, int n_bits, const CompileOptions& o
         analyze(g, wire_of, atoms);
         for (size_t i = before; i < atoms.size(); i++) gate_of.push_back((int)gi);
     }
+    if (opt.fuse && opt.fuse_matrices) tape.n_fused = fuse_matrices(atoms);
     tape.n_gates = (int)gates.size();
     tape.n_atoms = (int)atoms.size();
 
@@ -1335,7 +1471,7 @@ Tape compile(const std::vector<Gate>& gates, int n_bits, const CompileOptions& o
 std::string describe(const Tape& t) {
     std::ostringstream os;
     os << "tape: n_bits=" << t.n_bits << " gates=" << t.n_gates << " atoms=" << t.n_atoms
-       << " steps=" << t.steps.size() << (t.n_relabeled ? " relabeled_swaps=" + std::to_string(t.n_relabeled) : std::string()) << "\n";
+       << " steps=" << t.steps.size() << (t.n_fused ? " matrix_merges=" + std::to_string(t.n_fused) : std::string()) << (t.n_relabeled ? " relabeled_swaps=" + std::to_string(t.n_relabeled) : std::string()) << "\n";
     for (size_t i = 0; i < t.steps.size(); i++) {
         const Step& s = t.steps[i];
         if (s.kind == Step::BIG) {

@@ -3,9 +3,8 @@
 // Replaces, for the GPU path, what the reference does in
 // src/compile-gate.lisp:315-361,409-526 (per-gate compiled lambdas) and the
 // external quil::fuse-gates-in-executable-code (called src/qvm.lisp:166-175):
-// instead of multiplying small matrices together it packs runs of gates into
-// passes/rounds of the tile kernel (see qv_program.h), which keeps every gate's
-// own arithmetic (and therefore its rounding) intact.
+// it packs runs of gates into passes/rounds of the tile kernel (see qv_program.h); gates that act on the same one or
+// two qubits back to back are first multiplied together on the host, as the reference's fusion does.
 #pragma once
 #include <complex>
 #include <cstdint>
@@ -37,6 +36,7 @@ struct CompileOptions {
     bool store_perm = true;      // fold trailing X / CNOT / SWAP gates of a pass into its write-back addressing
     bool fuse_pull = true;       // with remap_pull: merge a pull remap into the tile pass that follows it
     bool relabel_global_swaps = true;   // sharded: an exact SWAP touching a rank bit only exchanges the two wires' physical bits
+    bool fuse_matrices = true;   // with fuse: multiply neighbouring dense / diagonal atoms on the same <= 2 wires together on the host
     bool remap_pull = false;     // remaps as out-of-place pulls into the alternate buffer (needs 2x shard memory)
 };
 
@@ -58,6 +58,7 @@ struct Tape {
     std::vector<int> l2p;        // logical -> physical qubit map after the tape ran
     int n_gates = 0;
     int n_atoms = 0;
+    int n_fused = 0;             // atoms merged away by host-side matrix fusion
     int n_relabeled = 0;         // SWAP gates on rank bits executed as relabelings (sharded)
 };
 

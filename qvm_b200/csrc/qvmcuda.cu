@@ -884,12 +884,10 @@ int qvmcuda_collapse(qvmcuda_state* s, int qubit, int keep_bit, double inv_norm)
     return elementwise_locked(s, 1, (uint32_t)pbit, 0, keep_bit ? 1u : 0u, inv_norm);
 }
 
-int qvmcuda_sample(qvmcuda_state* s, const double* uniforms, uint64_t n_shots, uint64_t* out, int strict) {
-    if (!s || (n_shots && (!uniforms || !out))) return fail("null argument");
-    if (n_shots == 0) return 0;
-    std::lock_guard<std::mutex> lk(s->mu);
-    DeviceGuard dg(s->device);
-    if (int rc = canonicalize_locked(s)) return rc;
+// Blocked-order sampler on this handle's vector.  base = mass in front of it (sharded states); total_out (optional)
+// receives the vector's own mass in tree order.  n_shots may be 0 (total only).
+static int sample_locked(qvmcuda_state* s, const double* uniforms, uint64_t n_shots, uint64_t* out, int strict, double base,
+                         double* total_out) {
     const uint64_t n1 = (s->n_amps + QV_SB - 1) / QV_SB;
     const uint64_t n2 = (n1 + QV_SB - 1) / QV_SB;
     // Persistent scratch (no allocation on the measurement path): the two summation levels + top prefix live
@@ -909,7 +907,7 @@ int qvmcuda_sample(qvmcuda_state* s, const double* uniforms, uint64_t n_shots, u
     double* d_top = d_l2 + n2;
     uint64_t* d_out = reinterpret_cast<uint64_t*>(s->d_shots);
     double* d_u = reinterpret_cast<double*>(d_out + s->shot_cap);
-    CK(cudaMemcpyAsync(d_u, uniforms, n_shots * sizeof(double), cudaMemcpyHostToDevice, s->stream));
+    if (n_shots) CK(cudaMemcpyAsync(d_u, uniforms, n_shots * sizeof(double), cudaMemcpyHostToDevice, s->stream));
     auto warps_grid = [&](uint64_t blocks) {
         uint64_t g = (blocks * 32 + QV_THREADS - 1) / QV_THREADS;
         const uint64_t cap = (uint64_t)s->sm_count * 8 * 4;
@@ -918,13 +916,41 @@ int qvmcuda_sample(qvmcuda_state* s, const double* uniforms, uint64_t n_shots, u
     qv_sample_build_kernel<<<warps_grid(n1), QV_THREADS, 0, s->stream>>>(s->d_amps, nullptr, s->n_amps, d_l1, n1);
     qv_sample_build_kernel<<<warps_grid(n2), QV_THREADS, 0, s->stream>>>(nullptr, d_l1, n1, d_l2, n2);
     qv_sample_top_kernel<<<1, 32, 0, s->stream>>>(d_l2, n2, d_top);
-    qv_sample_descend_kernel<<<(int)((n_shots + 127) / 128), 128, 0, s->stream>>>(s->d_amps, s->n_amps, d_l1, n1, d_top, n2,
-                                                                               d_u, n_shots, strict ? 1 : 0, d_out);
-    g_launches += 4;
+    g_launches += 3;
+    if (n_shots) {
+        qv_sample_descend_kernel<<<(int)((n_shots + 127) / 128), 128, 0, s->stream>>>(s->d_amps, s->n_amps, d_l1, n1, d_top, n2, d_u, n_shots,
+                                                                                   strict ? 1 : 0, base, d_out);
+        g_launches++;
+    }
     CK(cudaGetLastError());
-    CK(cudaMemcpyAsync(out, d_out, n_shots * sizeof(uint64_t), cudaMemcpyDeviceToHost, s->stream));
+    if (n_shots) CK(cudaMemcpyAsync(out, d_out, n_shots * sizeof(uint64_t), cudaMemcpyDeviceToHost, s->stream));
+    if (total_out) CK(cudaMemcpyAsync(total_out, d_top + (n2 - 1), sizeof(double), cudaMemcpyDeviceToHost, s->stream));
     CK(cudaStreamSynchronize(s->stream));
     return 0;
+}
+
+int qvmcuda_sample(qvmcuda_state* s, const double* uniforms, uint64_t n_shots, uint64_t* out, int strict) {
+    if (!s || (n_shots && (!uniforms || !out))) return fail("null argument");
+    if (n_shots == 0) return 0;
+    std::lock_guard<std::mutex> lk(s->mu);
+    DeviceGuard dg(s->device);
+    if (int rc = canonicalize_locked(s)) return rc;
+    return sample_locked(s, uniforms, n_shots, out, strict, 0.0, nullptr);
+}
+
+int qvmcuda_sample_total(qvmcuda_state* s, double* total) {
+    if (!s || !total) return fail("null argument");
+    std::lock_guard<std::mutex> lk(s->mu);
+    DeviceGuard dg(s->device);
+    return sample_locked(s, nullptr, 0, nullptr, 0, 0.0, total);
+}
+
+int qvmcuda_sample_shard(qvmcuda_state* s, const double* uniforms, uint64_t n_shots, uint64_t* out, int strict, double base) {
+    if (!s || (n_shots && (!uniforms || !out))) return fail("null argument");
+    if (n_shots == 0) return 0;
+    std::lock_guard<std::mutex> lk(s->mu);
+    DeviceGuard dg(s->device);
+    return sample_locked(s, uniforms, n_shots, out, strict, base, nullptr);
 }
 
 // ------------------------------------------------------------------ density matrix

@@ -96,7 +96,8 @@ class CudaShardEngine:
     def norm2(self): return self.vec.norm2()
     def prob_excited(self, q): return self.vec.prob_excited(q)
     def collapse(self, q, keep, inv): self.vec.collapse(q, keep, inv)
-    def sample_local(self, u, strict): return self.vec.sample(u, strict)
+    def sample_total(self): return self.vec.sample_total()
+    def sample_local(self, u, strict, base): return self.vec.sample_shard(u, strict, base)
     def download(self): return self.vec.download()
     def upload(self, a): self.vec.upload(a)
     def close(self): self.vec.close()
@@ -189,30 +190,45 @@ class ShardedState:
         return cbit
 
     def sample(self, uniforms: Sequence[float], strict: bool = False) -> np.ndarray:
-        """Multi-shot sampling: shard totals -> the owning shard resolves the draw.  Returns LOGICAL basis
-        state indices.  The CDF runs in physical index order (rank-major)."""
+        """Multi-shot sampling (SAMPLE-WAVEFUNCTION-MULTIPLE-TIMES, src/measurement.lisp:246-288, on a partitioned CDF).
+        Returns LOGICAL basis state indices.  The CDF runs in physical index order (rank-major).  Summation order
+        (restated as orc_sample_tree_sharded, bit-exact): every shard's mass in its own tree order, the totals added
+        left to right, a draw resolved by the first shard whose inclusive prefix hits it, with the exclusive prefix
+        as the descent's starting accumulator (NOT subtracted from the draw: that would round differently)."""
         u = np.ascontiguousarray(uniforms, dtype=np.float64)
-        totals = [None] * self.world
-        self.dist.all_gather_object(totals, float(self.engine.norm2()))
-        prefix = np.zeros(self.world + 1)
-        for r in range(self.world):
-            prefix[r + 1] = prefix[r] + totals[r]
-        hit = (u[:, None] < prefix[None, 1:]) if strict else (u[:, None] <= prefix[None, 1:])
-        owner = np.where(hit.any(axis=1), hit.argmax(axis=1), self.world - 1)
-        mine = np.nonzero(owner == self.rank)[0]
-        phys = np.zeros(u.size, dtype=np.uint64)
-        if mine.size:
-            local = self.engine.sample_local(u[mine] - prefix[self.rank], strict)
-            phys[mine] = local + (np.uint64(self.rank) << np.uint64(self.n_local))
-        parts = [None] * self.world
-        self.dist.all_gather_object(parts, (mine, phys[mine]))
-        for idx, vals in parts:
-            phys[idx] = vals
+        phys = self.sample_physical(u, strict)
         l2p = self.layout()
         logical = np.zeros_like(phys)
         for q in range(self.n):
             logical |= ((phys >> np.uint64(int(l2p[q]))) & np.uint64(1)) << np.uint64(q)
         return logical
+
+    def sample_physical(self, u: np.ndarray, strict: bool = False) -> np.ndarray:
+        """Physical (rank-major) indices of the draws, identical on every rank."""
+        totals = [None] * self.world
+        self.dist.all_gather_object(totals, float(self.engine.sample_total()))
+        prefix = np.zeros(self.world + 1)
+        for r in range(self.world):
+            prefix[r + 1] = prefix[r] + totals[r]       # left to right, one rounding per shard
+        hit = (prefix[None, 1:] > u[:, None]) if strict else (prefix[None, 1:] >= u[:, None])
+        owner = np.where(hit.any(axis=1), hit.argmax(axis=1), self.world - 1)
+        mine = np.nonzero(owner == self.rank)[0]
+        phys = np.zeros(u.size, dtype=np.uint64)
+        if mine.size:
+            local = self.engine.sample_local(u[mine], strict, float(prefix[self.rank]))
+            phys[mine] = local + (np.uint64(self.rank) << np.uint64(self.n_local))
+        parts = [None] * self.world
+        self.dist.all_gather_object(parts, (mine, phys[mine]))
+        for idx, vals in parts:
+            phys[idx] = vals
+        return phys
+
+    def gather_physical(self) -> np.ndarray:
+        """Whole state in PHYSICAL index order (shards back to back) on every rank (tests / small states only)."""
+        self._barrier()
+        parts = [None] * self.world
+        self.dist.all_gather_object(parts, self.engine.download())
+        return np.concatenate(parts)
 
     def gather_logical(self) -> np.ndarray:
         """Whole state in logical index order on every rank (tests / small states only)."""

@@ -126,6 +126,19 @@ class DeviceVector:
         L.check(L.lib().qvmcuda_sample(self.handle, L.ptr(u), u.size, L.ptr(out), 1 if strict else 0))
         return out
 
+    def sample_total(self) -> float:
+        """This vector's probability mass in the sampler's own summation order (sharded sampling)."""
+        t = C.c_double(0.0)
+        L.check(L.lib().qvmcuda_sample_total(self.handle, C.byref(t)))
+        return float(t.value)
+
+    def sample_shard(self, uniforms, strict: bool, base: float) -> np.ndarray:
+        """Shard-local indices for draws this shard owns; base = mass of the shards in front of it."""
+        u = np.ascontiguousarray(uniforms, dtype=np.float64)
+        out = np.empty(u.size, dtype=np.uint64)
+        L.check(L.lib().qvmcuda_sample_shard(self.handle, L.ptr(u), u.size, L.ptr(out), 1 if strict else 0, float(base)))
+        return out
+
     # -- density ------------------------------------------------------------------------------
     def density_apply_kraus(self, n: int, kraus, qubits: Sequence[int], fuse: bool = True):
         ks = np.ascontiguousarray(np.stack([np.asarray(k, dtype=np.complex128) for k in kraus]))

@@ -74,9 +74,13 @@ class EmuShardEngine:
         self.local[~m] = 0
         self.local[m] *= inv
 
-    def sample_local(self, u, strict):
+    def sample_total(self):
         from oracle import oracle as O
-        return O.sample_tree(np.ascontiguousarray(self.local), u, strict)
+        return O.sample_tree_total(np.ascontiguousarray(self.local))
+
+    def sample_local(self, u, strict, base):
+        from oracle import oracle as O
+        return O.sample_tree_base(np.ascontiguousarray(self.local), u, strict, base)
 
     def download(self): return np.array(self.local)
     def upload(self, a): self.local[:] = a

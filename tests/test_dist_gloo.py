@@ -52,6 +52,10 @@ def _worker(rank, world, port, q):
         # sampling: every rank returns the same logical indices, distributed like |psi|^2
         u = np.random.default_rng(7).random(4000)
         idx = st.sample(u, strict=False)
+        # bit-exact against the oracle's restatement of the sharded summation order (physical, rank-major indices)
+        for strict in (False, True):
+            want = O.sample_tree_sharded(st.gather_physical(), world, u, strict)
+            assert (st.sample_physical(u, strict) == want).all()
         probs = np.abs(ref) ** 2
         hist = np.bincount(idx.astype(np.int64), minlength=1 << n) / u.size
         assert np.abs(hist - probs).sum() < 0.9          # coarse: 2048 bins, 4000 shots

@@ -60,6 +60,10 @@ def _worker(rank, world, port, q, inplace):
             assert abs(st.prob_excited(qb) - O.prob_excited(ref, qb)) < 1e-12
         u = np.random.default_rng(7).random(20000)
         idx = st.sample(u, strict=False).astype(np.int64)
+        # bit-exact against the oracle's restatement of the sharded summation order (physical, rank-major indices)
+        for strict in (False, True):
+            want = O.sample_tree_sharded(st.gather_physical(), world, u, strict)
+            assert (st.sample_physical(u, strict) == want).all()
         probs = np.abs(ref) ** 2
         assert probs[idx].min() > 0
         # coarse distribution check on the top 3 logical qubits
