@@ -169,6 +169,10 @@ int qvmcuda_shard_compile(qvmcuda_state *s, int n_gates, const int32_t *ks, cons
                           const double *matrices, uint32_t flags, qvmcuda_tape **out);
 int qvmcuda_tape_num_steps(qvmcuda_tape *t, int *n_steps);
 int qvmcuda_tape_step_flags(qvmcuda_tape *t, int step, uint32_t *flags);
+/* info[0] = step flags, [1] = kind (0 tile pass, 1 generic dense gate, 2 stand-alone pull remap), [2] = atoms in the step,
+ * [3] = (global, local) qubit pairs exchanged by a pull pass (each rank then reads (1 - 2^-pairs) of its shard over NVLink),
+ *        or rank bits inside the tile of an in-place peer pass, [4] = micro-ops, [5] = rounds, [6] = 1 for an in-place peer pass */
+int qvmcuda_tape_step_info(qvmcuda_tape *t, int step, int64_t info[8]);
 int qvmcuda_tape_run_step(qvmcuda_state *s, qvmcuda_tape *t, int step);
 int qvmcuda_tape_commit(qvmcuda_state *s, qvmcuda_tape *t);
 /* current logical -> physical qubit map (n entries; physical bits >= log2(shard length) select the rank) */

@@ -70,6 +70,7 @@ _SIGS = {
     "qvmcuda_shard_compile": [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.POINTER(C.c_void_p)],
     "qvmcuda_tape_num_steps": [C.c_void_p, C.POINTER(C.c_int)],
     "qvmcuda_tape_step_flags": [C.c_void_p, C.c_int, C.POINTER(C.c_uint32)],
+    "qvmcuda_tape_step_info": [C.c_void_p, C.c_int, C.c_void_p],
     "qvmcuda_tape_run_step": [C.c_void_p, C.c_void_p, C.c_int],
     "qvmcuda_tape_commit": [C.c_void_p, C.c_void_p],
     "qvmcuda_state_layout": [C.c_void_p, C.c_void_p, C.c_int],

@@ -262,6 +262,17 @@ bool trace_on() {
     return t;
 }
 
+// Generator variant of a step: QVMCUDA_JIT_VARIANT forces one; otherwise passes whose FP64 work dominates (layers of dense
+// gates: bound by the FP64 pipe, not by HBM) get two CTAs per SM with up to 128 registers per thread -- measured 6 % faster
+// on 25-qubit random layers (gpurun_out/r2b_configs_v{0,2}.jsonl) -- and everything else three CTAs with 80.
+int variant_of(const Step& st) {
+    static const int forced = getenv("QVMCUDA_JIT_VARIANT") ? atoi(getenv("QVMCUDA_JIT_VARIANT")) : -1;
+    if (forced >= 0) return forced;
+    Tape one;
+    one.steps.push_back(st);
+    return tape_cost(one) > 180.0 ? 2 : 0;
+}
+
 uint32_t real_uops(const Step& st) {
     QvPassHeader h;
     std::memcpy(&h, st.blob.data(), sizeof(h));
@@ -362,13 +373,12 @@ void jit_prepare(const std::vector<const Step*>& steps, int device, std::vector<
     out.assign(steps.size(), nullptr);
     const JitPolicy pol = jit_policy();
     if (pol == JitPolicy::OFF) return;
-    static const int variant = getenv("QVMCUDA_JIT_VARIANT") ? atoi(getenv("QVMCUDA_JIT_VARIANT")) : 0;
     std::vector<std::shared_ptr<Entry>> ent(steps.size());
     std::vector<uint64_t> sigs(steps.size(), 0);
     for (size_t i = 0; i < steps.size(); i++) {
         const Step& st = *steps[i];
         if (st.kind != Step::TILE || real_uops(st) < jit_min_uops()) continue;
-        JitSource src = jit_generate(st, variant);
+        JitSource src = jit_generate(st, variant_of(st));
         if (!src.ok) continue;
         sigs[i] = src.sig;
         std::unique_lock<std::mutex> lk(g_mu);
@@ -424,7 +434,6 @@ void jit_prepare(const std::vector<const Step*>& steps, int device, std::vector<
 
 void jit_precompile(const std::vector<const Step*>& steps, int& n_eligible, int& n_ok, std::string& log) {
     n_eligible = n_ok = 0;
-    static const int variant = getenv("QVMCUDA_JIT_VARIANT") ? atoi(getenv("QVMCUDA_JIT_VARIANT")) : 0;
     struct Job {
         JitSource src;
         bool ok = false, done = false;
@@ -436,7 +445,7 @@ void jit_precompile(const std::vector<const Step*>& steps, int& n_eligible, int&
     std::condition_variable cv;
     for (const Step* st : steps) {
         if (st->kind != Step::TILE || real_uops(*st) < jit_min_uops()) continue;
-        JitSource src = jit_generate(*st, variant);
+        JitSource src = jit_generate(*st, variant_of(*st));
         if (!src.ok || seen.count(src.sig)) continue;
         seen[src.sig] = true;
         n_eligible++;

@@ -14,7 +14,7 @@
 
 #include "qv_sched.h"
 
-#define QVJIT_VERSION "qvjit-2"
+#define QVJIT_VERSION "qvjit-3"
 
 struct QvPeers;
 struct qvc;

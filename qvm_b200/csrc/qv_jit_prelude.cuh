@@ -1,6 +1,7 @@
 // qv_jit_prelude.cuh -- first include of every generated pass (qv_jit_gen.cpp): the micro-op templates and the
 // handful of macros that let the same text compile for the device (NVRTC) and, under QVJ_HOST, for the test emulator.
 #pragma once
+#define QV_NATURAL_DENSE 1
 #if defined(QVJ_HOST)
 #include "qv_ops.h"
 #define QVJ_FN static inline

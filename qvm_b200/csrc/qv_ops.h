@@ -12,6 +12,12 @@
 #define QV_HD inline
 #endif
 
+// 1 in the translation units the pass compiler generates (qv_jit_prelude.cuh): dense micro-ops use plain sums over
+// temporaries instead of the in-place forms the interpreter kernel needs (see "In-place FP64 primitives" below)
+#if !defined(QV_NATURAL_DENSE)
+#define QV_NATURAL_DENSE 0
+#endif
+
 struct alignas(16) qvc {
     double x, y;
 };
@@ -123,6 +129,27 @@ QV_HD void qv_dense1(qvc (&a)[NS], const qvc* M, uint32_t slot_ok) {
             qv_fma_acc(a[r].y, m01.x, a[r1].y);
             qv_fma_self(a[r1].x, m11.x, ux);
             qv_fma_self(a[r1].y, m11.x, uy);
+        } else if (QV_NATURAL_DENSE) {
+            // compiled passes: plain row-times-column sums, 1 multiply + 3 fused multiply-adds per real output (16 FP64
+            // instructions per pair, the minimum for a general complex 2x2); the copies cost no FP64-pipe slot
+            const double a0x = a[r].x, a0y = a[r].y, a1x = a[r1].x, a1y = a[r1].y;
+            double x0 = m00.x * a0x, y0 = m00.x * a0y, x1 = m10.x * a0x, y1 = m10.x * a0y;
+            qv_fnma_acc(x0, m00.y, a0y);
+            qv_fma_acc(y0, m00.y, a0x);
+            qv_fnma_acc(x1, m10.y, a0y);
+            qv_fma_acc(y1, m10.y, a0x);
+            qv_fma_acc(x0, m01.x, a1x);
+            qv_fma_acc(y0, m01.x, a1y);
+            qv_fma_acc(x1, m11.x, a1x);
+            qv_fma_acc(y1, m11.x, a1y);
+            qv_fnma_acc(x0, m01.y, a1y);
+            qv_fma_acc(y0, m01.y, a1x);
+            qv_fnma_acc(x1, m11.y, a1y);
+            qv_fma_acc(y1, m11.y, a1x);
+            a[r].x = x0;
+            a[r].y = y0;
+            a[r1].x = x1;
+            a[r1].y = y1;
         } else {
             const qvc p = qv_cmul(m10, a[r]);          // the part of the second row that needs the old a[r]
             const double w = a[r].x * m00.y;
@@ -160,6 +187,32 @@ QV_HD void qv_dense2(qvc (&a)[NS], const qvc* M, uint32_t slot_ok) {
         if (r & ((1 << RB0) | (1 << RB1))) continue;
         if (CTRL && !((slot_ok >> r) & 1u)) continue;
         const int ix[4] = {r, r | (1 << RB0), r | (1 << RB1), r | (1 << RB0) | (1 << RB1)};
+        if (QV_NATURAL_DENSE && !REAL) {
+            // compiled passes: 16 FP64 instructions per output amplitude (1 multiply + 7 fused multiply-adds per real part)
+            const qvc v0 = a[ix[0]], v1 = a[ix[1]], v2 = a[ix[2]], v3 = a[ix[3]];
+#pragma unroll
+            for (int i = 0; i < 4; i++) {
+                const qvc* row = M + 4 * i;
+                double x = row[0].x * v0.x, y = row[0].x * v0.y;
+                qv_fnma_acc(x, row[0].y, v0.y);
+                qv_fma_acc(y, row[0].y, v0.x);
+                qv_fma_acc(x, row[1].x, v1.x);
+                qv_fma_acc(y, row[1].x, v1.y);
+                qv_fnma_acc(x, row[1].y, v1.y);
+                qv_fma_acc(y, row[1].y, v1.x);
+                qv_fma_acc(x, row[2].x, v2.x);
+                qv_fma_acc(y, row[2].x, v2.y);
+                qv_fnma_acc(x, row[2].y, v2.y);
+                qv_fma_acc(y, row[2].y, v2.x);
+                qv_fma_acc(x, row[3].x, v3.x);
+                qv_fma_acc(y, row[3].x, v3.y);
+                qv_fnma_acc(x, row[3].y, v3.y);
+                qv_fma_acc(y, row[3].y, v3.x);
+                a[ix[i]].x = x;
+                a[ix[i]].y = y;
+            }
+            continue;
+        }
         // off-diagonal part of every row first (needs all four old amplitudes), then the diagonal term in place
         qvc p[4];
 #pragma unroll

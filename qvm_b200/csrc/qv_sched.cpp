@@ -256,6 +256,70 @@ int fuse_matrices(std::vector<Atom>& atoms) {
     return merges;
 }
 
+// ---------------------------------------------------------------- Euler split of complex 1-qubit unitaries
+// On B200 the dense-heavy passes (layers of general 1-qubit gates) are bound by the FP64 pipe, not by HBM.  A general
+// complex 2x2 costs 8 FP64 instructions per amplitude; written as  U = diag(1, l) . R . diag(r0, r1)  with R a REAL
+// rotation [[c, -s], [s, c]] it costs 4, plus two diagonals -- and diagonals merge: the right factor of one layer, the
+// CZ / CPHASE gates between the layers and the left factor of the previous layer all land in the same table lookup
+// (one complex multiply per amplitude for up to 8 qubits).  compile() schedules both forms and keeps the cheaper one
+// (tape_cost below), so an isolated gate stays a single dense micro-op.
+bool euler_split_atom(const Atom& a, Atom out[3]) {
+    if (a.kind != Atom::DENSE || a.tw.size() != 1 || a.cmask != 0) return false;
+    const cd u00 = a.mat[0], u01 = a.mat[1], u10 = a.mat[2], u11 = a.mat[3];
+    bool real = true;
+    for (const cd& e : a.mat)
+        if (e.imag() != 0.0) real = false;
+    if (real) return false;
+    // unitary?  (Kraus operators and arbitrary DEFGATE matrices are not: they stay dense)
+    const cd g00 = std::conj(u00) * u00 + std::conj(u10) * u10, g01 = std::conj(u00) * u01 + std::conj(u10) * u11;
+    const cd g11 = std::conj(u01) * u01 + std::conj(u11) * u11;
+    if (std::abs(g00 - 1.0) > 1e-13 || std::abs(g11 - 1.0) > 1e-13 || std::abs(g01) > 1e-13) return false;
+    const double c = std::abs(u00), s = std::abs(u10);
+    if (c < 1e-8 || s < 1e-8) return false;     // (anti)diagonal up to rounding: nothing to gain
+    const cd l0 = u00 / c, l1 = u10 / s;        // r0 = 1
+    const cd r1 = u11 / (l1 * c);
+    // U = diag(l0, l1) R diag(1, r1) = diag(1, l1 / l0) R diag(l0, l0 r1)
+    const cd dl = l1 / l0, d0 = l0, d1 = l0 * r1;
+    // reconstruction check in double precision
+    const cd w00 = d0 * c, w01 = -s * d1, w10 = dl * s * d0, w11 = dl * c * d1;
+    if (std::abs(w00 - u00) + std::abs(w01 - u01) + std::abs(w10 - u10) + std::abs(w11 - u11) > 4e-15) return false;
+    const int w = a.tw[0];
+    Atom right, rot, left;
+    right.kind = Atom::DIAG;
+    right.dw = {w};
+    right.mat = {d0, d1};
+    right.touch = 1ull << w;
+    rot.kind = Atom::DENSE;
+    rot.tw = {w};
+    rot.mat = {cd(c, 0.0), cd(-s, 0.0), cd(s, 0.0), cd(c, 0.0)};
+    rot.mix = rot.touch = 1ull << w;
+    left.kind = Atom::DIAG;
+    left.dw = {w};
+    left.mat = {cd(1.0, 0.0), dl};
+    left.touch = 1ull << w;
+    out[0] = std::move(right);      // applied first
+    out[1] = std::move(rot);
+    out[2] = std::move(left);
+    return true;
+}
+
+int euler_split(std::vector<Atom>& atoms) {
+    std::vector<Atom> out;
+    out.reserve(atoms.size() * 2);
+    int n = 0;
+    for (Atom& a : atoms) {
+        Atom parts[3];
+        if (euler_split_atom(a, parts)) {
+            for (Atom& p : parts) out.push_back(std::move(p));
+            n++;
+        } else {
+            out.push_back(std::move(a));
+        }
+    }
+    atoms.swap(out);
+    return n;
+}
+
 // ---------------------------------------------------------------- segments
 std::vector<QvSeg> make_segs(const std::vector<int>& srcpos, const std::vector<int>& dstpos) {
     std::vector<QvSeg> segs;
@@ -526,6 +590,23 @@ void emit_round(BlobWriter& w, const std::vector<RoundOp>& rops, const std::vect
             }
             return nonreg + (any_reg ? (size_t)(reg_bits - (gate >= 0 ? 1 : 0)) : 0);
         };
+        // Several gates at once (one-qubit phases and CZ-like factors hanging off different register bits: layers of
+        // general gates) cost 2 FP64 instructions per amplitude PER GATE BIT; when the whole group fits ONE table
+        // (slot field + a few other tile-local bits) a single ungated lookup does it for 4.
+        {
+            std::vector<int> all_l;
+            bool any_plain = false;
+            std::vector<int> gates_used;
+            for (size_t i = 0; i < nf; i++) {
+                for (int b : ro.factors[i].pos)
+                    if (tm.local_of[b] >= 0 && std::find(all_l.begin(), all_l.end(), b) == all_l.end()) all_l.push_back(b);
+                if (want[i] < 0) any_plain = true;
+                else if (std::find(gates_used.begin(), gates_used.end(), want[i]) == gates_used.end()) gates_used.push_back(want[i]);
+            }
+            const size_t gated_cost = 2 * gates_used.size() + (any_plain ? 4 : 0);
+            if (gated_cost > 4 && eff_bits(all_l, -1) <= QV_MAX_CHUNK_BITS)
+                for (size_t i = 0; i < nf; i++) want[i] = -1;
+        }
         std::vector<PlanChunk> plan;
         for (size_t i = 0; i < nf; i++) {
             DiagFactor f = want[i] >= 0 ? restrict_to_one(ro.factors[i], want[i]) : ro.factors[i];
@@ -847,17 +928,20 @@ void build_rounds(BlobWriter& w, const std::vector<const Atom*>& atoms, const Ti
                 DiagFactor f;
                 for (int wq : a->dw) f.pos.push_back(lay.phys(wq));
                 f.diag = a->mat;
+                // (as soon as possible: diagonals commute with each other, so the factor moves back past diagonal groups
+                // as well and joins the EARLIEST group it can reach -- "phases before the rotations of this layer" and
+                // "phases after them" end up as two groups instead of one per rotation)
                 int j = (int)rops.size() - 1;
-                bool merged = false;
+                int target = -1;
                 while (j >= 0) {
-                    if (rops[j].is_diag) {
-                        rops[j].factors.push_back(f);
-                        rops[j].touch |= a->touch;
-                        merged = true;
-                        break;
-                    }
-                    if ((rops[j].mix & a->touch) != 0) break;
+                    if (rops[j].is_diag) target = j;
+                    else if ((rops[j].mix & a->touch) != 0) break;
                     j--;
+                }
+                const bool merged = target >= 0;
+                if (merged) {
+                    rops[target].factors.push_back(f);
+                    rops[target].touch |= a->touch;
                 }
                 if (!merged) {
                     RoundOp ro;
@@ -1170,9 +1254,54 @@ void fuse_pulls(Tape& tape, const CompileOptions& opt) {
 
 }  // namespace
 
+// Cost model of a tape in FP64 instructions per amplitude (the unit the dense-heavy passes are bound by on B200).  A pass
+// cannot be faster than its HBM traffic: 32 B per amplitude at ~6.2 TB/s against 64 FP64 lanes x 148 SMs x 1.965 GHz is worth
+// about 96 FP64 instructions per amplitude; exchange passes cost about eight times that (NVLink ingress).
+double tape_cost(const Tape& t) {
+    double total = 0.0;
+    for (const Step& st : t.steps) {
+        if (st.kind == Step::REMAP) { total += 800.0; continue; }
+        if (st.kind == Step::BIG) { total += std::max(96.0, 8.0 * (double)(1u << st.big.k)); continue; }
+        QvPassHeader h;
+        std::memcpy(&h, st.blob.data(), sizeof(h));
+        const QvUop* uops = reinterpret_cast<const QvUop*>(st.blob.data() + h.off_uops);
+        double fp = h.has_scale ? 2.0 : 0.0, other = 10.0 + 3.0 * h.n_rounds;
+        for (uint32_t k = 0; k < h.n_uops; k++) {
+            const uint32_t kind = uops[k].kind;
+            if (kind == QV_K_END) continue;
+            const double share = (uops[k].flags & (QV_UF_CTRL | QV_UF_PRED)) ? 0.5 : 1.0;
+            if (kind < QV_K_DENSE2) fp += share * ((kind & 1) ? 8.5 : 4.0);
+            else if (kind < QV_K_DIAG_BASE) fp += share * ((kind & 1) ? 17.0 : 8.0);
+            else if (kind >= QV_K_BFLY && kind < QV_K_BFLY + 4) fp += 2.0;
+            else if (kind >= QV_K_BFLY_DIAG1_S) { fp += 4.0; other += 1.0; }
+            else {
+                const uint32_t gate = (kind - QV_K_DIAG_BASE) % 5u;
+                fp += gate ? 2.0 : 4.0;
+                other += 1.0;
+            }
+        }
+        const double floor_cost = (h.pull || st.uses_peers) ? 800.0 : 96.0;
+        total += std::max(floor_cost, fp / 0.8 + 0.25 * other);
+    }
+    return total;
+}
+
 Tape compile(const std::vector<Gate>& gates, int n_bits, const CompileOptions& opt,
              const std::vector<int>& l2p_in) {
     if (n_bits < 1 || n_bits > 40) throw std::runtime_error("qubit count out of range");
+    if (opt.fuse && opt.euler_split < 0) {
+        // schedule with fused complex 1q matrices; if any could be written diag . rotation . diag, schedule that form too
+        // and keep the cheaper tape (both are exact to rounding; the choice is a cost model, not a semantic one)
+        CompileOptions o = opt;
+        o.euler_split = 0;
+        Tape fused = compile(gates, n_bits, o, l2p_in);
+        if (fused.n_splittable == 0) return fused;
+        o.euler_split = 1;
+        Tape split = compile(gates, n_bits, o, l2p_in);
+        const double cf = tape_cost(fused), cs = tape_cost(split);
+        if (getenv("QV_SCHED_DEBUG")) fprintf(stderr, "euler split: cost fused %.1f split %.1f\n", cf, cs);
+        return cs < cf ? split : fused;
+    }
     Tape tape;
     tape.n_bits = n_bits;
     std::vector<int> w2p = l2p_in;          // wire q starts as logical qubit q
@@ -1223,6 +1352,12 @@ Tape compile(const std::vector<Gate>& gates, int n_bits, const CompileOptions& o
         for (size_t i = before; i < atoms.size(); i++) gate_of.push_back((int)gi);
     }
     if (opt.fuse && opt.fuse_matrices) tape.n_fused = fuse_matrices(atoms);
+    if (opt.fuse && opt.euler_split > 0) tape.n_split = euler_split(atoms);
+    else if (opt.fuse) {
+        Atom parts[3];
+        for (const Atom& a : atoms)
+            if (euler_split_atom(a, parts)) tape.n_splittable++;
+    }
     tape.n_gates = (int)gates.size();
     tape.n_atoms = (int)atoms.size();
 
@@ -1471,7 +1606,8 @@ Tape compile(const std::vector<Gate>& gates, int n_bits, const CompileOptions& o
 std::string describe(const Tape& t) {
     std::ostringstream os;
     os << "tape: n_bits=" << t.n_bits << " gates=" << t.n_gates << " atoms=" << t.n_atoms
-       << " steps=" << t.steps.size() << (t.n_fused ? " matrix_merges=" + std::to_string(t.n_fused) : std::string()) << (t.n_relabeled ? " relabeled_swaps=" + std::to_string(t.n_relabeled) : std::string()) << "\n";
+       << " steps=" << t.steps.size() << (t.n_fused ? " matrix_merges=" + std::to_string(t.n_fused) : std::string())
+       << (t.n_split ? " euler_splits=" + std::to_string(t.n_split) : std::string()) << (t.n_relabeled ? " relabeled_swaps=" + std::to_string(t.n_relabeled) : std::string()) << "\n";
     for (size_t i = 0; i < t.steps.size(); i++) {
         const Step& s = t.steps[i];
         if (s.kind == Step::BIG) {

@@ -37,6 +37,7 @@ struct CompileOptions {
     bool fuse_pull = true;       // with remap_pull: merge a pull remap into the tile pass that follows it
     bool relabel_global_swaps = true;   // sharded: an exact SWAP touching a rank bit only exchanges the two wires' physical bits
     bool fuse_matrices = true;   // with fuse: multiply neighbouring dense / diagonal atoms on the same <= 2 wires together on the host
+    int euler_split = -1;        // complex 1q unitaries as diag . real rotation . diag: 1 always, 0 never, -1 = whichever tape is cheaper
     bool remap_pull = false;     // remaps as out-of-place pulls into the alternate buffer (needs 2x shard memory)
 };
 
@@ -59,6 +60,8 @@ struct Tape {
     int n_gates = 0;
     int n_atoms = 0;
     int n_fused = 0;             // atoms merged away by host-side matrix fusion
+    int n_split = 0;             // complex 1q unitaries written as diag . rotation . diag (Euler split)
+    int n_splittable = 0;        // ... that could have been
     int n_relabeled = 0;         // SWAP gates on rank bits executed as relabelings (sharded)
 };
 
@@ -67,5 +70,8 @@ Tape compile(const std::vector<Gate>& gates, int n_bits, const CompileOptions& o
              const std::vector<int>& l2p_in = {});
 
 std::string describe(const Tape& t);
+
+// estimated cost in FP64 instructions per amplitude (used to choose between equivalent schedules)
+double tape_cost(const Tape& t);
 
 }  // namespace qv

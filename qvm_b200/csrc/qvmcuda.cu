@@ -275,6 +275,10 @@ qv::CompileOptions make_options(const qvmcuda_state* s, uint32_t flags) {
     opt.absorb_swaps = (flags & QVMCUDA_ABSORB_SWAPS) != 0;
     static const int forced_reg_bits = getenv("QVMCUDA_REG_BITS") ? atoi(getenv("QVMCUDA_REG_BITS")) : 0;   // profiling knob: 3 or 4
     if (forced_reg_bits == 3 || forced_reg_bits == 4) opt.reg_bits = forced_reg_bits;
+    static const int euler = getenv("QVMCUDA_EULER") ? atoi(getenv("QVMCUDA_EULER")) : 0;     // 1 always, 0 never, -1 cost model
+    opt.euler_split = euler;
+    static const int fuse_mats = getenv("QVMCUDA_FUSE_MATRICES") ? atoi(getenv("QVMCUDA_FUSE_MATRICES")) : 1;
+    opt.fuse_matrices = fuse_mats != 0;
     if (s) {
         opt.rank = s->rank;
         opt.n_local_bits = s->n_bits;
@@ -648,6 +652,33 @@ int qvmcuda_tape_step_flags(qvmcuda_tape* t, int step, uint32_t* flags) {
     if (step < 0 || step >= (int)t->tape.steps.size()) return fail("step out of range");
     const qv::Step& st = t->tape.steps[step];
     *flags = (st.uses_peers ? QVMCUDA_STEP_PEER : 0u) | (st.is_remap ? QVMCUDA_STEP_REMAP : 0u);
+    return 0;
+}
+
+int qvmcuda_tape_step_info(qvmcuda_tape* t, int step, int64_t info[8]) {
+    if (!t || !info) return fail("null argument");
+    if (step < 0 || step >= (int)t->tape.steps.size()) return fail("step out of range");
+    const qv::Step& st = t->tape.steps[step];
+    std::memset(info, 0, 8 * sizeof(int64_t));
+    info[0] = (st.uses_peers ? QVMCUDA_STEP_PEER : 0u) | (st.is_remap ? QVMCUDA_STEP_REMAP : 0u);
+    info[1] = (int64_t)st.kind;
+    info[2] = st.n_gates;
+    if (st.kind == qv::Step::REMAP) info[3] = st.remap.n_pairs;
+    if (st.kind == qv::Step::TILE) {
+        QvPassHeader h;
+        std::memcpy(&h, st.blob.data(), sizeof(h));
+        info[4] = h.n_uops - h.n_rounds;
+        info[5] = h.n_rounds;
+        if (h.pull) info[3] = h.pull_remap.n_pairs;
+        else if (h.uses_peers) {      // in-place exchange: rank bits inside the tile
+            int sbits = 0;
+            for (uint32_t k = 0; k < h.n_tile_segs; k++)
+                for (uint32_t b = 0; b < h.tile_segs[k].len; b++)
+                    if ((uint32_t)h.tile_segs[k].dst + b >= h.n_local_bits) sbits++;
+            info[3] = sbits;
+            info[6] = 1;
+        }
+    }
     return 0;
 }
 

@@ -79,6 +79,11 @@ class CudaShardEngine:
         self.L.check(self.L.lib().qvmcuda_tape_step_flags(tape, i, C.byref(f)))
         return f.value
 
+    def step_info(self, tape, i) -> np.ndarray:
+        a = np.zeros(8, dtype=np.int64)
+        self.L.check(self.L.lib().qvmcuda_tape_step_info(tape, i, self.L.ptr(a)))
+        return a
+
     def run_step(self, tape, i): self.L.check(self.L.lib().qvmcuda_tape_run_step(self.vec.handle, tape, i))
     def commit(self, tape): self.L.check(self.L.lib().qvmcuda_tape_commit(self.vec.handle, tape))
     def free_tape(self, tape): self.L.lib().qvmcuda_tape_destroy(tape)
@@ -118,6 +123,10 @@ class ShardedState:
         self.engine = engine_factory()
         self.peer_steps = 0
         self.steps = 0
+        # NVLink accounting of the exchange passes (bench: fraction of the NVLink roofline): seconds spent in passes that
+        # read peer shards and the bytes this rank pulled over NVLink in them
+        self.peer_seconds = 0.0
+        self.peer_bytes = 0.0
         self.set_zero_state()
 
     # ---- plumbing -------------------------------------------------------------------------------
@@ -156,13 +165,23 @@ class ShardedState:
                     self._barrier()       # every shard must be complete before anyone reads it remotely
                 if trace:
                     self.engine.synchronize()
-                    t0 = time.perf_counter()
+                if peer or trace:
+                    t0 = time.perf_counter()      # the stream is idle here (barrier / synchronize above)
                 self.engine.run_step(tape, i)
                 if trace:
                     self.engine.synchronize()
                     print(f"[dist] step {i}: {'REMAP' if flags & STEP_REMAP else 'PEER' if peer else 'LOCAL'} "
                           f"{1e3 * (time.perf_counter() - t0):.2f} ms", flush=True)
                 if peer:
+                    self.engine.synchronize()
+                    self.peer_seconds += time.perf_counter() - t0
+                    info = self.engine.step_info(tape, i) if hasattr(self.engine, "step_info") else None
+                    if info is not None:
+                        shard_bytes = 16.0 * (1 << self.n_local)
+                        frac = 1.0 - 2.0 ** (-int(info[3]))
+                        # a pull pass reads (1 - 2^-pairs) of the new shard from peers; an in-place pass pulls that
+                        # share of its tiles and pushes it back (counted once: ingress)
+                        self.peer_bytes += shard_bytes * frac
                     self._barrier()       # remote writes must have landed before local work resumes
                     self.peer_steps += 1
                 self.steps += 1
@@ -278,29 +297,87 @@ def _stop_clock_sampler(sampler):
         return None
 
 
-def _sharded_roofline(local_qubits: int, step_seconds: float, passes_per_step: float, peer_passes_per_step: float):
-    """Per-GPU figure for the sharded run: every pass reads and writes the rank's whole shard (32 B per amplitude,
-    SURVEY 8d), so achieved = 32 * 2^local_qubits * passes / step time.  Pull passes are bounded by NVLink ingress,
-    not by HBM: their count is reported beside it."""
+def _sharded_roofline(local_qubits: int, step_seconds: float, passes_per_step: float, peer_passes_per_step: float,
+                      peer_seconds_per_step: float, peer_bytes_per_step: float):
+    """Per-GPU figures for the sharded run.  HBM: every pass reads and writes the rank's whole shard (32 B per amplitude,
+    SURVEY 8d), so achieved = 32 * 2^local_qubits * passes / step time.  NVLink: the exchange passes pull
+    (1 - 2^-pairs) of the shard from peer memory; their ingress rate is set against the 900 GB/s per direction of NVLink 5."""
     try:
         peaks = _main_attr("measured_peaks")
         peak, src = peaks() if peaks is not None else (6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)")
+        traffic_fn = _main_attr("measured_traffic")
+        traffic = traffic_fn() if traffic_fn is not None else {}
         bytes_per_pass = 32.0 * float(1 << local_qubits)
         achieved = bytes_per_pass * passes_per_step / step_seconds / 1e9 if step_seconds > 0 else None
+        ratio = traffic.get("fused_pass_dram_bytes", 0) / traffic.get("algorithmic_bytes", 1) if traffic else 0
+        nv = None
+        if peer_seconds_per_step > 0:
+            gbs = peer_bytes_per_step / peer_seconds_per_step / 1e9
+            nv = {"bound": "nvlink", "achieved": gbs, "peak": 900.0, "unit": "GB/s", "frac": gbs / 900.0,
+                  "bytes_pulled_per_gpu_per_step": peer_bytes_per_step, "exchange_ms_per_step": 1e3 * peer_seconds_per_step,
+                  "exchange_passes_per_step": peer_passes_per_step,
+                  "peak_source": "NVLink 5: 900 GB/s per direction per GPU (B200_PROFILING.md)",
+                  "what": "ingress of the passes that load through a qubit remap from peer shards while applying their gates"}
         return {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                "frac": (achieved / peak) if achieved else None, "traffic": None,
-                "kernel": "qv_tile_kernel per GPU, average over the passes of a step (pull passes are NVLink-ingress-bound)",
+                "frac": (achieved / peak) if achieved else None,
+                "traffic": (bytes_per_pass * ratio) if ratio else None,
+                "traffic_source": (traffic.get("source", "") + "; DRAM bytes per pass scale with the shard") if ratio else None,
+                "kernel": "compiled gate passes (qvj_kernel) + qv_tile_kernel per GPU, average over the passes of a step "
+                          "(exchange passes are NVLink-ingress-bound, see nvlink)",
                 "peak_source": src, "bytes_per_launch": bytes_per_pass, "launches_per_step": passes_per_step,
-                "pull_passes_per_step": peer_passes_per_step}
+                "nvlink": nv}
     except Exception:
         return None
 
 
+def sharded_parity_check(dist_mod, rank: int, world: int, device: int, n_small: int = 20) -> dict:
+    """A small instance of the SAME sharded code path on the SAME ranks, checked against the CPU oracle before anything
+    is timed: amplitudes within the north-star tolerance, sampled indices bit-exact, in both exchange modes (fused pull
+    remaps into an alternate buffer / in-place peer passes)."""
+    from . import circuits
+    out = {"qubits": n_small, "tolerance": "1e-12 rel / 1e-14 abs, sampler indices identical", "modes": {}}
+    rng = np.random.default_rng(12345)
+    psi = rng.standard_normal(1 << n_small) + 1j * rng.standard_normal(1 << n_small)
+    psi = np.ascontiguousarray(psi / np.linalg.norm(psi))
+    circ = circuits.qft_circuit(range(n_small)) + circuits.random_layer_circuit(n_small, 2, 3)
+    ref = None
+    u = np.random.default_rng(2024).random(2000)
+    ok_all = True
+    for mode in ("pull", "inplace"):
+        if mode == "inplace":
+            os.environ["QVM_REMAP_INPLACE"] = "1"
+        try:
+            st = ShardedState(n_small, dist_mod, device=device)
+            st.scatter_logical(psi)
+            st.apply_gates(circ, fuse=True)
+            got = st.gather_logical()
+            phys = st.gather_physical()
+            idx = st.sample_physical(u, False)
+            res = {"exchange_passes": st.peer_steps}
+            if rank == 0:
+                from oracle import oracle as O      # the checker, not the thing measured
+                if ref is None:
+                    ref = psi.copy()
+                    for m, q in circ:
+                        O.apply_matrix(ref, m, q)
+                err = np.abs(got - ref)
+                res["max_abs_err"] = float(err.max())
+                res["amplitudes_ok"] = bool((err <= 1e-14 + 1e-12 * np.abs(ref)).all())
+                res["sampler_bit_exact"] = bool((idx == O.sample_tree_sharded(phys, world, u, False)).all())
+                ok_all = ok_all and res["amplitudes_ok"] and res["sampler_bit_exact"]
+            st.close()
+            out["modes"][mode] = res
+        finally:
+            os.environ.pop("QVM_REMAP_INPLACE", None)
+    out["ok"] = bool(ok_all)
+    return out
+
 
 def bench_sharded(args, rank: int, world: int, local_rank: int):
-    """Weak scaling: every rank keeps a 2^args.qubits shard; the circuit is the QFT on
-    args.qubits + log2(world) qubits.  value = 30-qubit-equivalent gates/s = gates * 2^(n - args.qubits) / s,
-    i.e. amplitude updates per second divided by 2^args.qubits, so N = 1 is the plain gates/s."""
+    """Weak scaling: every rank keeps a 2^L shard (L = args.local_qubits, default 32 = 64 GiB: 8 GPUs hold the 35-qubit
+    state BASELINE.json names); the circuit is the QFT on L + log2(world) qubits.
+    value = 30-qubit-equivalent gates/s = gates * 2^(n - 30) / s (amplitude updates per second / 2^30), so the series
+    continues the N = 1 line (plain gates/s at 30 qubits)."""
     import torch
     import torch.distributed as dist
 
@@ -309,59 +386,124 @@ def bench_sharded(args, rank: int, world: int, local_rank: int):
     torch.cuda.set_device(local_rank)
     dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     g = _log2(world)
-    n = args.qubits + g
+    L = args.local_qubits
+    n = L + g
+    parity = None
+    if not args.no_parity_check:
+        parity = sharded_parity_check(dist, rank, world, local_rank)
     st = ShardedState(n, dist, device=local_rank)
-    if getattr(args, "workload", "qft") == "random":
-        gates = circuits.random_layer_circuit(n, args.layers, seed=0)
-        wl = f"random 1q(RZ.RY.RZ)/CZ circuit, {args.layers} layers, {n} qubits (SURVEY 8d C5)"
-    else:
-        gates = circuits.qft_circuit(range(n))
-        wl = f"qft-{n}"
+    stream = torch.cuda.Stream()
+    st.engine.vec.set_stream(stream.cuda_stream)
+    gates = circuits.qft_circuit(range(n))
+    wl = f"qft-{n}"
 
     def step():
         st.apply_gates(gates, fuse=True, absorb_swaps=False)
 
-    for _ in range(args.warmup):
-        step()
+    def timed(fn, steps):
+        """CUDA events on the stream the kernels run on, bracketed by barrier + synchronize; max over ranks."""
+        st._barrier()
+        torch.cuda.synchronize()
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ev0.record(stream)
+        for _ in range(steps):
+            fn()
+        ev1.record(stream)
+        st._barrier()
+        torch.cuda.synchronize()
+        t = torch.tensor([ev0.elapsed_time(ev1) / 1e3], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    j0 = _lib.jit_stats()
+    t_prep = time.perf_counter()
+    step()                                  # untimed: schedules, compiles the passes (pass compiler), first touch
     st._barrier()
-    torch.cuda.synchronize()
+    prep_s = time.perf_counter() - t_prep
+    for _ in range(max(0, args.warmup - 1)):
+        step()
     l0 = _lib.launch_count()
-    p0, s0 = st.peer_steps, st.steps
+    p0, s0, ps0, pb0 = st.peer_steps, st.steps, st.peer_seconds, st.peer_bytes
     sampler = _start_clock_sampler(rank, local_rank)     # nvidia-smi clocks during the timed region (rank 0)
-    t0 = time.perf_counter()
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    ev0.record()
-    for _ in range(args.steps):
-        step()
-    st._barrier()
-    ev1.record()
-    torch.cuda.synchronize()
-    dt_local = time.perf_counter() - t0
-    t = torch.tensor([dt_local], device="cuda", dtype=torch.float64)
-    dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    dt = float(t.item())
+    dt = timed(step, args.steps)
     launches = _lib.launch_count() - l0
     clocks = _stop_clock_sampler(sampler)
+    passes_per_step = (st.steps - s0) / args.steps
+    peer_per_step = (st.peer_steps - p0) / args.steps
+    peer_s = (st.peer_seconds - ps0) / args.steps
+    peer_b = (st.peer_bytes - pb0) / args.steps
     norm2 = st.norm2()
+
+    # ---- e2e: through the public API with host buffers every step: reset, gate arrays -> schedule -> device, run,
+    #      1000-shot sample and one probability back on the host
+    u = np.random.default_rng(2024).random(1000)
+
+    def e2e_step():
+        st.set_zero_state()
+        st.apply_gates(gates, fuse=True)
+        st.sample(u, strict=False)
+        st.prob_excited(0)
+
+    e2e_step()
+    e2e_steps = max(1, min(args.steps, 3))
+    st._barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        e2e_step()
+    st._barrier()
+    te = torch.tensor([time.perf_counter() - t0], device="cuda", dtype=torch.float64)
+    dist.all_reduce(te, op=dist.ReduceOp.MAX)
+    e2e_dt = float(te.item())
+    ks, qf, mf = _lib.flatten_gates(gates)
+    h2d = ks.nbytes + qf.nbytes + mf.nbytes + u.nbytes
+    d2h = u.size * 8 + 8 * 2       # sampled indices, the shard total for the sampler prefix and one probability partial
+
+    # ---- BASELINE configs[4]: random 1q (RZ.RY.RZ) / CZ layers on all n qubits, sharded (SURVEY 8d C5)
+    c5 = None
+    if args.c5_layers > 0:
+        rgates = circuits.random_layer_circuit(n, args.c5_layers, seed=0)
+
+        def rstep():
+            st.apply_gates(rgates, fuse=True)
+
+        st.set_zero_state()
+        rstep()                             # untimed: compiles the passes
+        p1, s1, ps1, pb1 = st.peer_steps, st.steps, st.peer_seconds, st.peer_bytes
+        rdt = timed(rstep, 1)
+        rp = st.steps - s1
+        c5 = {"workload": f"random 1q(RZ.RY.RZ)/CZ circuit, {args.c5_layers} layers on {n} qubits, seed 0", "gates": len(rgates),
+              "seconds_per_circuit": rdt, "gates_per_s": len(rgates) / rdt, "value_30q_equivalent": len(rgates) * 2.0 ** (n - 30) / rdt,
+              "hbm_passes": rp, "exchange_passes": st.peer_steps - p1,
+              "roofline": _sharded_roofline(L, rdt, rp, st.peer_steps - p1, st.peer_seconds - ps1, st.peer_bytes - pb1),
+              "norm2": st.norm2()}
+    j1 = _lib.jit_stats()
     if rank == 0:
-        scale = 2.0 ** (n - args.qubits)
+        scale = 2.0 ** (n - 30)
         value = len(gates) * args.steps * scale / dt
-        peer_per_step = (st.peer_steps - p0) / args.steps
         print(json.dumps({
             "metric": "gates/s", "value": value, "unit": "gates/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": f"{wl} sharded over {world} GPUs ({args.qubits} local qubits = {16 << args.qubits} B per GPU), gate fusion on",
-                       "value_definition": f"gates/s x 2^(n-{args.qubits}): amplitude updates per second / 2^{args.qubits}; equals plain gates/s at N=1",
-                       "raw_gates_per_s": len(gates) * args.steps / dt,
-                       "hbm_passes_per_step": (st.steps - s0) / args.steps, "peer_passes_per_step": peer_per_step,
-                       "exchange": "tile kernel P2P loads/stores over NVLink (IPC-mapped shards); torch.distributed barriers only",
-                       "timing": "host wall clock bracketed by barrier + cudaDeviceSynchronize, max over ranks"},
-            "roofline": _sharded_roofline(args.qubits, dt / args.steps, (st.steps - s0) / args.steps, peer_per_step),
+            "config": {"workload": f"{wl} (examples/qft.lisp qft-circuit, {len(gates)} gates) sharded over {world} GPUs: {n} qubits, "
+                                   f"{L} local qubits = {16 << L} B per GPU, gate fusion on",
+                       "value_definition": "gates/s x 2^(n-30): amplitude updates per second / 2^30 (30-qubit-equivalent gates/s); "
+                                           "equals plain gates/s on the 30-qubit N=1 line",
+                       "raw_gates_per_s": len(gates) * args.steps / dt, "circuit_seconds": dt / args.steps,
+                       "hbm_passes_per_step": passes_per_step, "exchange_passes_per_step": peer_per_step,
+                       "exchange": "tile kernel P2P loads over NVLink (IPC-mapped shards), remap fused into the gate pass; "
+                                   "torch.distributed (NCCL) for barriers and scalars only",
+                       "l2_policy": "shard (64 GiB) is far larger than the 126 MB L2; no flush needed",
+                       "timing": "CUDA events on the kernels' stream, bracketed by barrier + cudaDeviceSynchronize, max over ranks",
+                       "pass_compiler": {"prepare_seconds": prep_s, "kernels_compiled": j1["compiled"] - j0["compiled"],
+                                         "disk_cache_hits": j1["disk_hits"] - j0["disk_hits"], "compile_ms_total": j1["compile_ms"] - j0["compile_ms"]}},
+            "roofline": _sharded_roofline(L, dt / args.steps, passes_per_step, peer_per_step, peer_s, peer_b),
+            "parity_check": parity, "c5_random": c5,
             "clocks": clocks,
             "gpu_launches": int(launches), "norm2": norm2,
-            "e2e": {"value": value, "unit": "gates/s", "h2d_bytes_per_step": int(sum(np.asarray(m).nbytes for m, _ in gates)),
-                    "d2h_bytes_per_step": 0, "what": "apply_gates from host gate arrays (scheduled, uploaded and run inside the timed region)"},
+            "e2e": {"value": len(gates) * e2e_steps * scale / e2e_dt, "unit": "gates/s", "h2d_bytes_per_step": int(h2d),
+                    "d2h_bytes_per_step": int(d2h), "steps": e2e_steps,
+                    "what": "reset + apply_gates(host gate arrays: scheduled, uploaded and run) + 1000-shot sample + prob_excited, "
+                            "host wall clock, max over ranks"},
         }))
     st.close()
     dist.destroy_process_group()
