@@ -136,6 +136,13 @@ int qvmcuda_set_basis_state(qvmcuda_state *s, uint64_t basis);
  * operator sum_j K_j (x) conj(K_j) on the 2k bits (qubits, qubits+n). */
 int qvmcuda_density_apply_kraus(qvmcuda_state *s, int n_qubits, int k, const int32_t *qubits, int m,
                                 const double *kraus, uint32_t flags);
+/* A RUN of such operators in one call (one CFFI crossing per stretch of gate transitions of the DENSITY-QVM,
+ * src/density-qvm.lisp:125-137): operator i acts on ks[i] qubits (nat-tuple order, concatenated in QUBITS) with ms[i] Kraus
+ * matrices (2*4^ks[i] doubles each, concatenated in KRAUS).  The whole run is scheduled together: U, U* and the channel
+ * that follows them on the same qubit become one 4x4 on the (column, row) bit pair, and operators on different qubits share
+ * HBM passes (QVMCUDA_FUSE). */
+int qvmcuda_density_apply_ops(qvmcuda_state *s, int n_qubits, int n_ops, const int32_t *ks, const int32_t *qubits,
+                              const int32_t *ms, const double *kraus, uint32_t flags);
 /* GET-EXCITED-STATE-PROBABILITY (density-matrix-state) src/measurement.lisp:77-85 */
 int qvmcuda_density_prob_excited(qvmcuda_state *s, int n_qubits, int qubit, double *p);
 /* FORCE-MEASUREMENT (density-matrix-state) src/measurement.lisp:43-68 */

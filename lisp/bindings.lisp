@@ -37,6 +37,8 @@
   (matrices :pointer) (flags :uint32))
 (defcuda density-apply-kraus "qvmcuda_density_apply_kraus" (state :pointer) (n-qubits :int) (k :int)
   (qubits :pointer) (m :int) (kraus :pointer) (flags :uint32))
+(defcuda density-apply-ops "qvmcuda_density_apply_ops" (state :pointer) (n-qubits :int) (n-ops :int) (ks :pointer)
+  (qubits :pointer) (ms :pointer) (kraus :pointer) (flags :uint32))
 ;;; measurement protocol
 (defcuda prob-excited "qvmcuda_prob_excited" (state :pointer) (qubit :int) (p :pointer))
 (defcuda prob-ground "qvmcuda_prob_ground" (state :pointer) (qubit :int) (p :pointer))

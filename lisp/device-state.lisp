@@ -35,6 +35,10 @@ vector itself is created by MAKE-DEVICE-PURE-STATE, which owns the handle."
    (tape :initform nil :accessor gate-tape
          :documentation "Pending gates (matrix . qubits), flushed in ONE qvmcuda_apply_gates call.")))
 
+(defgeneric flush-gate-tape (state)
+  (:documentation "Send the pending transitions of STATE to the GPU in one call (methods in operators.lisp).  Qubit lists go
+out in NAT-TUPLE order (src/utilities.lisp:43-51), i.e. reversed Quil argument order."))
+
 (defclass device-pure-state (device-state-mixin qvm::pure-state) ())
 (defclass device-density-matrix-state (device-state-mixin qvm::density-matrix-state) ())
 
@@ -121,29 +125,63 @@ vector itself is created by MAKE-DEVICE-PURE-STATE, which owns the handle."
         (host-newer-p state) nil))
 
 ;;; ---- machines ---------------------------------------------------------------------------------
+;;;
+;;; The machines are SUBCLASSES of the reference's: every method of the run loop (LOAD-PROGRAM, RUN, TRANSITION, classical
+;;; memory; src/execution.lisp, src/transition.lisp) is inherited unchanged, and the protocols whose default methods would
+;;; generate host code -- COMPILE-LOADED-PROGRAM / COMPILE-INSTRUCTION -- can be specialised on them (compile.lisp), the way
+;;; the reference itself opts DENSITY-QVM out (src/density-qvm.lisp:183-190).
+
+(defclass cuda-pure-state-qvm (qvm:pure-state-qvm) ()
+  (:documentation "PURE-STATE-QVM (src/qvm.lisp:114-148) whose STATE is a DEVICE-PURE-STATE."))
+
+(defclass cuda-density-qvm (qvm:density-qvm) ()
+  (:documentation "DENSITY-QVM (src/density-qvm.lisp:33-71) whose STATE is a DEVICE-DENSITY-MATRIX-STATE."))
+
+(defvar *cuda-mirror-refresh-limit* 26
+  "RUN refreshes the host mirror afterwards only for states of at most this many qubits (callers of the reference's tests
+hold the AMPLITUDES vector across runs, tests/gate-tests.lisp:91-103).  Larger states are downloaded lazily, when
+QVM::AMPLITUDES / STATE-ELEMENTS is actually called: 16 GiB at 30 qubits should not cross PCIe after every RUN.")
 
 (defun make-cuda-qvm (num-qubits &rest args)
   "QVM:MAKE-QVM (src/qvm.lisp:150-164) with a device-resident state; everything above the state
 (LOAD-PROGRAM, RUN, TRANSITION, classical memory) is the unchanged reference code."
-  (apply #'make-instance 'qvm:pure-state-qvm
+  (apply #'make-instance 'cuda-pure-state-qvm
          :number-of-qubits num-qubits
          :state (make-device-pure-state num-qubits)
          args))
 
 (defun make-cuda-density-qvm (num-qubits &rest args)
-  (apply #'make-instance 'qvm:density-qvm
+  "QVM::MAKE-DENSITY-QVM (src/density-qvm.lisp:52-71) with vec(rho) on the device."
+  (apply #'make-instance 'cuda-density-qvm
          :number-of-qubits num-qubits
          :state (make-device-density-matrix-state num-qubits)
          args))
 
-(defmethod qvm:run :before ((qvm qvm:pure-state-qvm))
-  (let ((state (qvm::state qvm)))
-    (when (typep state 'device-state-mixin)
-      (sync-to-device state))))
+(defun %state-index-bits (state)
+  (etypecase state
+    (device-pure-state (qvm::num-qubits state))
+    (device-density-matrix-state (* 2 (qvm::num-qubits state)))))
 
-(defmethod qvm:run :after ((qvm qvm:pure-state-qvm))
-  ;; tests hold the AMPLITUDES vector across runs (tests/gate-tests.lisp:91-103): refresh the mirror
+(defun %before-run (qvm)
+  ;; the host may have written into the mirror since it was handed out
+  (sync-to-device (qvm::state qvm)))
+
+(defun %after-run (qvm)
+  ;; all queued transitions reach the device; the mirror follows only for small states (see *CUDA-MIRROR-REFRESH-LIMIT*)
   (let ((state (qvm::state qvm)))
-    (when (and (typep state 'device-state-mixin) *cuda-lazy-mirror*)
-      (flush-gate-tape state)
+    (flush-gate-tape state)
+    (when (and *cuda-lazy-mirror*
+               (<= (%state-index-bits state) *cuda-mirror-refresh-limit*))
       (sync-to-host state))))
+
+;;; Specialised on OUR classes only: an :AFTER method on BASE-QVM would replace the reference's own
+;;; (RUN :AFTER BASE-QVM), src/execution.lisp:39-44.
+(defmethod qvm:run :before ((qvm cuda-pure-state-qvm)) (%before-run qvm))
+(defmethod qvm:run :before ((qvm cuda-density-qvm)) (%before-run qvm))
+(defmethod qvm:run :after ((qvm cuda-pure-state-qvm)) (%after-run qvm))
+(defmethod qvm:run :after ((qvm cuda-density-qvm)) (%after-run qvm))
+
+;;; REQUIRES-SWAPPING-AMPS-P (src/state-representation.lisp:137-146) compares AMPLITUDES with ORIGINAL-AMPLITUDES; the
+;;; stochastic-Kraus path that swaps them is not routed to the device by this shim (SURVEY section 8f #2 is served by the
+;;; Python twin), so a device state never needs the swap.
+(defmethod qvm::requires-swapping-amps-p ((state device-state-mixin)) nil)

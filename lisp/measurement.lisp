@@ -9,6 +9,7 @@
   (call-returning-double #'prob-excited (device-handle state) qubit))
 
 (defmethod qvm::get-excited-state-probability ((state device-density-matrix-state) qubit)
+  (flush-gate-tape state)
   (call-returning-double #'density-prob-excited (device-handle state) (qvm::num-qubits state) qubit))
 
 (defmethod qvm::force-measurement (measured-value qubit (state device-pure-state) excited-probability)
@@ -24,6 +25,7 @@
 (defmethod qvm::force-measurement (measured-value qubit (state device-density-matrix-state)
                                    excited-probability)
   ;; src/measurement.lisp:43-68: rescale by 1/p, not 1/sqrt(p)
+  (flush-gate-tape state)
   (let ((inv-norm (if (= 1 measured-value)
                       (/ excited-probability)
                       (/ (- (qvm:flonum 1) excited-probability)))))
@@ -48,6 +50,7 @@
 (defmethod qvm::apply-measure-discard-to-state (qvm (state device-density-matrix-state)
                                                 (instr quil:measure-discard))
   ;; src/measurement.lisp:111-120
+  (flush-gate-tape state)
   (density-measure-discard (device-handle state) (qvm::num-qubits state)
                            (quil:qubit-index (quil:measurement-qubit instr)))
   (setf (device-newer-p state) t)
@@ -87,4 +90,15 @@ DEVICE-PURE-STATE as a vector of double-floats, reduced to 8 bytes per basis sta
          (probs (make-array n :element-type 'double-float)))
     (cffi:with-pointer-to-vector-data (p probs)
       (probabilities (device-handle state) p 0 n))
+    probs))
+
+(defun density-measurement-probabilities/cuda (state)
+  "DENSITY-MATRIX-STATE-MEASUREMENT-PROBABILITIES (src/state-representation.lisp:268-286; DENSITY-QVM-MEASUREMENT-PROBABILITIES,
+src/density-qvm.lisp:151-154) for a DEVICE-DENSITY-MATRIX-STATE: the real parts of the diagonal of rho, gathered on the device
+(2^n doubles cross PCIe instead of the 4^n complex entries of the mirror)."
+  (flush-gate-tape state)
+  (let* ((dim (expt 2 (qvm::num-qubits state)))
+         (probs (make-array dim :element-type 'double-float)))
+    (cffi:with-pointer-to-vector-data (p probs)
+      (density-diag-probs (device-handle state) (qvm::num-qubits state) p))
     probs))

@@ -9,9 +9,13 @@
            #:make-device-density-matrix-state
            #:make-cuda-qvm
            #:make-cuda-density-qvm
+           #:cuda-pure-state-qvm
+           #:cuda-density-qvm
+           #:*cuda-mirror-refresh-limit*
            #:*cuda-device*
            #:*cuda-lazy-mirror*
            #:flush-gate-tape
            #:sample-wavefunction-multiple-times/cuda
            #:pure-state-expectation/cuda
-           #:probabilities/cuda))
+           #:probabilities/cuda
+           #:density-measurement-probabilities/cuda))

@@ -13,4 +13,5 @@
                (:file "bindings")
                (:file "device-state")
                (:file "operators")
+               (:file "compile")
                (:file "measurement")))

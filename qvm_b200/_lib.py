@@ -59,6 +59,7 @@ _SIGS = {
     "qvmcuda_sample_total": [C.c_void_p, C.POINTER(C.c_double)],
     "qvmcuda_sample_shard": [C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p, C.c_int, C.c_double],
     "qvmcuda_density_apply_kraus": [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_uint32],
+    "qvmcuda_density_apply_ops": [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32],
     "qvmcuda_density_prob_excited": [C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_double)],
     "qvmcuda_density_collapse": [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_double],
     "qvmcuda_density_measure_discard": [C.c_void_p, C.c_int, C.c_int],

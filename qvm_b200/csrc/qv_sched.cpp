@@ -928,20 +928,20 @@ void build_rounds(BlobWriter& w, const std::vector<const Atom*>& atoms, const Ti
                 DiagFactor f;
                 for (int wq : a->dw) f.pos.push_back(lay.phys(wq));
                 f.diag = a->mat;
-                // (as soon as possible: diagonals commute with each other, so the factor moves back past diagonal groups
-                // as well and joins the EARLIEST group it can reach -- "phases before the rotations of this layer" and
-                // "phases after them" end up as two groups instead of one per rotation)
+                // Nearest group, not the earliest reachable one: merging "as soon as possible" (diagonals commute with each
+                // other) was measured on the 30-qubit QFT and LOST 4.5 ms per circuit (gpurun_out/r2c_bench.json vs
+                // r2a_bench_jit.json): it moves ladder phases away from the butterfly they fuse with.
                 int j = (int)rops.size() - 1;
-                int target = -1;
+                bool merged = false;
                 while (j >= 0) {
-                    if (rops[j].is_diag) target = j;
-                    else if ((rops[j].mix & a->touch) != 0) break;
+                    if (rops[j].is_diag) {
+                        rops[j].factors.push_back(f);
+                        rops[j].touch |= a->touch;
+                        merged = true;
+                        break;
+                    }
+                    if ((rops[j].mix & a->touch) != 0) break;
                     j--;
-                }
-                const bool merged = target >= 0;
-                if (merged) {
-                    rops[target].factors.push_back(f);
-                    rops[target].touch |= a->touch;
                 }
                 if (!merged) {
                     RoundOp ro;

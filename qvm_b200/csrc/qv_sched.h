@@ -37,7 +37,9 @@ struct CompileOptions {
     bool fuse_pull = true;       // with remap_pull: merge a pull remap into the tile pass that follows it
     bool relabel_global_swaps = true;   // sharded: an exact SWAP touching a rank bit only exchanges the two wires' physical bits
     bool fuse_matrices = true;   // with fuse: multiply neighbouring dense / diagonal atoms on the same <= 2 wires together on the host
-    int euler_split = -1;        // complex 1q unitaries as diag . real rotation . diag: 1 always, 0 never, -1 = whichever tape is cheaper
+    int euler_split = 0;         // complex 1q unitaries as diag . real rotation . diag: 1 always, 0 never, -1 = whichever tape the
+                                 // cost model prefers.  Off: measured slower on B200 (25-qubit random layers 6.3 vs 5.5 ms,
+                                 // gpurun_out/r2c_configs_euler*.jsonl) -- the extra table lookups cost more than the FP64 saved
     bool remap_pull = false;     // remaps as out-of-place pulls into the alternate buffer (needs 2x shard memory)
 };
 

@@ -985,15 +985,14 @@ int qvmcuda_sample_shard(qvmcuda_state* s, const double* uniforms, uint64_t n_sh
 }
 
 // ------------------------------------------------------------------ density matrix
-int qvmcuda_density_apply_kraus(qvmcuda_state* s, int n_qubits, int k, const int32_t* qubits, int m,
-                                const double* kraus, uint32_t flags) {
-    if (!s || !qubits || (m > 0 && !kraus)) return fail("null argument");
-    if (s->n_bits != 2 * n_qubits) return fail("state length is not 4^n_qubits");
+// Gates on the 2n index bits of vec(rho) for one operator rho <- sum_j K_j rho K_j^dagger on QUBITS (nat-tuple order).
+static int density_gates_for_op(int n_qubits, int k, const int32_t* qubits, int m, const double* kraus, std::vector<qv::Gate>& gates) {
     if (k < 1 || k > 8) return fail("kraus operator arity out of range (1..8)");
+    for (int j = 0; j < k; j++)
+        if (qubits[j] < 0 || qubits[j] >= n_qubits) return fail("qubit out of range");
     if (m == 0) return 0;
     const size_t d = (size_t)1 << k;
     const qv::cd* K = reinterpret_cast<const qv::cd*>(kraus);
-    std::vector<qv::Gate> gates;
     if (m == 1) {
         // single-kraus: conj(K) on the column bits, then K on the row bits (src/apply-gate.lisp:56-65)
         qv::Gate gc, gr;
@@ -1027,9 +1026,39 @@ int qvmcuda_density_apply_kraus(qvmcuda_state* s, int n_qubits, int k, const int
         for (int j = 0; j < k; j++) g.qubits.push_back(qubits[j] + n_qubits);
         gates.push_back(std::move(g));
     }
+    return 0;
+}
+
+int qvmcuda_density_apply_kraus(qvmcuda_state* s, int n_qubits, int k, const int32_t* qubits, int m,
+                                const double* kraus, uint32_t flags) {
+    if (!s || !qubits || (m > 0 && !kraus)) return fail("null argument");
+    if (s->n_bits != 2 * n_qubits) return fail("state length is not 4^n_qubits");
+    std::vector<qv::Gate> gates;
+    if (int rc = density_gates_for_op(n_qubits, k, qubits, m, kraus, gates)) return rc;
+    if (gates.empty()) return 0;
     std::lock_guard<std::mutex> lk(s->mu);
     DeviceGuard dg(s->device);
     return run_gates_locked(s, gates, flags | QVMCUDA_FUSE);
+}
+
+int qvmcuda_density_apply_ops(qvmcuda_state* s, int n_qubits, int n_ops, const int32_t* ks, const int32_t* qubits,
+                              const int32_t* ms, const double* kraus, uint32_t flags) {
+    if (!s || (n_ops > 0 && (!ks || !qubits || !ms || !kraus))) return fail("null argument");
+    if (n_ops < 0) return fail("negative operator count");
+    if (s->n_bits != 2 * n_qubits) return fail("state length is not 4^n_qubits");
+    std::vector<qv::Gate> gates;
+    size_t qo = 0, ko = 0;
+    for (int i = 0; i < n_ops; i++) {
+        if (ks[i] < 1 || ks[i] > 8) return fail("kraus operator arity out of range (1..8)");
+        if (ms[i] < 0) return fail("negative kraus count");
+        if (int rc = density_gates_for_op(n_qubits, ks[i], qubits + qo, ms[i], kraus + ko, gates)) return rc;
+        qo += (size_t)ks[i];
+        ko += (size_t)2 * ((size_t)1 << (2 * ks[i])) * (size_t)ms[i];
+    }
+    if (gates.empty()) return 0;
+    std::lock_guard<std::mutex> lk(s->mu);
+    DeviceGuard dg(s->device);
+    return run_gates_locked(s, gates, flags);
 }
 
 int qvmcuda_density_prob_excited(qvmcuda_state* s, int n_qubits, int qubit, double* p) {

@@ -126,6 +126,22 @@ class DeviceVector:
         L.check(L.lib().qvmcuda_sample(self.handle, L.ptr(u), u.size, L.ptr(out), 1 if strict else 0))
         return out
 
+    def density_apply_ops(self, n: int, ops, fuse: bool = True):
+        """A run of density operators in ONE library call (qvmcuda_density_apply_ops).
+        ops = [([K_0, ...] Kraus matrices, qubits in Quil argument order)]."""
+        if not ops:
+            return
+        ks = np.ascontiguousarray([len(q) for _, q in ops], dtype=np.int32)
+        ms = np.ascontiguousarray([len(k) for k, _ in ops], dtype=np.int32)
+        qf = np.ascontiguousarray([int(x) for _, q in ops for x in reversed(q)], dtype=np.int32)
+        kf = np.ascontiguousarray(np.concatenate([np.asarray(m, dtype=np.complex128).ravel() for k, _ in ops for m in k])).view(np.float64)
+        for k, q in ops:
+            for m in k:
+                if np.asarray(m).shape != (1 << len(q), 1 << len(q)):
+                    raise ValueError("Kraus matrix does not match its qubit count")
+        L.check(L.lib().qvmcuda_density_apply_ops(self.handle, n, len(ops), L.ptr(ks), L.ptr(qf), L.ptr(ms), L.ptr(kf),
+                                                  L.FUSE if fuse else 0))
+
     def sample_total(self) -> float:
         """This vector's probability mass in the sampler's own summation order (sharded sampling)."""
         t = C.c_double(0.0)
@@ -229,8 +245,9 @@ class DensityMatrixState:
         return self.vec.density_diag_probs(self.num_qubits)
 
     def apply_ops(self, ops, fuse: bool = True) -> None:
-        """A run of unitaries / Kraus channels in ONE library call (fused passes over vec(rho))."""
-        self.vec.apply_gates(density_gate_list(self.num_qubits, ops), fuse=fuse)
+        """A run of unitaries / Kraus channels in ONE library call (fused passes over vec(rho)), through the same
+        entry point the Lisp shim's gate tape flushes into (lisp/operators.lisp FLUSH-GATE-TAPE)."""
+        self.vec.density_apply_ops(self.num_qubits, [(list(g) if isinstance(g, (list, tuple)) else [g], q) for g, q in ops], fuse=fuse)
 
 
 def density_gate_list(n: int, ops):
@@ -254,9 +271,25 @@ def density_gate_list(n: int, ops):
     return out
 
 
-def apply_gate_to_state(gate, state, qubits: Sequence[int]) -> None:
-    """APPLY-GATE-TO-STATE (src/apply-gate.lisp:106-212).  GATE is a matrix, or a list of Kraus
-    matrices (a KRAUS-LIST superoperator).  QUBITS in Quil argument order."""
+class CompiledGateApplication:
+    """Stand-in for COMPILED-MATRIX / COMPILED-INLINED-MATRIX / COMPILED-PERMUTATION-GATE-APPLICATION
+    (src/compile-gate.lisp:363-409): an instruction that carries its matrix and its own arguments.  The reference's
+    TRANSITION hands such an instruction to APPLY-GATE-TO-STATE with QUBITS = NIL (src/transition.lisp:182-186)."""
+
+    def __init__(self, matrix, qubits: Sequence[int]):
+        self.matrix = np.ascontiguousarray(matrix, dtype=np.complex128)
+        self.qubits = tuple(int(q) for q in qubits)
+
+
+def apply_gate_to_state(gate, state, qubits: Optional[Sequence[int]]) -> None:
+    """APPLY-GATE-TO-STATE (src/apply-gate.lisp:106-212).  GATE is a matrix, a list of Kraus matrices (a KRAUS-LIST
+    superoperator) or a compiled gate application; QUBITS in Quil argument order, or None for a compiled gate
+    application (the qubits then come from the instruction, as in lisp/operators.lisp)."""
+    if isinstance(gate, CompiledGateApplication):
+        qubits = tuple(qubits) if qubits else gate.qubits
+        gate = gate.matrix
+    if qubits is None:
+        raise ValueError("only a compiled gate application carries its own qubits")
     if isinstance(state, PureState):
         if isinstance(gate, (list, tuple)):
             raise ValueError("a Kraus list on a pure state needs a uniform draw: use evolve_pure_state_stochastically")
@@ -446,6 +479,8 @@ class DensityQVM(BaseQVM):
         self.state = DensityMatrixState(num_qubits, device)
         self.noisy_gate_definitions: Dict[Tuple[str, Tuple[int, ...]], list] = {}
         self.readout_povms: Dict[int, Tuple[float, float, float, float]] = {}
+        self.fuse_gates = True
+        self._tape: list = []
 
     @property
     def amplitudes(self) -> np.ndarray:
@@ -492,17 +527,27 @@ class DensityQVM(BaseQVM):
             return 0 if r <= p00 else 1
         return 0 if r <= p01 else 1
 
+    def flush_gate_tape(self):
+        """What the Lisp shim does when something needs rho (lisp/operators.lisp FLUSH-GATE-TAPE): all pending gate /
+        channel transitions (src/density-qvm.lisp:125-137) go to the device in ONE qvmcuda_density_apply_ops call."""
+        if self._tape:
+            self.state.vec.density_apply_ops(self.number_of_qubits(), self._tape, fuse=self.fuse_gates)
+            self._tape = []
+
     def run(self):
         prog = self.program
         n = self.number_of_qubits()
+        self._tape = []
         for x in prog.instructions:
             if isinstance(x, GateApp):
                 key = (x.name, tuple(x.qubits))
                 if key in self.noisy_gate_definitions and not x.modifiers:
-                    self.state.vec.density_apply_kraus(n, self.noisy_gate_definitions[key], x.qubits)
+                    self._tape.append((self.noisy_gate_definitions[key], tuple(x.qubits)))
                 else:
-                    self.state.vec.density_apply_kraus(n, [prog.gate_matrix(x)], x.qubits)
-            elif isinstance(x, Measure):
+                    self._tape.append(([prog.gate_matrix(x)], tuple(x.qubits)))
+                continue
+            self.flush_gate_tape()
+            if isinstance(x, Measure):
                 if x.target is None:
                     self.state.vec.density_measure_discard(n, x.qubit)
                 else:
@@ -514,6 +559,7 @@ class DensityQVM(BaseQVM):
                     raise NotImplementedError("RESET q on a density matrix is outside the hot path")
             elif isinstance(x, Halt):
                 break
+        self.flush_gate_tape()
         return self
 
 

@@ -1,0 +1,157 @@
+"""GPU tests of the boundary in the order the reference's call stacks use it:
+compiled-mode transitions (APPLY-GATE-TO-STATE with QUBITS = NIL, compiled MEASURE), the density machine's gate tape,
+NAIVE-MEASURE-ALL on rho, and the remaining BASELINE.json configurations at sizes the oracle can follow."""
+import numpy as np
+import pytest
+
+import helpers as H
+from qvm_b200 import circuits as CC
+from qvm_b200 import gates as G
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def Q():
+    from qvm_b200 import qvm
+    return qvm
+
+
+@pytest.fixture(scope="module")
+def O():
+    from oracle import oracle
+    return oracle
+
+
+def test_compiled_mode_call_stack(Q, O):
+    """src/transition.lisp:182-194 on a device state: TRANSITION hands a compiled gate application to
+    APPLY-GATE-TO-STATE with QUBITS = NIL -- the qubits come from the instruction (lisp/operators.lisp) -- and the
+    compiled MEASURE decides with p0 and `r < p0` (src/compile-gate.lisp:231-254).  Nothing runs on a host copy."""
+    n = 10
+    rng = np.random.default_rng(4)
+    circ = CC.qft_circuit(range(n)) + H.random_circuit(n, 30, rng)
+    psi = H.rand_state(n, 9)
+    state = Q.PureState(n)
+    state.vec.upload(psi)
+    program = [Q.CompiledGateApplication(m, q) for m, q in circ]      # COMPILE-LOADED-PROGRAM's output, stand-in
+    for instr in program:
+        Q.apply_gate_to_state(instr, state, None)                      # (apply-gate-to-state instr (state qvm) nil)
+    ref = H.run_oracle(psi.copy(), circ)
+    H.assert_close(state.vec.download(), ref)
+    with pytest.raises(ValueError):
+        Q.apply_gate_to_state(circ[0][0], state, None)                 # a bare matrix has no qubits of its own
+    # compiled MEASURE: same rule, same uniform as the oracle
+    q = 3
+    p0 = O.prob_ground(ref, q) if hasattr(O, "prob_ground") else 1.0 - O.prob_excited(ref, q)
+    assert abs(state.vec.prob_ground(q) - p0) < 1e-13
+    r = 0.41
+    bit = 0 if r < p0 else 1
+    inv = 1.0 / np.sqrt(p0) if bit == 0 else 1.0 / np.sqrt(1.0 - p0)
+    state.vec.collapse(q, bit, inv)
+    O.force_measurement(ref, q, bit, O.prob_excited(ref, q))
+    H.assert_close(state.vec.download(), ref)
+    state.vec.close()
+
+
+def test_density_measure_all_matches_oracle(Q, O):
+    """NAIVE-MEASURE-ALL on rho (src/measurement.lisp:153-162) with identical uniforms."""
+    n = 4
+    prog = "H 0\nCNOT 0 1\nRX(0.7) 2\nCNOT 2 3\nRY(1.1) 1"
+    for seed in range(6):
+        qvm = Q.DensityQVM(n, seed=seed)
+        qvm.set_noisy_gate("RX", (2,), G.depolarizing_kraus_map(0.2))
+        qvm.load_program(prog).run()
+        rho = O.zero_density(n)
+        for name, params, qubits in (("H", [], (0,)), ("CNOT", [], (0, 1))):
+            O.density_apply_unitary(rho, n, G.gate_matrix(name, params), qubits)
+        O.density_apply_kraus(rho, n, G.depolarizing_kraus_map(0.2), (2,))
+        O.density_apply_unitary(rho, n, G.gate_matrix("CNOT"), (2, 3))
+        O.density_apply_unitary(rho, n, G.gate_matrix("RY", [1.1]), (1,))
+        H.assert_close(qvm.amplitudes, rho)
+        uniforms = np.random.default_rng(1000 + seed).random(n)
+        it = iter(uniforms)
+        qvm.random = lambda: float(next(it))
+        bits = qvm.measure_all()
+        want = O.density_measure_all(rho, n, uniforms)
+        assert bits == want
+        H.assert_close(qvm.amplitudes, rho)
+        assert abs(np.trace(qvm.state.matrix_view()).real - 1.0) < 1e-12
+
+
+@pytest.mark.parametrize("n", [8, 9])
+def test_density_qaoa_with_two_qubit_channels(Q, O, n):
+    """BASELINE configs[3] at a size the oracle follows: noisy QAOA on vec(rho) with the depolarizing channel after every
+    gate -- 1q channels from DEPOLARIZING-KRAUS-MAP, 2q channels as their KRAUS-KRON tensor (16 Kraus operators on four
+    index bits, src/basic-noise-qvm.lisp:251-269) -- through the density machine's gate tape in ONE library call."""
+    circ = CC.qaoa_maxcut_circuit(n, CC.line_graph(n))
+    dep = G.depolarizing_kraus_map(0.01)
+    dep2 = G.kraus_kron(dep, dep)
+    ops = []
+    for m, q in circ:
+        ops.append(([m], q))
+        ops.append((dep if len(q) == 1 else dep2, q))
+    st = Q.DensityMatrixState(n)
+    st.vec.density_apply_ops(n, ops)
+    rho = O.zero_density(n)
+    for kraus, q in ops:
+        O.density_apply_kraus(rho, n, kraus, q)
+    H.assert_close(st.state_elements(), rho)
+    probs = st.measurement_probabilities()
+    assert abs(probs.sum() - 1.0) < 1e-12
+    np.testing.assert_allclose(probs, O.density_diag_probs(rho, n), rtol=1e-12, atol=1e-14)
+    st.vec.close()
+
+
+def test_density_machine_batches_its_transitions(Q):
+    """The 14-qubit configuration's circuit shape at 7 qubits: DensityQVM.run must reach the fused schedule through the
+    protocol (one library call per stretch of gate transitions), not one pass per operator."""
+    from qvm_b200 import _lib
+    n = 7
+    lines = [f"H {q}" for q in range(n)]
+    for a, b in CC.line_graph(n):
+        lines += [f"CNOT {a} {b}", f"RZ(1.4) {b}", f"CNOT {a} {b}"]
+    lines += [f"RX(0.6) {q}" for q in range(n)]
+    qvm = Q.DensityQVM(n, seed=1)
+    for q in range(n):
+        for name in ("H", "RX", "RZ"):
+            pass
+    qvm.load_program("\n".join(lines))
+    before = _lib.launch_count()
+    qvm.run()
+    launches = _lib.launch_count() - before
+    n_ops = len(lines)
+    assert launches <= 8 < n_ops, f"{launches} kernel launches for {n_ops} operators"
+    assert abs(qvm.state.measurement_probabilities().sum() - 1.0) < 1e-12
+
+
+def test_bench_20H_on_gpu(Q):
+    """BASELINE configs[0]: bench/20H.quil verbatim on PURE-STATE-QVM -- every amplitude 2^-10."""
+    circ, _, n = H.load_bench_circuit("20H")
+    vec = Q.DeviceVector(1 << n)
+    vec.set_zero_state()
+    vec.apply_gates(circ, fuse=True)
+    amps = vec.download()
+    np.testing.assert_allclose(amps, 2.0 ** -10, rtol=0, atol=1e-14)
+    vec.set_zero_state()
+    vec.apply_gates(circ, fuse=False)
+    np.testing.assert_allclose(vec.download(), 2.0 ** -10, rtol=0, atol=1e-14)
+    vec.close()
+
+
+def test_qft_30_properties(Q):
+    """BASELINE configs[1] at full size through size-independent properties: QFT|x> has uniform magnitudes and the phase
+    ramp exp(2 pi i x k / 2^n) on the low indices; the norm survives; fused and unfused prefixes agree."""
+    n = 30
+    circ = CC.qft_circuit(range(n))
+    vec = Q.DeviceVector(1 << n)
+    x = 5
+    vec.set_basis_state(x)
+    vec.apply_gates(circ, fuse=True)
+    assert abs(vec.norm2() - 1.0) < 1e-10
+    head = vec.download(0, 4096)
+    k = np.arange(4096)
+    want = np.exp(2j * np.pi * x * k / float(1 << n)) * 2.0 ** (-n / 2)
+    np.testing.assert_allclose(head, want, rtol=0, atol=1e-12 * 2.0 ** (-n / 2) * 100)
+    for q in (0, 15, 29):
+        assert abs(vec.prob_excited(q) - 0.5) < 1e-10
+    vec.close()
