@@ -266,14 +266,13 @@ def max_threads() -> int:
 
 def density_measure_all(rho, n, uniforms):
     """NAIVE-MEASURE-ALL on a density matrix (src/measurement.lisp:153-162): MEASURE q for q = n-1 .. 0, each with the
-    decision rule of src/measurement.lisp:93-105 (bit = 0 if p1 = 0; 1 if r <= p1; else 0) and the collapse of :43-68, fed
-    the given uniforms in that order.  Returns the bits, element i = qubit i."""
+    decision rule of src/measurement.lisp:93-105 (bit = 0 if p1 = 0 -- WITHOUT drawing; else 1 if (random 1d0) <= p1; else 0)
+    and the collapse of :43-68, fed the given uniforms in that order.  Returns the bits, element i = qubit i."""
     bits = [0] * n
     it = iter(uniforms)
     for q in range(n - 1, -1, -1):
         p1 = density_prob_excited(rho, n, q)
-        r = next(it)
-        bit = 0 if p1 == 0.0 else (1 if r <= p1 else 0)
+        bit = 0 if p1 == 0.0 else (1 if next(it) <= p1 else 0)      # COND evaluates (random 1d0) only when p1 /= 0
         density_force_measurement(rho, n, q, bit, p1)
         bits[q] = bit
     return bits

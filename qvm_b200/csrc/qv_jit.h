@@ -14,7 +14,7 @@
 
 #include "qv_sched.h"
 
-#define QVJIT_VERSION "qvjit-3"
+#define QVJIT_VERSION "qvjit-4"
 
 struct QvPeers;
 struct qvc;

@@ -109,7 +109,8 @@ JitSource jit_generate(const Step& st, int variant) {
     const bool fences = (variant & 4) != 0;        // 4 = compiler fence after every micro-op (table loads are not hoisted across micro-ops)
     o("#define QVJ_M %d\n#define QVJ_THREADS %d\n#define QVJ_MIN_CTAS %d\n#define QVJ_MODE %d\n#define QVJ_PROG_BYTES %d\n", M, threads,
       min_ctas, js.mode, js.prog_bytes);
-    o("#define QVJ_HAS_SCALE %d\n#define QVJ_HAS_TABLES %d\n", h.has_scale ? 1 : 0, (h.n_sources | h.n_preds | h.n_slice_entries) ? 1 : 0);
+    o("#define QVJ_HAS_SCALE %d\n#define QVJ_STORE_PERM %d\n#define QVJ_HAS_TABLES %d\n", h.has_scale ? 1 : 0, h.store_perm ? 1 : 0,
+      (h.n_sources | h.n_preds | h.n_slice_entries) ? 1 : 0);
     o("#include \"qv_jit_prelude.cuh\"\n\n");
 
     static const int pairs[6][2] = {{0, 1}, {0, 2}, {1, 2}, {0, 3}, {1, 3}, {2, 3}};
@@ -187,17 +188,10 @@ JitSource jit_generate(const Step& st, int variant) {
                         const uint32_t space = (dk - QV_K_DIAG_BASE) / 5u, gate = (dk - QV_K_DIAG_BASE) % 5u;
                         const std::string idx = index_expr(u, blob);
                         const uint32_t field = (NS == 16 ? 4u : 3u) - (gate ? 1u : 0u);
-                        // table-pool offsets are DATA (read from the micro-op record, a fixed constant-bank address): the pool
-                        // interleaves static tables with slice sources whose sizes depend on the tile geometry
-                        char tdata[64];
-                        snprintf(tdata, sizeof(tdata), "qvj_u32(blob, %uu)", (uint32_t)(h.off_uops + k * sizeof(QvUop) + offsetof(QvUop, data)));
-                        if (space == 1) {
-                            o("            qvc t = tables[%s + %s];\n", tdata, idx.c_str());
-                            if (flags & QV_UF_SCALE) o("            t = qv_cmul(t, s_slice[%uu]);\n", (unsigned)u.scale);
-                            o("            qv_diag1<%d, %u>(a, t);\n", NS, gate);
-                        } else if (space == 3) {
-                            o("            qv_diagr<%d, %u>(a, tables + %s + (%s << %uu));\n", NS, gate, tdata, idx.c_str(), field);
-                        } else if (space < 2) {
+                        // (Reading table offsets from the micro-op record instead -- so that passes differing only in table
+                        // sizes share a kernel -- was measured: +3 % instructions, +5 % time on the QFT's heavy passes,
+                        // gpurun_out/r2d_summary.md vs r2a_summary.md.  Literals it is; a pass structure costs 0.35 s to compile.)
+                        if (space < 2) {
                             o("            qvc t = %s[%uu + %s];\n", space == 0 ? "s_slice" : "tables", u.data, idx.c_str());
                             if (flags & QV_UF_SCALE) o("            t = qv_cmul(t, s_slice[%uu]);\n", (unsigned)u.scale);
                             o("            qv_diag1<%d, %u>(a, t);\n", NS, gate);

@@ -10,7 +10,7 @@
 // (src/compile-gate.lisp:156-209, 315-334), one level up: one compiled function per fused pass.
 //
 // The generated translation unit defines, before including this file:
-//   QVJ_M, QVJ_THREADS, QVJ_MODE (0 local, 2 pull), QVJ_PROG_BYTES, QVJ_HAS_SCALE, QVJ_HAS_TABLES,
+//   QVJ_M, QVJ_THREADS, QVJ_MODE (0 local, 2 pull), QVJ_PROG_BYTES, QVJ_HAS_SCALE, QVJ_STORE_PERM, QVJ_HAS_TABLES,
 //   the round functions qvj_round_<r>() and QVJ_RUN_ROUNDS (the sequence of rounds with barriers in between).
 // With QVJ_HOST defined the same text compiles as plain C++ (tests/support: the round functions are run by the CPU
 // emulator in place of its interpreter, which checks the generator without a GPU).
@@ -46,15 +46,14 @@ qvj_kernel(const __grid_constant__ QvjProg prog, const __grid_constant__ QvPeers
     const uint64_t glo = qv_gather((uint64_t)tid, h->tile_segs, h->n_tile_segs);
     qvc* const my_tile = tile + qv_swz(tid);
     qvc* const own = PULL ? alt_own : peers.base[(fixed_bits >> n_local) & (QV_MAX_PEERS - 1)];
-    // store permutation (trailing X / CNOT / SWAP gates folded into the write-back): a uniform run-time switch, so
-    // passes with and without one share a kernel
-    const bool store_perm = h->store_perm != 0;
+    // store permutation (trailing X / CNOT / SWAP gates folded into the write-back).  A compile-time switch: as a uniform
+    // run-time branch the write-back of the QFT's fourth pass went from 7.6 to 10.5 ms (r2d_summary.md vs r2a_summary.md).
+#if QVJ_STORE_PERM
     uint32_t st_lo = h->st_const;
-    if (store_perm) {
 #pragma unroll
-        for (uint32_t k = 0; k < 12; k++)
-            if (tid >> k & 1) st_lo ^= h->st_col[k];
-    }
+    for (uint32_t k = 0; k < 12; k++)
+        if (tid >> k & 1) st_lo ^= h->st_col[k];
+#endif
 #if QVJ_HAS_SCALE
     const double out_scale = h->out_scale;
 #endif
@@ -104,26 +103,18 @@ qvj_kernel(const __grid_constant__ QvjProg prog, const __grid_constant__ QvPeers
         // ---- shared memory -> HBM
         {
             char* tdst = reinterpret_cast<char*>(own + pbase);
-            if (store_perm) {
 #pragma unroll
-                for (int i = 0; i < ITERS; i++) {
-                    qvc v = tile[st_lo ^ h->st_hi[i]];
-#if QVJ_HAS_SCALE
-                    v.x *= out_scale;
-                    v.y *= out_scale;
+            for (int i = 0; i < ITERS; i++) {
+#if QVJ_STORE_PERM
+                qvc v = tile[st_lo ^ h->st_hi[i]];
+#else
+                qvc v = my_tile[i * THREADS];
 #endif
-                    qv_st_stream(reinterpret_cast<qvc*>(tdst + h->hi_byte[i]), v);
-                }
-            } else {
-#pragma unroll
-                for (int i = 0; i < ITERS; i++) {
-                    qvc v = my_tile[i * THREADS];
 #if QVJ_HAS_SCALE
-                    v.x *= out_scale;
-                    v.y *= out_scale;
+                v.x *= out_scale;
+                v.y *= out_scale;
 #endif
-                    qv_st_stream(reinterpret_cast<qvc*>(tdst + h->hi_byte[i]), v);
-                }
+                qv_st_stream(reinterpret_cast<qvc*>(tdst + h->hi_byte[i]), v);
             }
         }
         __syncthreads();

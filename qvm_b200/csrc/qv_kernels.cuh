@@ -71,6 +71,21 @@ qv_big_kernel(qvc* __restrict__ psi, QvBigGate g, const qvc* __restrict__ mat, u
     }
 }
 
+// Diagonal gate on k > QV_MAX_CHUNK_BITS qubits: psi_i *= table[bits of i at the gate's positions].  Element-wise, 32 B per
+// amplitude; positions may be rank bits (their value comes from fixed_bits).
+__global__ void __launch_bounds__(QV_THREADS)
+qv_bigdiag_kernel(qvc* __restrict__ psi, QvBigGate g, const qvc* __restrict__ table, uint64_t count) {
+    const uint64_t stride = (uint64_t)gridDim.x * QV_THREADS;
+    for (uint64_t i = (uint64_t)blockIdx.x * QV_THREADS + threadIdx.x; i < count; i += stride) {
+        const uint64_t full = i | g.fixed_bits;
+        uint32_t idx = 0;
+        for (uint32_t j = 0; j < g.k; j++) idx |= (uint32_t)((full >> g.pos[j]) & 1ull) << j;
+        qvc a = qv_ld_stream(psi + i);
+        qv_cmul_ip(a, table[idx]);
+        qv_st_stream(psi + i, a);
+    }
+}
+
 // ---------------------------------------------------------------------------
 // Reductions: per-thread strided partial sums, warp-shuffle + shared-memory
 // block reduction, one partial per CTA; a second single-CTA kernel adds the

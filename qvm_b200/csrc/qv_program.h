@@ -204,7 +204,7 @@ struct QvPassHeader {
 // A k>=3 dense gate runs as its own pass through the generic kernel.
 struct QvBigGate {
     uint32_t k;
-    uint32_t pad;
+    uint32_t diag;                  // 1: the "matrix" is the 2^k diagonal of a diagonal gate too wide for the table micro-ops
     uint32_t pos[16];               // physical bit of matrix index bit j
     uint64_t ctrl_mask, ctrl_val;   // physical control bits (identity when not matching)
     uint64_t fixed_bits;            // rank bits of this shard (for controls on global qubits)

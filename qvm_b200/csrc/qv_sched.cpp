@@ -28,6 +28,7 @@ struct Atom {
     std::vector<cd> mat;        // DENSE/BIG: 2^kt x 2^kt row-major; DIAG: 2^k diagonal entries
     std::vector<int> dw;        // DIAG: wire of entry index bit j
     uint64_t cmask = 0, cval = 0;   // control wires / required values
+    bool bigdiag = false;       // BIG: mat holds the 2^k diagonal entries (a diagonal on more than QV_MAX_CHUNK_BITS qubits)
     uint64_t mix = 0;           // wires the atom mixes (its targets)
     uint64_t touch = 0;         // every wire the atom reads
 };
@@ -89,9 +90,23 @@ void analyze(const Gate& g, const std::vector<int>& wire_of, std::vector<Atom>& 
         if (!ident) out.push_back(std::move(a));
         return;
     }
-    if (mixbits == 0) mixbits = d - 1;   // oversized diagonal: run it as a dense gate
+    if (mixbits == 0) {
+        // A diagonal on more than QV_MAX_CHUNK_BITS qubits: its own element-wise pass with a 2^k-entry table.  It mixes
+        // nothing, so its wires may sit anywhere (rank bits included) and other atoms commute past it like past any diagonal.
+        Atom a;
+        a.kind = Atom::BIG;
+        a.bigdiag = true;
+        a.touch = touch;
+        a.mat.resize(d);
+        for (uint32_t r = 0; r < d; r++) a.mat[r] = g.mat[(size_t)r * d + r];
+        for (int j = 0; j < k; j++) a.tw.push_back(wire(j));
+        out.push_back(std::move(a));
+        return;
+    }
     const uint32_t nonmix = (d - 1) & ~mixbits;
     const int km = popc(mixbits);
+    // checked here, before any step exists: a failure at launch time would leave earlier steps of the batch applied
+    if (km > 11) throw std::runtime_error("dense gates on more than 11 mixing qubits are not supported");
     const uint32_t dm = 1u << km;
     uint32_t v = 0;
     for (;;) {   // every value of the non-mixing bits selects one block
@@ -1206,6 +1221,7 @@ Step build_big_step(const Atom& a, const Geometry& geo, const Layout& lay) {
     Step st;
     st.kind = Step::BIG;
     st.big.k = (uint32_t)a.tw.size();
+    st.big.diag = a.bigdiag ? 1u : 0u;
     for (size_t j = 0; j < a.tw.size(); j++) st.big.pos[j] = (uint32_t)lay.phys(a.tw[j]);
     for (int wq = 0; wq < 64; wq++)
         if (a.cmask >> wq & 1) {

@@ -187,6 +187,15 @@ int launch_tile(qvmcuda_state* s, const qv::Step& st, const uint8_t* d_tables, q
 }
 
 int launch_big(qvmcuda_state* s, const qv::Step& st, const uint8_t* d_mat) {
+    if (st.big.diag) {
+        uint64_t blocks = (s->n_amps + QV_THREADS - 1) / QV_THREADS;
+        const uint64_t cap = (uint64_t)s->sm_count * 8 * 4;
+        if (blocks > cap) blocks = cap;
+        qv_bigdiag_kernel<<<(int)blocks, QV_THREADS, 0, s->stream>>>(s->d_amps, st.big, (const qvc*)d_mat, s->n_amps);
+        g_launches++;
+        CK(cudaGetLastError());
+        return 0;
+    }
     if (st.big.k > 11) return fail("dense gates on more than 11 mixing qubits are not supported");
     const uint64_t groups = 1ull << (s->n_bits - (int)st.big.k);
     const uint64_t G = QV_BIG_ELEMS >> st.big.k;

@@ -333,10 +333,12 @@ class BaseQVM:
         if target is None:
             return
         name, off = target
+        # the reference signals an error for a memory reference outside the declared region
+        # (DEREFERENCE-MREF, src/classical-memory-mixin.lisp); so do we, instead of growing the register
         if name not in self.registers:
-            self.registers[name] = np.zeros(max(off + 1, 1), dtype=np.int64)
-        if off >= self.registers[name].size:
-            self.registers[name] = np.resize(self.registers[name], off + 1)
+            raise KeyError(f"MEASURE into undeclared memory region {name!r}")
+        if off < 0 or off >= self.registers[name].size:
+            raise IndexError(f"memory reference {name}[{off}] is outside the declared region of {self.registers[name].size}")
         self.registers[name][off] = bit
 
     def load_program(self, program):
@@ -345,6 +347,7 @@ class BaseQVM:
         self.program = program
         self.pc = 0
         self._compiled = None
+        self.registers = {}                 # a new program starts from its own DECLAREs only
         for ins in program.instructions:
             if isinstance(ins, Declare):
                 self.registers[ins.name] = np.zeros(ins.length, dtype=np.int64)
@@ -425,9 +428,11 @@ class PureStateQVM(BaseQVM):
             if isinstance(x, GateApp):
                 if compiled:
                     # COMPILE-LOADED-PROGRAM: a maximal run of gates becomes one fused tape
+                    # (same predicate as the interpreted path below: a gate with modifiers is never the noisy gate)
+                    def noisy(g):
+                        return (g.name, tuple(g.qubits)) in self.superoperator_definitions and not g.modifiers
                     j = i
-                    while (j < len(ins) and isinstance(ins[j], GateApp)
-                           and (ins[j].name, tuple(ins[j].qubits)) not in self.superoperator_definitions):
+                    while j < len(ins) and isinstance(ins[j], GateApp) and not noisy(ins[j]):
                         j += 1
                     if j == i:        # a noisy gate: stochastic evolution, like the interpreted path
                         evolve_pure_state_stochastically(self.superoperator_definitions[(x.name, tuple(x.qubits))],

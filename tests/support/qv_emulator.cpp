@@ -175,6 +175,16 @@ void run_tile_step(qvc* const* peers, const qv::Step& st, qvc* alt_own = nullptr
 void run_big_step(qvc* psi, int n_bits, const qv::Step& st) {   // psi = this rank's shard, n_bits = its log2 size
     const uint32_t k = st.big.k;
     const uint64_t d = 1ull << k;
+    if (st.big.diag) {      // wide diagonal: element-wise table lookup (qv_bigdiag_kernel)
+        for (uint64_t i = 0; i < (1ull << n_bits); i++) {
+            const uint64_t full = i | st.big.fixed_bits;
+            uint32_t idx = 0;
+            for (uint32_t j = 0; j < k; j++) idx |= (uint32_t)((full >> st.big.pos[j]) & 1ull) << j;
+            const qvc t{st.bigmat[idx].real(), st.bigmat[idx].imag()};
+            psi[i] = qv_cmul(psi[i], t);
+        }
+        return;
+    }
     uint64_t tmask = 0;
     for (uint32_t j = 0; j < k; j++) tmask |= 1ull << st.big.pos[j];
     std::vector<qvc> in(d), out(d);

@@ -69,6 +69,8 @@ def test_density_measure_all_matches_oracle(Q, O):
         O.density_apply_unitary(rho, n, G.gate_matrix("RY", [1.1]), (1,))
         H.assert_close(qvm.amplitudes, rho)
         uniforms = np.random.default_rng(1000 + seed).random(n)
+        # (a probability that is exactly 0 in the oracle must be exactly 0 on the device too, or the two would consume a
+        # different number of draws: the collapse writes exact zeros, so it is)
         it = iter(uniforms)
         qvm.random = lambda: float(next(it))
         bits = qvm.measure_all()

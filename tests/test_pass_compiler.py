@@ -149,6 +149,5 @@ def test_cache_key_is_structural():
     b = _signatures(qvm.Tape(24, layer(list(range(8, 16)), 1.7), fuse=True))
     c = _signatures(qvm.Tape(24, layer(list(range(14, 22)), 0.9), fuse=True))
     assert a == b == c and a[0] is not None
-    # the three heavy passes of a 30-qubit QFT differ in tile position and in the number of external phases only
-    s = _signatures(qvm.Tape(30, circuits.qft_circuit(range(30)), fuse=True))
-    assert s[0] == s[1]
+    # (table offsets and the presence of a store permutation are literals -- measured faster than reading them at run time --
+    # so passes whose phase tables differ in size, like the QFT's three heavy passes, get their own kernels)

@@ -108,3 +108,37 @@ def test_trailing_permutation_gates_fold_into_the_write_back(reg_bits):
     run_oracle(b0, circ)
     assert np.array_equal(a0, b0)
     assert "rounds=0" in desc, desc
+
+
+def test_wide_diagonal_gate():
+    """A diagonal on more than 8 qubits runs as its own element-wise pass (it used to be densified and rejected above 11
+    qubits at launch time); its wires may sit on rank bits of a sharded state."""
+    import helpers as H
+    n = 14
+    rng = np.random.default_rng(21)
+    for k in (9, 12):
+        qs = tuple(int(x) for x in rng.choice(n, k, replace=False))
+        d = np.exp(1j * rng.uniform(0, 6.28, size=1 << k))
+        circ = H.random_circuit(n, 10, rng) + [(np.diag(d), qs)] + H.random_circuit(n, 10, rng)
+        psi = H.rand_state(n, k)
+        ref = H.run_oracle(psi.copy(), circ)
+        x = psi.copy()
+        H.run_emulator(x, n, circ)
+        H.assert_close(x, ref)
+        y = psi.copy()
+        _, _, _, l2p = H.run_emulator_sharded(y, n, 4, circ, remap_pull=True)
+        H.assert_close(H.unpermute(y, l2p), ref)
+
+
+def test_too_wide_dense_gate_fails_before_anything_runs():
+    import helpers as H
+    n = 14
+    rng = np.random.default_rng(3)
+    u = H.rand_unitary(1, rng)
+    big = np.eye(1 << 12, dtype=np.complex128)
+    big[0, 0] = 0; big[0, -1] = 1; big[-1, -1] = 0; big[-1, 0] = 1      # mixes all 12 qubits
+    psi = H.rand_state(n, 1)
+    x = psi.copy()
+    with pytest.raises(RuntimeError, match="more than 11 mixing qubits"):
+        H.run_emulator(x, n, [(u, (0,)), (big, tuple(range(12)))])
+    assert (x == psi).all()      # the schedule is rejected as a whole: the first gate has not been applied
