@@ -319,7 +319,7 @@ def main():
     ap.add_argument("--ref-gates-per-step", type=int, default=4)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--local-qubits", type=int, default=32, help="N>1: qubits per shard (32 = 64 GiB per GPU; 8 GPUs = 35 qubits)")
-    ap.add_argument("--c5-layers", type=int, default=20, help="N>1: layers of the random 1q/CZ circuit timed beside the QFT (0 = skip)")
+    ap.add_argument("--c5-layers", type=int, default=10, help="N>1: layers of the random 1q/CZ circuit timed beside the QFT (0 = skip)")
     ap.add_argument("--no-parity-check", action="store_true", help="N>1: skip the small sharded parity check before the timed region")
     args = ap.parse_args()
     if args.impl == "reference":

@@ -14,7 +14,7 @@
 
 #include "qv_sched.h"
 
-#define QVJIT_VERSION "qvjit-4"
+#define QVJIT_VERSION "qvjit-5"
 
 struct QvPeers;
 struct qvc;

@@ -34,6 +34,39 @@ uint64_t fnv1a(const std::string& s, uint64_t h = 1469598103934665603ull) {
     return h;
 }
 
+inline uint32_t swz1(uint32_t e) { return e ^ ((e >> 3) & 7u); }
+inline uint32_t swz2(uint32_t e) { return e ^ ((e >> 3) & 7u) ^ ((e >> 6) & 7u) ^ ((e >> 9) & 7u); }
+
+// rank over GF(2) of three 3-bit vectors
+int rank3(uint32_t a, uint32_t b, uint32_t c) {
+    uint32_t v[3] = {a & 7u, b & 7u, c & 7u};
+    int rank = 0;
+    for (int bit = 2; bit >= 0; bit--) {
+        int piv = -1;
+        for (int i = rank; i < 3; i++)
+            if (v[i] >> bit & 1) { piv = i; break; }
+        if (piv < 0) continue;
+        std::swap(v[rank], v[piv]);
+        for (int i = 0; i < 3; i++)
+            if (i != rank && (v[i] >> bit & 1)) v[i] ^= v[rank];
+        rank++;
+    }
+    return rank;
+}
+
+// Shared-memory swizzle of a pass.  The default (qv_swz: 16-byte column ^= bits 3..5) keeps every ROUND free of bank
+// conflicts; a store permutation that sends the three lowest tile-local bits to positions >= 6 (the QFT's bit reversal) makes
+// the eight lanes of a quarter-warp read the same column in the write-back (measured: 1.0e9 conflicts, 7.6 ms instead of
+// ~6 for the QFT's fourth pass, profiles/r02_a_compiled_passes.md).  The wide swizzle folds bits 6..8 and 9..11 into the
+// column as well; it is chosen only when it removes that conflict (it costs one XOR per element in the tile load / store).
+bool wants_wide_swizzle(const QvPassHeader& h) {
+    if (!h.store_perm) return false;
+    // st_col[k] = qv_swz(A e_k): the swizzle is an involution, so A e_k = qv_swz(st_col[k])
+    const uint32_t c0 = swz1(h.st_col[0]), c1 = swz1(h.st_col[1]), c2 = swz1(h.st_col[2]);
+    const int r1 = rank3(swz1(c0), swz1(c1), swz1(c2)), r2 = rank3(swz2(c0), swz2(c1), swz2(c2));
+    return r1 < 3 && r2 > r1;
+}
+
 // index expression of a diagonal micro-op over the group counter g
 std::string index_expr(const QvUop& u, const uint8_t* blob) {
     std::string e;
@@ -109,8 +142,9 @@ JitSource jit_generate(const Step& st, int variant) {
     const bool fences = (variant & 4) != 0;        // 4 = compiler fence after every micro-op (table loads are not hoisted across micro-ops)
     o("#define QVJ_M %d\n#define QVJ_THREADS %d\n#define QVJ_MIN_CTAS %d\n#define QVJ_MODE %d\n#define QVJ_PROG_BYTES %d\n", M, threads,
       min_ctas, js.mode, js.prog_bytes);
-    o("#define QVJ_HAS_SCALE %d\n#define QVJ_STORE_PERM %d\n#define QVJ_HAS_TABLES %d\n", h.has_scale ? 1 : 0, h.store_perm ? 1 : 0,
-      (h.n_sources | h.n_preds | h.n_slice_entries) ? 1 : 0);
+    const bool wide = wants_wide_swizzle(h);
+    o("#define QVJ_HAS_SCALE %d\n#define QVJ_STORE_PERM %d\n#define QVJ_HAS_TABLES %d\n#define QVJ_WIDE_SWZ %d\n", h.has_scale ? 1 : 0,
+      h.store_perm ? 1 : 0, (h.n_sources | h.n_preds | h.n_slice_entries) ? 1 : 0, wide ? 1 : 0);
     o("#include \"qv_jit_prelude.cuh\"\n\n");
 
     static const int pairs[6][2] = {{0, 1}, {0, 2}, {1, 2}, {0, 3}, {1, 3}, {2, 3}};
@@ -133,13 +167,11 @@ JitSource jit_generate(const Step& st, int variant) {
             const uint32_t width_before = (uint32_t)(12 - M + i);
             if (rd.regpos[i] < width_before) o("        e0 = qv_insert_zero(e0, %uu);\n", rd.regpos[i]);
         }
-        o("        const uint32_t se0 = qv_swz(e0);\n");
+        o("        const uint32_t se0 = qvj_swz(e0);\n");
         o("        qvc a[%d];\n", NS);
-        // slot address: bits of the slot offset that the swizzle leaves alone and that are zero in se0 can be ADDED
-        // (immediate offset of the shared-memory access); the others are XORed
-        uint32_t regmask = 0;
-        for (int i = 0; i < M; i++) regmask |= 1u << rd.regpos[i];
-        const uint32_t add_ok = regmask & ~0x3fu;      // register bits >= 6: untouched by qv_swz, zero in se0
+        // slot address: the register bits are zero in e0 and the swizzle only rewrites the three column bits, so the slot of
+        // (e0 | dep) is (se0 ^ x) + (dep & ~7) with x = the column bits of swizzle(dep): one XOR (none when x = 0) and an
+        // immediate offset
         for (int pass = 0; pass < 2; pass++) {
             if (pass == 1) {
                 // ---- micro-ops
@@ -207,13 +239,11 @@ JitSource jit_generate(const Step& st, int variant) {
                 }
             }
             for (int s = 0; s < NS; s++) {
-                const uint32_t sx = rd.slot_xor[s];
-                // slot_xor = swz(dep): split into the part that can be added and the part that must be XORed
                 uint32_t dep = 0;
                 for (int i = 0; i < M; i++)
                     if (s >> i & 1) dep |= 1u << rd.regpos[i];
-                const uint32_t addpart = dep & add_ok;
-                const uint32_t xorpart = sx ^ addpart;      // swz is XOR-linear and leaves bits >= 6 alone
+                const uint32_t sw = wide ? swz2(dep) : swz1(dep);
+                const uint32_t xorpart = sw & 7u, addpart = sw & ~7u;      // == dep & ~7
                 char addr[96];
                 if (xorpart && addpart) snprintf(addr, sizeof(addr), "(se0 ^ 0x%xu) + 0x%xu", xorpart, addpart);
                 else if (xorpart) snprintf(addr, sizeof(addr), "se0 ^ 0x%xu", xorpart);
@@ -228,6 +258,8 @@ JitSource jit_generate(const Step& st, int variant) {
     o("#define QVJ_RUN_ROUNDS(tile, tid, blob, tables, s_slice, s_pred)");
     for (uint32_t r = 0; r < h.n_rounds; r++) o(" \\\n    qvj_round_%u(tile, tid, blob, tables, s_slice, s_pred); QVJ_SYNC();", r);
     o("\n\n");
+    o("#if defined(QVJ_HOST)\n// slot of the pass's layout for a slot of the default layout (the emulator stages and writes back through it)\n"
+      "extern \"C\" uint32_t qvj_host_slot(uint32_t s) { return qvj_from_swz1(s); }\n#endif\n");
     o("#if defined(QVJ_HOST)\nextern \"C\" void qvj_host_round(int r, qvc* tile, uint32_t tid, const uint8_t* blob, const qvc* tables,\n"
       "                               const qvc* s_slice, const uint8_t* s_pred) {\n    switch (r) {\n");
     for (uint32_t r = 0; r < h.n_rounds; r++) o("        case %u: qvj_round_%u(tile, tid, blob, tables, s_slice, s_pred); break;\n", r, r);

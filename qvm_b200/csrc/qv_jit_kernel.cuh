@@ -44,7 +44,14 @@ qvj_kernel(const __grid_constant__ QvjProg prog, const __grid_constant__ QvPeers
     const uint64_t local_mask = (1ull << n_local) - 1ull;
     const uint32_t tid = threadIdx.x;
     const uint64_t glo = qv_gather((uint64_t)tid, h->tile_segs, h->n_tile_segs);
-    qvc* const my_tile = tile + qv_swz(tid);
+    // element tid + THREADS*i of the tile: the default swizzle leaves bits >= 8 alone (slot = swz(tid) + THREADS*i); the wide
+    // one also folds them into the column, a compile-time constant per i
+    const uint32_t my_slot = qvj_swz(tid);
+#if QVJ_WIDE_SWZ
+#define QVJ_SLOT(i) ((my_slot ^ (qvj_swz((uint32_t)(i) * THREADS) & 7u)) + (uint32_t)(i) * THREADS)
+#else
+#define QVJ_SLOT(i) (my_slot + (uint32_t)(i) * THREADS)
+#endif
     qvc* const own = PULL ? alt_own : peers.base[(fixed_bits >> n_local) & (QV_MAX_PEERS - 1)];
     // store permutation (trailing X / CNOT / SWAP gates folded into the write-back).  A compile-time switch: as a uniform
     // run-time branch the write-back of the QFT's fourth pass went from 7.6 to 10.5 ms (r2d_summary.md vs r2a_summary.md).
@@ -53,6 +60,7 @@ qvj_kernel(const __grid_constant__ QvjProg prog, const __grid_constant__ QvPeers
 #pragma unroll
     for (uint32_t k = 0; k < 12; k++)
         if (tid >> k & 1) st_lo ^= h->st_col[k];
+    st_lo = qvj_from_swz1(st_lo);       // the host constants are in the default layout; the map is XOR-linear
 #endif
 #if QVJ_HAS_SCALE
     const double out_scale = h->out_scale;
@@ -66,13 +74,13 @@ qvj_kernel(const __grid_constant__ QvjProg prog, const __grid_constant__ QvPeers
         if (!PULL) {
             const char* tsrc = reinterpret_cast<const char*>(own + pbase);
 #pragma unroll
-            for (int i = 0; i < ITERS; i++) qv_cp_async16(my_tile + i * THREADS, reinterpret_cast<const qvc*>(tsrc + h->hi_byte[i]));
+            for (int i = 0; i < ITERS; i++) qv_cp_async16(tile + QVJ_SLOT(i), reinterpret_cast<const qvc*>(tsrc + h->hi_byte[i]));
         } else {
             const uint64_t sbase = qv_remap_index(base | glo, h->pull_remap);
 #pragma unroll
             for (int i = 0; i < ITERS; i++) {
                 const uint64_t p = sbase ^ h->hi_src[i];
-                qv_cp_async16(my_tile + i * THREADS, peers.base[(p >> n_local) & (QV_MAX_PEERS - 1)] + (p & local_mask));
+                qv_cp_async16(tile + QVJ_SLOT(i), peers.base[(p >> n_local) & (QV_MAX_PEERS - 1)] + (p & local_mask));
             }
         }
         asm volatile("cp.async.commit_group;" ::: "memory");
@@ -106,9 +114,9 @@ qvj_kernel(const __grid_constant__ QvjProg prog, const __grid_constant__ QvPeers
 #pragma unroll
             for (int i = 0; i < ITERS; i++) {
 #if QVJ_STORE_PERM
-                qvc v = tile[st_lo ^ h->st_hi[i]];
+                qvc v = tile[st_lo ^ qvj_from_swz1(h->st_hi[i])];
 #else
-                qvc v = my_tile[i * THREADS];
+                qvc v = tile[QVJ_SLOT(i)];
 #endif
 #if QVJ_HAS_SCALE
                 v.x *= out_scale;

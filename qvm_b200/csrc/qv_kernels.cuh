@@ -71,6 +71,125 @@ qv_big_kernel(qvc* __restrict__ psi, QvBigGate g, const qvc* __restrict__ mat, u
     }
 }
 
+// ---------------------------------------------------------------------------
+// Dense k-qubit gate (3 <= k <= 8 mixing qubits) on the FP64 TENSOR path: mma.sync.m8n8k4.f64 (SASS: DMMA).
+// The complex 2^k x 2^k matrix is applied as the real (2d x 2d) block matrix W = [[Re, -Im], [Im, Re]] with rows and
+// columns interleaved (re, im) per amplitude, to a panel of G groups staged in shared memory:
+//     Y^T (groups x outputs) = X^T (groups x inputs) . W^T (inputs x outputs)
+// so that the A fragment of a lane is one real of one group (row-major panel in shared memory, padded by 4 doubles per row
+// against bank conflicts), the B fragment is W[output][input] straight from the row-major matrix, and the two accumulators of
+// a lane are (re, im) of ONE output amplitude of ONE group: results go back to the panel as 16-byte stores, no shuffles.
+// Why: measured on B200 (scripts/fp64_probe.cu, gpurun_out/r2d_fp64_probe.txt) the tensor path sustains 55 FP64 FMA per clock
+// per SM against 38 for DFMA; a dense k >= 5 gate is bound by FP64, not by HBM (4 * 2^k FMA per amplitude).
+// ---------------------------------------------------------------------------
+#define QV_MMA_ELEMS 2048
+__device__ __forceinline__ void qv_dmma(double& d0, double& d1, double a, double b) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(d0), "+d"(d1) : "d"(a), "d"(b));
+}
+
+template <int MT>   // m-tiles (8 groups each) per work item: they share every B (matrix) fragment
+__device__ __forceinline__ void qv_mma_item(const double* __restrict__ xa, const double* __restrict__ wb, uint32_t D2, uint32_t ld,
+                                            double* __restrict__ yo) {
+    double c0[MT], c1[MT];
+#pragma unroll
+    for (int m = 0; m < MT; m++) c0[m] = c1[m] = 0.0;
+    for (uint32_t k0 = 0; k0 < D2; k0 += 4) {
+        const double b = wb[k0];
+#pragma unroll
+        for (int m = 0; m < MT; m++) qv_dmma(c0[m], c1[m], xa[(size_t)m * 8 * ld + k0], b);
+    }
+#pragma unroll
+    for (int m = 0; m < MT; m++) {
+        qvc v;
+        v.x = c0[m];
+        v.y = c1[m];
+        *reinterpret_cast<qvc*>(yo + (size_t)m * 8 * ld) = v;
+    }
+}
+
+__global__ void __launch_bounds__(QV_THREADS)
+qv_bigmma_kernel(qvc* __restrict__ psi, QvBigGate g, const double* __restrict__ Wg, uint32_t n_bits, uint32_t w_in_smem) {
+    extern __shared__ __align__(16) double qv_mma_smem[];
+    const uint32_t k = g.k, d = 1u << k, D2 = 2u * d;
+    const uint32_t G = QV_MMA_ELEMS >> k;             // groups per panel (>= 8 for k <= 8)
+    const uint32_t ld = D2 + 4;                       // padded row of the panel, in doubles
+    double* X = qv_mma_smem;
+    double* Y = X + (size_t)G * ld;
+    double* Ws = Y + (size_t)G * ld;
+    const uint32_t ldw = w_in_smem ? D2 + 4 : D2;
+    const double* W = w_in_smem ? Ws : Wg;
+    if (w_in_smem)
+        for (uint32_t i = threadIdx.x; i < D2 * D2; i += QV_THREADS) Ws[(i / D2) * ldw + (i % D2)] = Wg[i];
+    const uint64_t n_groups = 1ull << (n_bits - k);
+    uint32_t sorted[16];
+    for (uint32_t j = 0; j < k; j++) sorted[j] = g.pos[j];
+    for (uint32_t i = 1; i < k; i++) {
+        uint32_t v = sorted[i];
+        int j = (int)i - 1;
+        while (j >= 0 && sorted[j] > v) { sorted[j + 1] = sorted[j]; j--; }
+        sorted[j + 1] = v;
+    }
+    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint32_t n_tiles = D2 / 8, m_tiles = G / 8;
+    for (uint64_t gb = (uint64_t)blockIdx.x * G; gb < n_groups; gb += (uint64_t)gridDim.x * G) {
+        // gather the panel (coalesced where the gate's positions allow, as qv_big_kernel)
+        for (uint32_t idx = threadIdx.x; idx < QV_MMA_ELEMS; idx += QV_THREADS) {
+            const uint64_t grp = gb + (idx >> k);
+            const uint32_t c = idx & (d - 1);
+            qvc v;
+            v.x = 0.0;
+            v.y = 0.0;
+            if (grp < n_groups) {
+                uint64_t base = grp;
+                for (uint32_t j = 0; j < k; j++) {
+                    const uint64_t lo = base & ((1ull << sorted[j]) - 1ull);
+                    base = ((base >> sorted[j]) << (sorted[j] + 1)) | lo;
+                }
+                uint64_t a = base;
+                for (uint32_t j = 0; j < k; j++)
+                    if (c >> j & 1) a |= 1ull << g.pos[j];
+                v = qv_ld_stream(psi + a);
+            }
+            *reinterpret_cast<qvc*>(X + (size_t)(idx >> k) * ld + 2 * c) = v;
+        }
+        __syncthreads();
+        // work items: (n-tile of 8 output reals) x (block of MT m-tiles); consecutive warps take consecutive n-tiles
+        if (m_tiles >= 4) {
+            const uint32_t m_blocks = m_tiles / 4;
+            for (uint32_t item = warp; item < n_tiles * m_blocks; item += QV_THREADS / 32) {
+                const uint32_t nt = item % n_tiles, mb = item / n_tiles;
+                qv_mma_item<4>(X + (size_t)(mb * 32 + lane / 4) * ld + lane % 4, W + (size_t)(nt * 8 + lane / 4) * ldw + lane % 4, D2, ld,
+                               Y + (size_t)(mb * 32 + lane / 4) * ld + nt * 8 + 2 * (lane % 4));
+            }
+        } else {
+            for (uint32_t item = warp; item < n_tiles * m_tiles; item += QV_THREADS / 32) {
+                const uint32_t nt = item % n_tiles, mt = item / n_tiles;
+                qv_mma_item<1>(X + (size_t)(mt * 8 + lane / 4) * ld + lane % 4, W + (size_t)(nt * 8 + lane / 4) * ldw + lane % 4, D2, ld,
+                               Y + (size_t)(mt * 8 + lane / 4) * ld + nt * 8 + 2 * (lane % 4));
+            }
+        }
+        __syncthreads();
+        for (uint32_t idx = threadIdx.x; idx < QV_MMA_ELEMS; idx += QV_THREADS) {
+            const uint64_t grp = gb + (idx >> k);
+            const uint32_t r = idx & (d - 1);
+            if (grp < n_groups) {
+                uint64_t base = grp;
+                for (uint32_t j = 0; j < k; j++) {
+                    const uint64_t lo = base & ((1ull << sorted[j]) - 1ull);
+                    base = ((base >> sorted[j]) << (sorted[j] + 1)) | lo;
+                }
+                if (((base | g.fixed_bits) & g.ctrl_mask) == g.ctrl_val) {
+                    uint64_t a = base;
+                    for (uint32_t j = 0; j < k; j++)
+                        if (r >> j & 1) a |= 1ull << g.pos[j];
+                    qv_st_stream(psi + a, *reinterpret_cast<const qvc*>(Y + (size_t)(idx >> k) * ld + 2 * r));
+                }
+            }
+        }
+        __syncthreads();
+    }
+}
+
 // Diagonal gate on k > QV_MAX_CHUNK_BITS qubits: psi_i *= table[bits of i at the gate's positions].  Element-wise, 32 B per
 // amplitude; positions may be rank bits (their value comes from fixed_bits).
 __global__ void __launch_bounds__(QV_THREADS)

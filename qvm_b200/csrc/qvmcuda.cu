@@ -110,12 +110,39 @@ bool l2p_is_identity(const std::vector<int>& l2p) {
     return true;
 }
 
+// Dense gates on 3..8 mixing qubits run on the FP64 tensor path (qv_bigmma_kernel); QVMCUDA_BIG=scalar keeps the
+// scalar kernel (A/B measurements, and the kernel for k > 8).
+bool big_uses_mma(const qv::Step& st) {
+    static const bool scalar = getenv("QVMCUDA_BIG") && std::string(getenv("QVMCUDA_BIG")) == "scalar";
+    return st.kind == qv::Step::BIG && !st.big.diag && st.big.k >= 3 && st.big.k <= 8 && !scalar;
+}
+
+// host bytes of a step's device data: tables (tile pass) or matrix (+ real block form W[2r+p][2c+q], see qv_bigmma_kernel)
+void fill_step_data(const qv::Step& st, uint8_t* dst) {
+    const std::vector<qv::cd>& src = st.kind == qv::Step::TILE ? st.tables : st.bigmat;
+    if (src.empty()) return;
+    std::memcpy(dst, src.data(), src.size() * sizeof(qv::cd));
+    if (big_uses_mma(st)) {
+        const size_t d = (size_t)1 << st.big.k, D2 = 2 * d;
+        double* W = reinterpret_cast<double*>(dst + src.size() * sizeof(qv::cd));
+        for (size_t r = 0; r < d; r++)
+            for (size_t c = 0; c < d; c++) {
+                const qv::cd m = st.bigmat[r * d + c];
+                W[(2 * r) * D2 + 2 * c] = m.real();
+                W[(2 * r) * D2 + 2 * c + 1] = -m.imag();
+                W[(2 * r + 1) * D2 + 2 * c] = m.imag();
+                W[(2 * r + 1) * D2 + 2 * c + 1] = m.real();
+            }
+    }
+}
+
 void layout_tape(qvmcuda_tape* t) {
     t->offsets.clear();
     size_t off = 0;
     for (const qv::Step& st : t->tape.steps) {
         t->offsets.push_back(off);
-        const size_t bytes = (st.kind == qv::Step::TILE ? st.tables.size() : st.bigmat.size()) * sizeof(qv::cd);
+        size_t bytes = (st.kind == qv::Step::TILE ? st.tables.size() : st.bigmat.size()) * sizeof(qv::cd);
+        if (big_uses_mma(st)) bytes += 4 * bytes;      // + the real (2d x 2d) block form the tensor-path kernel reads
         off += (bytes + 255) & ~(size_t)255;
     }
     t->total_bytes = off;
@@ -197,6 +224,23 @@ int launch_big(qvmcuda_state* s, const qv::Step& st, const uint8_t* d_mat) {
         return 0;
     }
     if (st.big.k > 11) return fail("dense gates on more than 11 mixing qubits are not supported");
+    if (big_uses_mma(st) && s->n_bits >= (int)st.big.k) {
+        const uint32_t k = st.big.k, D2 = 2u << k, G = QV_MMA_ELEMS >> k, ld = D2 + 4;
+        const uint32_t w_in_smem = k <= 4 ? 1u : 0u;
+        const size_t smem = ((size_t)2 * G * ld + (w_in_smem ? (size_t)D2 * (D2 + 4) : 0)) * sizeof(double);
+        static std::atomic<bool> attr_set[64];
+        if (s->device >= 0 && s->device < 64 && !attr_set[s->device].exchange(true))
+            CK(cudaFuncSetAttribute(qv_bigmma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+        const uint64_t n_groups = 1ull << (s->n_bits - (int)k);
+        uint64_t blocks = (n_groups + G - 1) / G;
+        const uint64_t cap = (uint64_t)s->sm_count * 2 * 4;
+        if (blocks > cap) blocks = cap;
+        const double* W = reinterpret_cast<const double*>(d_mat + st.bigmat.size() * sizeof(qv::cd));
+        qv_bigmma_kernel<<<(int)blocks, QV_THREADS, smem, s->stream>>>(s->d_amps, st.big, W, (uint32_t)s->n_bits, w_in_smem);
+        g_launches++;
+        CK(cudaGetLastError());
+        return 0;
+    }
     const uint64_t groups = 1ull << (s->n_bits - (int)st.big.k);
     const uint64_t G = QV_BIG_ELEMS >> st.big.k;
     uint64_t blocks = (groups + G - 1) / G;
@@ -340,11 +384,7 @@ int run_gates_locked(qvmcuda_state* s, const std::vector<qv::Gate>& gates, uint3
     } else {
         CK(cudaEventSynchronize(s->upload_done));
     }
-    for (size_t i = 0; i < t.tape.steps.size(); i++) {
-        const qv::Step& st = t.tape.steps[i];
-        const std::vector<qv::cd>& src = st.kind == qv::Step::TILE ? st.tables : st.bigmat;
-        if (!src.empty()) std::memcpy(s->h_scratch + t.offsets[i], src.data(), src.size() * sizeof(qv::cd));
-    }
+    for (size_t i = 0; i < t.tape.steps.size(); i++) fill_step_data(t.tape.steps[i], s->h_scratch + t.offsets[i]);
     CK(cudaMemcpyAsync(s->d_scratch, s->h_scratch, need, cudaMemcpyHostToDevice, s->stream));
     CK(cudaEventRecord(s->upload_done, s->stream));
     int rc = run_steps(s, t.tape, t.offsets, s->d_scratch);
@@ -614,11 +654,7 @@ static int tape_device_buffer(qvmcuda_state* s, qvmcuda_tape* t, uint8_t** out) 
     uint8_t*& d_buf = t->d_blobs[s->device];
     if (!d_buf) {
         std::vector<uint8_t> host(t->total_bytes ? t->total_bytes : 256, 0);
-        for (size_t i = 0; i < t->tape.steps.size(); i++) {
-            const qv::Step& st = t->tape.steps[i];
-            const std::vector<qv::cd>& src = st.kind == qv::Step::TILE ? st.tables : st.bigmat;
-            if (!src.empty()) std::memcpy(host.data() + t->offsets[i], src.data(), src.size() * sizeof(qv::cd));
-        }
+        for (size_t i = 0; i < t->tape.steps.size(); i++) fill_step_data(t->tape.steps[i], host.data() + t->offsets[i]);
         CK(cudaMalloc((void**)&d_buf, host.size()));
         CK(cudaMemcpy(d_buf, host.data(), host.size(), cudaMemcpyHostToDevice));
     }

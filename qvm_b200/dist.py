@@ -383,6 +383,8 @@ def bench_sharded(args, rank: int, world: int, local_rank: int):
 
     from . import _lib, circuits
 
+    # the ranks of one box share its host cores: split them between the ranks' pass-compiler pools
+    os.environ.setdefault("QVMCUDA_JIT_THREADS", str(max(1, (os.cpu_count() or 8) // world)))
     torch.cuda.set_device(local_rank)
     dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     g = _log2(world)
@@ -415,17 +417,36 @@ def bench_sharded(args, rank: int, world: int, local_rank: int):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
+    def settle(fn, max_iters):
+        """Untimed preparation.  A sharded state is never moved back to the canonical qubit layout (the host maps indices through
+        the layout instead), so consecutive runs of the same circuit start from different layouts and the schedule -- and with
+        it the set of compiled passes -- only repeats after a few runs.  Run until one whole circuit needs no new kernel."""
+        iters = 0
+        for _ in range(max_iters):
+            before = _lib.jit_stats()
+            fn()
+            st._barrier()
+            after = _lib.jit_stats()
+            new = torch.tensor([after["compiled"] + after["disk_hits"] - before["compiled"] - before["disk_hits"]], device="cuda",
+                               dtype=torch.int64)
+            dist.all_reduce(new, op=dist.ReduceOp.MAX)
+            iters += 1
+            if int(new.item()) == 0:
+                break
+        return iters
+
     j0 = _lib.jit_stats()
     t_prep = time.perf_counter()
-    step()                                  # untimed: schedules, compiles the passes (pass compiler), first touch
-    st._barrier()
+    prep_iters = settle(step, 16)           # untimed: schedules, compiles the passes (pass compiler), first touch
     prep_s = time.perf_counter() - t_prep
-    for _ in range(max(0, args.warmup - 1)):
+    for _ in range(args.warmup):
         step()
     l0 = _lib.launch_count()
     p0, s0, ps0, pb0 = st.peer_steps, st.steps, st.peer_seconds, st.peer_bytes
     sampler = _start_clock_sampler(rank, local_rank)     # nvidia-smi clocks during the timed region (rank 0)
+    jt0 = _lib.jit_stats()
     dt = timed(step, args.steps)
+    jt1 = _lib.jit_stats()
     launches = _lib.launch_count() - l0
     clocks = _stop_clock_sampler(sampler)
     passes_per_step = (st.steps - s0) / args.steps
@@ -467,14 +488,19 @@ def bench_sharded(args, rank: int, world: int, local_rank: int):
             st.apply_gates(rgates, fuse=True)
 
         st.set_zero_state()
-        rstep()                             # untimed: compiles the passes
+        c5_prep = settle(rstep, 6)          # untimed: compiles the passes
         p1, s1, ps1, pb1 = st.peer_steps, st.steps, st.peer_seconds, st.peer_bytes
+        j_before = _lib.jit_stats()
         rdt = timed(rstep, 1)
+        j_after = _lib.jit_stats()
         rp = st.steps - s1
         c5 = {"workload": f"random 1q(RZ.RY.RZ)/CZ circuit, {args.c5_layers} layers on {n} qubits, seed 0", "gates": len(rgates),
               "seconds_per_circuit": rdt, "gates_per_s": len(rgates) / rdt, "value_30q_equivalent": len(rgates) * 2.0 ** (n - 30) / rdt,
               "hbm_passes": rp, "exchange_passes": st.peer_steps - p1,
               "roofline": _sharded_roofline(L, rdt, rp, st.peer_steps - p1, st.peer_seconds - ps1, st.peer_bytes - pb1),
+              "bound_note": "layers of general 1q gates are bound by the FP64 pipe on B200, not by HBM (see DESIGN.md); the HBM figure "
+                            "is reported for comparison with the QFT line",
+              "prepare_circuits": c5_prep, "kernels_compiled_in_timed_region": j_after["compiled"] - j_before["compiled"],
               "norm2": st.norm2()}
     j1 = _lib.jit_stats()
     if rank == 0:
@@ -494,7 +520,9 @@ def bench_sharded(args, rank: int, world: int, local_rank: int):
                                    "torch.distributed (NCCL) for barriers and scalars only",
                        "l2_policy": "shard (64 GiB) is far larger than the 126 MB L2; no flush needed",
                        "timing": "CUDA events on the kernels' stream, bracketed by barrier + cudaDeviceSynchronize, max over ranks",
-                       "pass_compiler": {"prepare_seconds": prep_s, "kernels_compiled": j1["compiled"] - j0["compiled"],
+                       "pass_compiler": {"prepare_seconds": prep_s, "prepare_circuits": prep_iters,
+                                         "kernels_compiled": j1["compiled"] - j0["compiled"],
+                                         "kernels_compiled_in_timed_region": jt1["compiled"] - jt0["compiled"],
                                          "disk_cache_hits": j1["disk_hits"] - j0["disk_hits"], "compile_ms_total": j1["compile_ms"] - j0["compile_ms"]}},
             "roofline": _sharded_roofline(L, dt / args.steps, passes_per_step, peer_per_step, peer_s, peer_b),
             "parity_check": parity, "c5_random": c5,

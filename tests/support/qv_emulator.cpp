@@ -31,11 +31,16 @@ bool g_jit_host = false;
 int g_jit_host_used = 0;
 std::string g_csrc_dir;
 typedef void (*qvj_round_fn)(int, qvc*, uint32_t, const uint8_t*, const qvc*, const qvc*, const uint8_t*);
-std::map<uint64_t, qvj_round_fn> g_jit_fns;
+typedef uint32_t (*qvj_slot_fn)(uint32_t);
+struct HostPass {
+    qvj_round_fn round = nullptr;
+    qvj_slot_fn slot = nullptr;       // default-layout slot -> slot of the pass's own shared-memory swizzle
+};
+std::map<uint64_t, HostPass> g_jit_fns;
 
-qvj_round_fn host_compiled_rounds(const qv::Step& st) {
+HostPass host_compiled_rounds(const qv::Step& st) {
     const qv::JitSource src = qv::jit_generate(st);
-    if (!src.ok) return nullptr;
+    if (!src.ok) return HostPass();
     auto it = g_jit_fns.find(src.sig);
     if (it != g_jit_fns.end()) return it->second;
     char base[128];
@@ -49,8 +54,10 @@ qvj_round_fn host_compiled_rounds(const qv::Step& st) {
     if (system(cmd.c_str()) != 0) throw std::runtime_error("emulator: g++ failed on a generated pass, see " + std::string(base) + ".log");
     void* lib = dlopen(so.c_str(), RTLD_NOW | RTLD_LOCAL);
     if (!lib) throw std::runtime_error(std::string("emulator: dlopen of a generated pass: ") + dlerror());
-    qvj_round_fn fn = (qvj_round_fn)dlsym(lib, "qvj_host_round");
-    if (!fn) throw std::runtime_error("emulator: generated pass lacks qvj_host_round");
+    HostPass fn;
+    fn.round = (qvj_round_fn)dlsym(lib, "qvj_host_round");
+    fn.slot = (qvj_slot_fn)dlsym(lib, "qvj_host_slot");
+    if (!fn.round || !fn.slot) throw std::runtime_error("emulator: generated pass lacks qvj_host_round / qvj_host_slot");
     unlink(cu.c_str());
     unlink(so.c_str());
     unlink((std::string(base) + ".log").c_str());
@@ -81,11 +88,13 @@ void run_tile_step(qvc* const* peers, const qv::Step& st, qvc* alt_own = nullptr
     if (h.n_sources > QV_MAX_SOURCES || h.n_preds > QV_MAX_PREDS || h.n_slice_entries > QV_SLICE_ENTRIES ||
         h.n_slices > QV_MAX_SLICES)
         throw std::runtime_error("emulator: per-tile table limits exceeded");
-    qvj_round_fn compiled = nullptr;
+    HostPass hp;
     if (g_jit_host && h.n_rounds > 0) {
-        compiled = host_compiled_rounds(st);
-        if (compiled) g_jit_host_used++;
+        hp = host_compiled_rounds(st);
+        if (hp.round) g_jit_host_used++;
     }
+    const qvj_round_fn compiled = hp.round;
+    auto slot_of = [&](uint32_t s1) { return hp.slot ? hp.slot(s1) : s1; };
     auto addr = [&](uint64_t p) { return peers[p >> h.n_local_bits] + (p & local_mask); };
     if (h.pull && !alt_own) throw std::runtime_error("emulator: pull pass without an alternate buffer");
     // the kernel's split source index: S(base | gather(tid)) ^ hi_src[i]
@@ -111,7 +120,7 @@ void run_tile_step(qvc* const* peers, const qv::Step& st, qvc* alt_own = nullptr
             const QvSlice& sl = slices[slice_of[f]];
             s_slice[f] = qv_slice_entry(sl, sources, s_srcext.data(), tables, f - sl.off);
         }
-        for (uint32_t e = 0; e < tile_n; e++) smem[qv_swz(e)] = h.pull ? *addr(src_index(base, e)) : *addr(phys(base, e));
+        for (uint32_t e = 0; e < tile_n; e++) smem[slot_of(qv_swz(e))] = h.pull ? *addr(src_index(base, e)) : *addr(phys(base, e));
         if (compiled) {     // the generated round functions, one virtual thread after the other, round by round
             for (uint32_t r = 0; r < h.n_rounds; r++)
                 for (uint32_t tid = 0; tid < threads; tid++)
@@ -161,7 +170,7 @@ void run_tile_step(qvc* const* peers, const qv::Step& st, qvc* alt_own = nullptr
                     if ((e & (threads - 1)) >> k & 1) slot ^= h.st_col[k];
                 slot ^= h.st_hi[e >> h.threads_log2];
             }
-            qvc v = smem[slot];
+            qvc v = smem[slot_of(slot)];
             if (h.has_scale) {
                 v.x *= h.out_scale;
                 v.y *= h.out_scale;

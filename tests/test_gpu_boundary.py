@@ -157,3 +157,72 @@ def test_qft_30_properties(Q):
     for q in (0, 15, 29):
         assert abs(vec.prob_excited(q) - 0.5) < 1e-10
     vec.close()
+
+
+def _dense_gate_cases(n, rng):
+    cases = []
+    for k in (3, 4, 5, 6, 8):
+        qs = tuple(int(x) for x in rng.choice(n, k, replace=False))
+        cases.append((H.rand_unitary(k, rng), qs))
+    # a controlled 3-qubit block: the control is a non-mixing qubit of a 4-qubit gate
+    u3 = H.rand_unitary(3, rng)
+    cu = np.eye(16, dtype=np.complex128)
+    cu[8:, 8:] = u3
+    cases.append((cu, tuple(int(x) for x in rng.choice(n, 4, replace=False))))
+    return cases
+
+
+def test_dense_k_qubit_gates_tensor_path(Q, O):
+    """APPLY-OPERATOR for k >= 3 (src/wavefunction.lisp:234-306) through the DMMA kernel (the default for 3 <= k <= 8)."""
+    n = 13
+    rng = np.random.default_rng(77)
+    psi = H.rand_state(n, 2)
+    vec = Q.DeviceVector(1 << n)
+    for m, qs in _dense_gate_cases(n, rng):
+        vec.upload(psi)
+        vec.apply_matrix(m, qs)
+        ref = O.apply_matrix(psi.copy(), m, qs)
+        H.assert_close(vec.download(), ref)
+    vec.close()
+
+
+def test_dense_k_qubit_gates_scalar_path(tmp_path):
+    """The same cases through the scalar kernel (QVMCUDA_BIG=scalar, read once per process): the A/B partner of the
+    tensor-path kernel and the kernel that serves k > 8."""
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    script = tmp_path / "scalar_big.py"
+    script.write_text(
+        "import sys, numpy as np\n"
+        f"sys.path.insert(0, {root!r}); sys.path.insert(0, {os.path.join(root, 'tests')!r})\n"
+        "import helpers as H\n"
+        "from oracle import oracle as O\n"
+        "from qvm_b200 import qvm\n"
+        "from test_gpu_boundary import _dense_gate_cases\n"
+        "n = 13\n"
+        "rng = np.random.default_rng(77)\n"
+        "psi = H.rand_state(n, 2)\n"
+        "vec = qvm.DeviceVector(1 << n)\n"
+        "for m, qs in _dense_gate_cases(n, rng):\n"
+        "    vec.upload(psi); vec.apply_matrix(m, qs)\n"
+        "    H.assert_close(vec.download(), O.apply_matrix(psi.copy(), m, qs))\n"
+        "print('scalar ok')\n")
+    env = dict(os.environ, QVMCUDA_BIG="scalar")
+    out = subprocess.run([sys.executable, str(script)], env=env, capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0 and "scalar ok" in out.stdout, out.stdout + out.stderr
+
+
+def test_two_qubit_channels_on_rho_use_dense_path(Q, O):
+    """KRAUS-KRON 2q depolarizing channels are 16x16 superoperators on four index bits of vec(rho): the k = 4 dense path."""
+    n = 5
+    dep2 = G.kraus_kron(G.depolarizing_kraus_map(0.05), G.depolarizing_kraus_map(0.1))
+    st = Q.DensityMatrixState(n)
+    ops = [([G.gate_matrix("H")], (0,)), ([G.gate_matrix("CNOT")], (0, 3)), (dep2, (0, 3)), (dep2, (4, 1))]
+    st.vec.density_apply_ops(n, ops)
+    rho = O.zero_density(n)
+    for kraus, q in ops:
+        O.density_apply_kraus(rho, n, kraus, q)
+    H.assert_close(st.state_elements(), rho)
+    st.vec.close()
