@@ -152,6 +152,14 @@ int qvmcuda_density_measure_discard(qvmcuda_state *s, int n_qubits, int qubit);
 /* DENSITY-MATRIX-STATE-MEASUREMENT-PROBABILITIES src/state-representation.lisp:268-286 (2^n doubles to host) */
 int qvmcuda_density_diag_probs(qvmcuda_state *s, int n_qubits, double *out);
 
+/* MIXED-STATE-EXPECTATION (app/src/api/expectation.lisp:91-107): tr(Q rho) for the Hermitian matrix Q of an operator program
+ * (row-major 2^n x 2^n complex doubles on the host); out = (re, im).  One read of vec(rho) and of Q. */
+int qvmcuda_density_expectation(qvmcuda_state *s, int n_qubits, const double *op_matrix, double out[2]);
+/* SET-TO-ZERO-STATE of UNITARY-STATE (src/unitary-qvm.lisp:57-61): the 4^n vector becomes vec(identity).  The UNITARY-QVM is
+ * the pure-state path on 2n index bits (gates act on the low n bits = the row index of the column-major matrix,
+ * src/unitary-qvm.lisp:113-137): every other entry point applies unchanged. */
+int qvmcuda_set_identity_matrix(qvmcuda_state *s, int n_qubits);
+
 /* ---- multi-GPU sharding (one process per GPU; layout after dqvm/src/global-addresses.lisp:99-151:
  *      the top log2(P) physical index bits select the rank).  The 64-byte IPC handle of every rank's
  *      shard is exchanged by the host (torch.distributed) and attached here so that the tile kernel can

@@ -64,6 +64,8 @@ _SIGS = {
     "qvmcuda_density_collapse": [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_double],
     "qvmcuda_density_measure_discard": [C.c_void_p, C.c_int, C.c_int],
     "qvmcuda_density_diag_probs": [C.c_void_p, C.c_int, C.c_void_p],
+    "qvmcuda_density_expectation": [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p],
+    "qvmcuda_set_identity_matrix": [C.c_void_p, C.c_int],
     "qvmcuda_shard_export": [C.c_void_p, C.c_void_p],
     "qvmcuda_shard_attach": [C.c_void_p, C.c_int, C.c_int, C.c_void_p],
     "qvmcuda_shard_export_alt": [C.c_void_p, C.c_void_p],

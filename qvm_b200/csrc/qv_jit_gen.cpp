@@ -9,6 +9,7 @@
 #include <cstdarg>
 #include <cstddef>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 
 namespace qv {
@@ -60,7 +61,8 @@ int rank3(uint32_t a, uint32_t b, uint32_t c) {
 // ~6 for the QFT's fourth pass, profiles/r02_a_compiled_passes.md).  The wide swizzle folds bits 6..8 and 9..11 into the
 // column as well; it is chosen only when it removes that conflict (it costs one XOR per element in the tile load / store).
 bool wants_wide_swizzle(const QvPassHeader& h) {
-    if (!h.store_perm) return false;
+    static const bool enabled = !(getenv("QVMCUDA_JIT_WIDE_SWZ") && atoi(getenv("QVMCUDA_JIT_WIDE_SWZ")) == 0);
+    if (!h.store_perm || !enabled) return false;
     // st_col[k] = qv_swz(A e_k): the swizzle is an involution, so A e_k = qv_swz(st_col[k])
     const uint32_t c0 = swz1(h.st_col[0]), c1 = swz1(h.st_col[1]), c2 = swz1(h.st_col[2]);
     const int r1 = rank3(swz1(c0), swz1(c1), swz1(c2)), r2 = rank3(swz2(c0), swz2(c1), swz2(c2));

@@ -131,26 +131,36 @@ qv_bigmma_kernel(qvc* __restrict__ psi, QvBigGate g, const double* __restrict__ 
     }
     const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const uint32_t n_tiles = D2 / 8, m_tiles = G / 8;
+    // Address arithmetic off the per-element path: element idx = threadIdx.x + 256*i of a panel is (group idx >> k, member
+    // idx & (d-1)); d <= 256 divides the block size, so a thread always handles the SAME member c -- its offset
+    // sum_j bit_j(c) << pos[j] is computed once -- and the group bases (zeros inserted at the gate's positions) are computed
+    // once per panel by G threads into shared memory.
+    __shared__ uint64_t s_base[QV_MMA_ELEMS >> 3];
+    const uint32_t my_c = threadIdx.x & (d - 1);
+    uint64_t my_dep = 0;
+    for (uint32_t j = 0; j < k; j++)
+        if (my_c >> j & 1) my_dep |= 1ull << g.pos[j];
     for (uint64_t gb = (uint64_t)blockIdx.x * G; gb < n_groups; gb += (uint64_t)gridDim.x * G) {
-        // gather the panel (coalesced where the gate's positions allow, as qv_big_kernel)
+        for (uint32_t t = threadIdx.x; t < G; t += QV_THREADS) {
+            uint64_t base = gb + t;
+            for (uint32_t j = 0; j < k; j++) {
+                const uint64_t lo = base & ((1ull << sorted[j]) - 1ull);
+                base = ((base >> sorted[j]) << (sorted[j] + 1)) | lo;
+            }
+            // bit 63 marks groups outside the state or not selected by the gate's controls (left untouched)
+            const bool live = gb + t < n_groups;
+            const bool sel = live && (((base | g.fixed_bits) & g.ctrl_mask) == g.ctrl_val);
+            s_base[t] = base | (live ? 0ull : (1ull << 63)) | (sel ? 0ull : (1ull << 62));
+        }
+        __syncthreads();
+        // gather the panel (coalesced where the gate's positions allow)
         for (uint32_t idx = threadIdx.x; idx < QV_MMA_ELEMS; idx += QV_THREADS) {
-            const uint64_t grp = gb + (idx >> k);
-            const uint32_t c = idx & (d - 1);
+            const uint64_t b = s_base[idx >> k];
             qvc v;
             v.x = 0.0;
             v.y = 0.0;
-            if (grp < n_groups) {
-                uint64_t base = grp;
-                for (uint32_t j = 0; j < k; j++) {
-                    const uint64_t lo = base & ((1ull << sorted[j]) - 1ull);
-                    base = ((base >> sorted[j]) << (sorted[j] + 1)) | lo;
-                }
-                uint64_t a = base;
-                for (uint32_t j = 0; j < k; j++)
-                    if (c >> j & 1) a |= 1ull << g.pos[j];
-                v = qv_ld_stream(psi + a);
-            }
-            *reinterpret_cast<qvc*>(X + (size_t)(idx >> k) * ld + 2 * c) = v;
+            if (!(b >> 63)) v = qv_ld_stream(psi + ((b & ~(3ull << 62)) | my_dep));
+            *reinterpret_cast<qvc*>(X + (size_t)(idx >> k) * ld + 2 * my_c) = v;
         }
         __syncthreads();
         // work items: (n-tile of 8 output reals) x (block of MT m-tiles); consecutive warps take consecutive n-tiles
@@ -170,21 +180,9 @@ qv_bigmma_kernel(qvc* __restrict__ psi, QvBigGate g, const double* __restrict__ 
         }
         __syncthreads();
         for (uint32_t idx = threadIdx.x; idx < QV_MMA_ELEMS; idx += QV_THREADS) {
-            const uint64_t grp = gb + (idx >> k);
-            const uint32_t r = idx & (d - 1);
-            if (grp < n_groups) {
-                uint64_t base = grp;
-                for (uint32_t j = 0; j < k; j++) {
-                    const uint64_t lo = base & ((1ull << sorted[j]) - 1ull);
-                    base = ((base >> sorted[j]) << (sorted[j] + 1)) | lo;
-                }
-                if (((base | g.fixed_bits) & g.ctrl_mask) == g.ctrl_val) {
-                    uint64_t a = base;
-                    for (uint32_t j = 0; j < k; j++)
-                        if (r >> j & 1) a |= 1ull << g.pos[j];
-                    qv_st_stream(psi + a, *reinterpret_cast<const qvc*>(Y + (size_t)(idx >> k) * ld + 2 * r));
-                }
-            }
+            const uint64_t b = s_base[idx >> k];
+            if (!(b >> 62))
+                qv_st_stream(psi + (b | my_dep), *reinterpret_cast<const qvc*>(Y + (size_t)(idx >> k) * ld + 2 * my_c));
         }
         __syncthreads();
     }
@@ -285,6 +283,36 @@ qv_inner_kernel(const qvc* __restrict__ a, const qvc* __restrict__ b, uint64_t c
     if (threadIdx.x == 0) {
         partial[2 * blockIdx.x] = re;
         partial[2 * blockIdx.x + 1] = im;
+    }
+}
+
+// tr(Q rho) = sum_{i,j} Q[i][j] rho[j][i] (MIXED-STATE-EXPECTATION, app/src/api/expectation.lisp:91-107): rho = vec(rho)
+// row-major on 2n bits, Q row-major dim x dim on the device; per-CTA partial sums (re, im) like qv_inner_kernel.
+__global__ void __launch_bounds__(QV_THREADS)
+qv_trace_product_kernel(const qvc* __restrict__ rho, const qvc* __restrict__ Q, uint32_t n_qubits, double* __restrict__ partial) {
+    double re = 0.0, im = 0.0;
+    const uint64_t dim = 1ull << n_qubits, count = dim * dim;
+    const uint64_t stride = (uint64_t)gridDim.x * QV_THREADS;
+    for (uint64_t idx = (uint64_t)blockIdx.x * QV_THREADS + threadIdx.x; idx < count; idx += stride) {
+        const uint64_t j = idx >> n_qubits, i = idx & (dim - 1);      // rho[j][i]
+        const qvc r = qv_ld_stream(rho + idx), q = Q[i * dim + j];
+        re += q.x * r.x - q.y * r.y;
+        im += q.x * r.y + q.y * r.x;
+    }
+    const double tre = qv_block_sum(re);
+    const double tim = qv_block_sum(im);
+    if (threadIdx.x == 0) {
+        partial[2 * blockIdx.x] = tre;
+        partial[2 * blockIdx.x + 1] = tim;
+    }
+}
+
+// vec(I) on 2n bits: the zero state of UNITARY-STATE (src/unitary-qvm.lisp:57-61)
+__global__ void __launch_bounds__(QV_THREADS) qv_set_identity_kernel(qvc* __restrict__ psi, uint64_t dim) {
+    const uint64_t i = (uint64_t)blockIdx.x * QV_THREADS + threadIdx.x;
+    if (i < dim) {
+        psi[i * dim + i].x = 1.0;
+        psi[i * dim + i].y = 0.0;
     }
 }
 

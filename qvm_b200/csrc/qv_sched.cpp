@@ -619,7 +619,8 @@ void emit_round(BlobWriter& w, const std::vector<RoundOp>& rops, const std::vect
                 else if (std::find(gates_used.begin(), gates_used.end(), want[i]) == gates_used.end()) gates_used.push_back(want[i]);
             }
             const size_t gated_cost = 2 * gates_used.size() + (any_plain ? 4 : 0);
-            if (gated_cost > 4 && eff_bits(all_l, -1) <= QV_MAX_CHUNK_BITS)
+            static const bool single_chunk = !(getenv("QVMCUDA_DIAG_SINGLE_CHUNK") && atoi(getenv("QVMCUDA_DIAG_SINGLE_CHUNK")) == 0);
+            if (single_chunk && gated_cost > 4 && eff_bits(all_l, -1) <= QV_MAX_CHUNK_BITS)
                 for (size_t i = 0; i < nf; i++) want[i] = -1;
         }
         std::vector<PlanChunk> plan;

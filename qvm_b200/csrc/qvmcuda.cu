@@ -81,12 +81,21 @@ struct qvmcuda_state {
     double* d_sample_tree = nullptr;
     void* d_shots = nullptr;
     uint64_t shot_cap = 0;
+    // export scratch (probabilities, diagonal of rho): persistent, grown on demand -- no allocation per call
+    double* d_aux = nullptr;
+    uint64_t aux_cap = 0;
     // immediate-mode program upload
     uint8_t* d_scratch = nullptr;
     uint8_t* h_scratch = nullptr;  // pinned
     size_t scratch_cap = 0;
+    uint64_t scratch_tape = 0;     // id of the tape whose step data d_scratch holds
     cudaEvent_t upload_done = nullptr;
 };
+
+static uint64_t next_tape_id() {
+    static std::atomic<uint64_t> n{1};
+    return n++;
+}
 
 struct qvmcuda_tape {
     std::mutex mu;
@@ -96,6 +105,8 @@ struct qvmcuda_tape {
     std::vector<size_t> offsets;          // per step offset into the buffer
     size_t total_bytes = 0;
     int n_local = 0, rank = 0, world = 1; // geometry the tape was compiled for
+    uint64_t id = next_tape_id();         // identifies the tape whose data sits in a state's scratch buffer
+    bool ephemeral = false;               // shard tapes are compiled per run: their data goes through the state's scratch
     // compiled passes (qv_jit.h) per device: jit[dev][step] = kernel or nullptr (interpreter); complete = no step is
     // still waiting for the asynchronous compiler
     std::map<int, std::vector<qv::JitKernel*>> jit;
@@ -340,6 +351,33 @@ qv::CompileOptions make_options(const qvmcuda_state* s, uint32_t flags) {
     return opt;
 }
 
+// Program data (diagonal tables / big matrices) of a tape go through a persistent pinned staging buffer and a persistent
+// device scratch buffer of the STATE: no allocation on the gate path.  The staging buffer is reused only after the previous
+// upload has completed (event), the device buffer is protected by stream order.  scratch_tape remembers whose data it holds.
+int upload_to_scratch_locked(qvmcuda_state* s, const qvmcuda_tape& t) {
+    const size_t need = t.total_bytes ? t.total_bytes : 256;
+    if (need > s->scratch_cap) {
+        CK(cudaStreamSynchronize(s->stream));
+        if (s->d_scratch) cudaFree(s->d_scratch);
+        if (s->h_scratch) cudaFreeHost(s->h_scratch);
+        s->d_scratch = nullptr;
+        s->h_scratch = nullptr;
+        s->scratch_cap = 0;
+        const size_t cap = std::max<size_t>(need * 2, 1 << 20);
+        CK(cudaMalloc((void**)&s->d_scratch, cap));
+        CK(cudaMallocHost((void**)&s->h_scratch, cap));
+        if (!s->upload_done) CK(cudaEventCreateWithFlags(&s->upload_done, cudaEventDisableTiming));
+        s->scratch_cap = cap;
+    } else {
+        CK(cudaEventSynchronize(s->upload_done));
+    }
+    for (size_t i = 0; i < t.tape.steps.size(); i++) fill_step_data(t.tape.steps[i], s->h_scratch + t.offsets[i]);
+    CK(cudaMemcpyAsync(s->d_scratch, s->h_scratch, need, cudaMemcpyHostToDevice, s->stream));
+    CK(cudaEventRecord(s->upload_done, s->stream));
+    s->scratch_tape = t.id;
+    return 0;
+}
+
 // compile + upload + run in immediate mode (state mutex held)
 int run_gates_locked(qvmcuda_state* s, const std::vector<qv::Gate>& gates, uint32_t flags) {
     static const bool trace = getenv("QVMCUDA_TRACE") != nullptr;
@@ -365,28 +403,7 @@ int run_gates_locked(qvmcuda_state* s, const std::vector<qv::Gate>& gates, uint3
         s->l2p = t.tape.l2p;
         return 0;
     }
-    // Program data (diagonal tables / big matrices) go through a persistent pinned staging buffer and a
-    // persistent device scratch buffer: no allocation on the gate path.  The staging buffer is reused only
-    // after the previous upload has completed (event), the device buffer is protected by stream order.
-    const size_t need = t.total_bytes ? t.total_bytes : 256;
-    if (need > s->scratch_cap) {
-        CK(cudaStreamSynchronize(s->stream));
-        if (s->d_scratch) cudaFree(s->d_scratch);
-        if (s->h_scratch) cudaFreeHost(s->h_scratch);
-        s->d_scratch = nullptr;
-        s->h_scratch = nullptr;
-        s->scratch_cap = 0;
-        const size_t cap = std::max<size_t>(need * 2, 1 << 20);
-        CK(cudaMalloc((void**)&s->d_scratch, cap));
-        CK(cudaMallocHost((void**)&s->h_scratch, cap));
-        if (!s->upload_done) CK(cudaEventCreateWithFlags(&s->upload_done, cudaEventDisableTiming));
-        s->scratch_cap = cap;
-    } else {
-        CK(cudaEventSynchronize(s->upload_done));
-    }
-    for (size_t i = 0; i < t.tape.steps.size(); i++) fill_step_data(t.tape.steps[i], s->h_scratch + t.offsets[i]);
-    CK(cudaMemcpyAsync(s->d_scratch, s->h_scratch, need, cudaMemcpyHostToDevice, s->stream));
-    CK(cudaEventRecord(s->upload_done, s->stream));
+    if (int rc = upload_to_scratch_locked(s, t)) return rc;
     int rc = run_steps(s, t.tape, t.offsets, s->d_scratch);
     if (rc) return rc;
     s->l2p = t.tape.l2p;
@@ -445,6 +462,19 @@ int prob_bit_locked(qvmcuda_state* s, int pbit, int value, double* p) {
         return 0;
     }
     return reduce_locked(s, s->n_amps, 0, 0, 0, p);
+}
+
+int aux_locked(qvmcuda_state* s, uint64_t n_doubles, double** out) {
+    if (n_doubles > s->aux_cap) {
+        CK(cudaStreamSynchronize(s->stream));
+        if (s->d_aux) cudaFree(s->d_aux);
+        s->d_aux = nullptr;
+        s->aux_cap = 0;
+        CK(cudaMalloc((void**)&s->d_aux, n_doubles * sizeof(double)));
+        s->aux_cap = n_doubles;
+    }
+    *out = s->d_aux;
+    return 0;
 }
 
 int elementwise_locked(qvmcuda_state* s, int mode, uint32_t q, uint32_t q2, uint32_t keep, double f) {
@@ -529,6 +559,7 @@ int qvmcuda_state_destroy(qvmcuda_state* s) {
         if (s->h_scratch) cudaFreeHost(s->h_scratch);
         if (s->d_sample_tree) cudaFree(s->d_sample_tree);
         if (s->d_shots) cudaFree(s->d_shots);
+        if (s->d_aux) cudaFree(s->d_aux);
         if (s->upload_done) cudaEventDestroy(s->upload_done);
         if (s->own_stream && s->stream) cudaStreamDestroy(s->stream);
         s->d_amps = nullptr;
@@ -651,6 +682,12 @@ int qvmcuda_tape_compile(int n_qubits, int n_gates, const int32_t* ks, const int
 }
 
 static int tape_device_buffer(qvmcuda_state* s, qvmcuda_tape* t, uint8_t** out) {
+    if (t->ephemeral) {      // no allocation, no blocking copy: one asynchronous upload per tape
+        if (s->scratch_tape != t->id)
+            if (int rc = upload_to_scratch_locked(s, *t)) return rc;
+        *out = s->d_scratch;
+        return 0;
+    }
     uint8_t*& d_buf = t->d_blobs[s->device];
     if (!d_buf) {
         std::vector<uint8_t> host(t->total_bytes ? t->total_bytes : 256, 0);
@@ -674,6 +711,7 @@ int qvmcuda_shard_compile(qvmcuda_state* s, int n_gates, const int32_t* ks, cons
     t->n_local = s->n_bits;
     t->rank = s->rank;
     t->world = s->world;
+    t->ephemeral = true;
     try {
         const int total_bits = s->n_bits + log2_exact((uint64_t)s->world);
         t->tape = qv::compile(gates, total_bits, make_options(s, flags), s->l2p);
@@ -913,7 +951,7 @@ int qvmcuda_probabilities(qvmcuda_state* s, double* out, uint64_t offset, uint64
     // chunks of at most 2^24 basis states through one temporary device buffer (128 MiB)
     const uint64_t chunk = count < (1ull << 24) ? count : (1ull << 24);
     double* d_tmp = nullptr;
-    CK(cudaMalloc((void**)&d_tmp, chunk * sizeof(double)));
+    if (int rc0 = aux_locked(s, chunk, &d_tmp)) return rc0;
     int rc = 0;
     for (uint64_t done = 0; done < count && !rc; done += chunk) {
         const uint64_t n = count - done < chunk ? count - done : chunk;
@@ -927,7 +965,6 @@ int qvmcuda_probabilities(qvmcuda_state* s, double* out, uint64_t offset, uint64
         if (e == cudaSuccess) e = cudaStreamSynchronize(s->stream);
         if (e != cudaSuccess) rc = fail(std::string("probabilities: ") + cudaGetErrorString(e));
     }
-    cudaFree(d_tmp);
     return rc;
 }
 
@@ -1144,13 +1181,46 @@ int qvmcuda_density_diag_probs(qvmcuda_state* s, int n_qubits, double* out) {
     if (int rc = canonicalize_locked(s)) return rc;
     const uint64_t dim = 1ull << n_qubits;
     double* d_out = nullptr;
-    CK(cudaMallocAsync((void**)&d_out, dim * sizeof(double), s->stream));
+    if (int rc = aux_locked(s, dim, &d_out)) return rc;
     qv_diag_probs_kernel<<<(int)((dim + QV_THREADS - 1) / QV_THREADS), QV_THREADS, 0, s->stream>>>(s->d_amps, dim, d_out);
     g_launches++;
     CK(cudaGetLastError());
     CK(cudaMemcpyAsync(out, d_out, dim * sizeof(double), cudaMemcpyDeviceToHost, s->stream));
-    cudaFreeAsync(d_out, s->stream);
     CK(cudaStreamSynchronize(s->stream));
+    return 0;
+}
+
+int qvmcuda_density_expectation(qvmcuda_state* s, int n_qubits, const double* op_matrix, double out[2]) {
+    if (!s || !op_matrix || !out) return fail("null argument");
+    std::lock_guard<std::mutex> lk(s->mu);
+    if (s->n_bits != 2 * n_qubits) return fail("state length is not 4^n_qubits");
+    DeviceGuard dg(s->device);
+    if (int rc = canonicalize_locked(s)) return rc;
+    double* d_q = nullptr;
+    if (int rc = aux_locked(s, 2 * s->n_amps, &d_q)) return rc;      // the operator matrix, as large as rho itself
+    CK(cudaMemcpyAsync(d_q, op_matrix, s->n_amps * sizeof(qvc), cudaMemcpyHostToDevice, s->stream));
+    uint64_t blocks = (s->n_amps + QV_THREADS - 1) / QV_THREADS;
+    if (blocks > (kReduceBlocks - 2) / 2) blocks = (kReduceBlocks - 2) / 2;
+    qv_trace_product_kernel<<<(int)blocks, QV_THREADS, 0, s->stream>>>(s->d_amps, reinterpret_cast<const qvc*>(d_q), (uint32_t)n_qubits, s->d_partial);
+    qv_final_sum2_kernel<<<1, QV_THREADS, 0, s->stream>>>(s->d_partial, (uint32_t)blocks, s->d_partial + 2 * blocks);
+    g_launches += 2;
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(out, s->d_partial + 2 * blocks, 2 * sizeof(double), cudaMemcpyDeviceToHost, s->stream));
+    CK(cudaStreamSynchronize(s->stream));
+    return 0;
+}
+
+int qvmcuda_set_identity_matrix(qvmcuda_state* s, int n_qubits) {
+    if (!s) return fail("null argument");
+    std::lock_guard<std::mutex> lk(s->mu);
+    if (s->n_bits != 2 * n_qubits) return fail("state length is not 4^n_qubits");
+    DeviceGuard dg(s->device);
+    for (size_t i = 0; i < s->l2p.size(); i++) s->l2p[i] = (int)i;
+    const uint64_t dim = 1ull << n_qubits;
+    CK(cudaMemsetAsync(s->d_amps, 0, s->n_amps * sizeof(qvc), s->stream));
+    qv_set_identity_kernel<<<(int)((dim + QV_THREADS - 1) / QV_THREADS), QV_THREADS, 0, s->stream>>>(s->d_amps, dim);
+    g_launches++;
+    CK(cudaGetLastError());
     return 0;
 }
 

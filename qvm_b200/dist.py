@@ -262,6 +262,38 @@ class ShardedState:
             src |= ((idx >> q) & 1) << int(l2p[q])
         return phys[src]
 
+    def save_wavefunction(self, filename: str):
+        """SAVE-WAVEFUNCTION of the distributed QVM (dqvm/src/distributed-qvm.lisp:118-137): the file is the ordered
+        amplitudes as consecutive (re, im) native doubles, every rank writing its own entries at byte offset
+        16 * logical address (dqvm: MPI_File_write_at per amplitude; here one strided write per rank through a memory map).
+        The logical address of physical index p comes from the current qubit layout."""
+        self._barrier()
+        local = self.engine.download()
+        if self.rank == 0:
+            with open(filename, "wb") as f:
+                f.truncate(16 << self.n)
+        self.dist.barrier()
+        l2p = self.layout()
+        phys = (np.arange(local.size, dtype=np.uint64) | (np.uint64(self.rank) << np.uint64(self.n_local)))
+        logical = np.zeros_like(phys)
+        for q in range(self.n):
+            logical |= ((phys >> np.uint64(int(l2p[q]))) & np.uint64(1)) << np.uint64(q)
+        mm = np.memmap(filename, dtype=np.complex128, mode="r+", shape=(1 << self.n,))
+        mm[logical.astype(np.int64)] = local
+        mm.flush()
+        del mm
+        self.dist.barrier()
+
+    def load_wavefunction(self, filename: str):
+        """LOAD-WAVEFUNCTION (dqvm/src/distributed-qvm.lisp:141-150): the ordered amplitudes back into the shards (the layout
+        is reset to the identity first)."""
+        self.set_zero_state()
+        mm = np.memmap(filename, dtype=np.complex128, mode="r", shape=(1 << self.n,))
+        lo = self.rank << self.n_local
+        self.engine.upload(np.ascontiguousarray(mm[lo: lo + (1 << self.n_local)]))
+        del mm
+        self._barrier()
+
     def scatter_logical(self, psi: np.ndarray):
         """Load a full logical state (identity layout required: call right after set_zero_state)."""
         assert (self.layout() == np.arange(self.n)).all()

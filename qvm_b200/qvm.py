@@ -142,6 +142,18 @@ class DeviceVector:
         L.check(L.lib().qvmcuda_density_apply_ops(self.handle, n, len(ops), L.ptr(ks), L.ptr(qf), L.ptr(ms), L.ptr(kf),
                                                   L.FUSE if fuse else 0))
 
+    def density_expectation(self, n: int, op_matrix) -> complex:
+        """tr(Q rho), MIXED-STATE-EXPECTATION (app/src/api/expectation.lisp:91-107)."""
+        q = np.ascontiguousarray(op_matrix, dtype=np.complex128)
+        if q.shape != (1 << n, 1 << n):
+            raise ValueError("operator matrix must be 2^n x 2^n")
+        out = np.zeros(2, dtype=np.float64)
+        L.check(L.lib().qvmcuda_density_expectation(self.handle, n, L.ptr(q), L.ptr(out)))
+        return complex(out[0], out[1])
+
+    def set_identity_matrix(self, n: int):
+        L.check(L.lib().qvmcuda_set_identity_matrix(self.handle, n))
+
     def sample_total(self) -> float:
         """This vector's probability mass in the sampler's own summation order (sharded sampling)."""
         t = C.c_double(0.0)
@@ -566,6 +578,61 @@ class DensityQVM(BaseQVM):
                 break
         self.flush_gate_tape()
         return self
+
+
+class UnitaryQVM(BaseQVM):
+    """UNITARY-QVM (src/unitary-qvm.lisp:30-137): computes the unitary matrix of a program.  The state is a 4^n vector
+    holding the matrix in COLUMN-major order, initialised to the identity; gates act on the low n index bits (the row
+    index), i.e. it is the pure-state path on 2n bits.  No measurement."""
+
+    def __init__(self, num_qubits: int, device: int = 0):
+        super().__init__(None)
+        self.num_qubits = num_qubits
+        self.state = PureState(2 * num_qubits, device)
+        self.state.vec.set_identity_matrix(num_qubits)
+
+    def number_of_qubits(self) -> int:
+        return self.num_qubits
+
+    def reset_quantum_state(self):
+        self.state.vec.set_identity_matrix(self.num_qubits)
+
+    def measure(self, q):
+        raise RuntimeError("MEASURE unsupported in unitary calculation.")
+
+    def measure_all(self):
+        raise RuntimeError("MEASURE unsupported in unitary calculation.")
+
+    def run(self):
+        gates = []
+        for x in self.program.instructions:
+            if isinstance(x, GateApp):
+                gates.append((self.program.gate_matrix(x), x.qubits))
+            elif isinstance(x, (Measure, Reset)):
+                raise RuntimeError("MEASURE / RESET unsupported in unitary calculation.")
+        self.state.vec.apply_gates(gates, fuse=fuse_gates_during_compilation)
+        return self
+
+    def underlying_matrix(self) -> np.ndarray:
+        """UNITARY-QVM-UNDERLYING-MATRIX: column-major storage -> (row, column) array."""
+        d = 1 << self.num_qubits
+        return self.state.vec.download().reshape(d, d).T.copy()
+
+
+def parsed_program_unitary_matrix(program, num_qubits: int, device: int = 0) -> np.ndarray:
+    """PARSED-PROGRAM-UNITARY-MATRIX (src/unitary-qvm.lisp:128-137)."""
+    q = UnitaryQVM(num_qubits, device)
+    q.load_program(program)
+    q.run()
+    m = q.underlying_matrix()
+    q.state.vec.close()
+    return m
+
+
+def mixed_state_expectation(qvm: "DensityQVM", op_matrix) -> complex:
+    """MIXED-STATE-EXPECTATION (app/src/api/expectation.lisp:91-107): tr(Q rho) reduced on the device."""
+    qvm.flush_gate_tape()
+    return qvm.state.vec.density_expectation(qvm.number_of_qubits(), op_matrix)
 
 
 def wavefunction_octets(amplitudes) -> bytes:

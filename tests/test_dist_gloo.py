@@ -60,6 +60,24 @@ def _worker(rank, world, port, q):
         hist = np.bincount(idx.astype(np.int64), minlength=1 << n) / u.size
         assert np.abs(hist - probs).sum() < 0.9          # coarse: 2048 bins, 4000 shots
         assert probs[idx.astype(np.int64)].min() > 0
+        # raw dump in dqvm's file layout (ordered amplitudes, 16 bytes each) and back
+        import tempfile
+        path = os.path.join(tempfile.gettempdir(), f"qvm_dump_{port}.bin")
+        st.save_wavefunction(path)
+        if rank == 0:
+            helpers.assert_close(np.fromfile(path, dtype=np.complex128), ref)
+        dist.barrier()
+        lay_before = st.layout().copy()
+        st.load_wavefunction(path)
+        helpers.assert_close(st.gather_logical(), ref)
+        dist.barrier()
+        if rank == 0:
+            os.remove(path)
+        # back to the layout the run left behind (the checks below pick a rank-selecting qubit)
+        st.set_zero_state()
+        st.scatter_logical(psi)
+        st.apply_gates(circ, fuse=True)
+        assert (st.layout() == lay_before).all()
         # measurement of a qubit that currently selects the rank and of a local one
         lay = st.layout()
         for qb in (int(np.argmax(lay)), int(np.argmin(lay))):

@@ -226,3 +226,37 @@ def test_two_qubit_channels_on_rho_use_dense_path(Q, O):
         O.density_apply_kraus(rho, n, kraus, q)
     H.assert_close(st.state_elements(), rho)
     st.vec.close()
+
+
+def test_mixed_state_expectation_on_device(Q, O):
+    """MIXED-STATE-EXPECTATION (app/src/api/expectation.lisp:91-107): tr(Q rho) reduced on the device."""
+    n = 5
+    rng = np.random.default_rng(8)
+    qvm = Q.DensityQVM(n, seed=3)
+    qvm.set_noisy_gate("X", (1,), G.depolarizing_kraus_map(0.3))
+    qvm.load_program("H 0\nCNOT 0 1\nX 1\nRY(0.4) 2\nCNOT 2 4\nRX(1.3) 3").run()
+    rho = qvm.state.matrix_view()
+    a = rng.standard_normal((1 << n, 1 << n)) + 1j * rng.standard_normal((1 << n, 1 << n))
+    herm = a + a.conj().T
+    got = Q.mixed_state_expectation(qvm, herm)
+    want = np.trace(herm @ rho)
+    assert abs(got - want) <= 1e-12 * abs(want) + 1e-13
+    assert abs(got.imag) < 1e-12
+    z0 = np.kron(np.eye(1 << (n - 1)), np.diag([1.0, -1.0]))        # Z on qubit 0
+    assert abs(Q.mixed_state_expectation(qvm, z0) - (1 - 2 * O.density_prob_excited(np.ascontiguousarray(rho.ravel()), n, 0))) < 1e-12
+
+
+def test_unitary_qvm_matches_gate_products(Q, O):
+    """UNITARY-QVM (src/unitary-qvm.lisp:30-137): the pure-state path on 2n bits computes the matrix of a program."""
+    n = 4
+    prog = "H 0\nCNOT 0 2\nRZ(0.3) 1\nCPHASE(0.9) 1 3\nISWAP 2 3\nRX(1.1) 0"
+    u = Q.parsed_program_unitary_matrix(prog, n)
+    # column c of the matrix = the program applied to basis state c (oracle, one column at a time)
+    from qvm_b200.quil import parse_quil
+    program = parse_quil(prog)
+    circ = [(program.gate_matrix(x), x.qubits) for x in program.instructions]
+    for c in range(1 << n):
+        e = np.zeros(1 << n, dtype=np.complex128)
+        e[c] = 1.0
+        H.assert_close(u[:, c], H.run_oracle(e, circ))
+    np.testing.assert_allclose(u.conj().T @ u, np.eye(1 << n), atol=1e-13)
