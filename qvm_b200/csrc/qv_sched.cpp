@@ -605,9 +605,11 @@ void emit_round(BlobWriter& w, const std::vector<RoundOp>& rops, const std::vect
             }
             return nonreg + (any_reg ? (size_t)(reg_bits - (gate >= 0 ? 1 : 0)) : 0);
         };
-        // Several gates at once (one-qubit phases and CZ-like factors hanging off different register bits: layers of
-        // general gates) cost 2 FP64 instructions per amplitude PER GATE BIT; when the whole group fits ONE table
-        // (slot field + a few other tile-local bits) a single ungated lookup does it for 4.
+        // Several gates at once (one-qubit phases and CZ-like factors hanging off different register bits) cost 2 FP64
+        // instructions per amplitude PER GATE BIT; when the whole group fits ONE table (slot field + a few other tile-local
+        // bits) a single ungated lookup does it for 4.  Measured (gpurun_out/r2g_*): no gain on random 1q/CZ layers or the density
+        // circuit (5.47 vs 5.50 ms, 22.83 vs 22.85 ms) and a LOSS on the QFT (39.7 vs 37.1 ms per circuit: per-slot table loads
+        // replace the gated lookups that fuse with the butterflies), so it is off unless QVMCUDA_DIAG_SINGLE_CHUNK=1.
         {
             std::vector<int> all_l;
             bool any_plain = false;
@@ -619,7 +621,7 @@ void emit_round(BlobWriter& w, const std::vector<RoundOp>& rops, const std::vect
                 else if (std::find(gates_used.begin(), gates_used.end(), want[i]) == gates_used.end()) gates_used.push_back(want[i]);
             }
             const size_t gated_cost = 2 * gates_used.size() + (any_plain ? 4 : 0);
-            static const bool single_chunk = !(getenv("QVMCUDA_DIAG_SINGLE_CHUNK") && atoi(getenv("QVMCUDA_DIAG_SINGLE_CHUNK")) == 0);
+            static const bool single_chunk = getenv("QVMCUDA_DIAG_SINGLE_CHUNK") && atoi(getenv("QVMCUDA_DIAG_SINGLE_CHUNK")) == 1;
             if (single_chunk && gated_cost > 4 && eff_bits(all_l, -1) <= QV_MAX_CHUNK_BITS)
                 for (size_t i = 0; i < nf; i++) want[i] = -1;
         }
