@@ -519,14 +519,20 @@ def bench_sharded(args, rank: int, world: int, local_rank: int):
         def rstep():
             st.apply_gates(rgates, fuse=True)
 
+        # Every run starts from |0...0> in the canonical layout (set_zero_state resets it), so the schedule -- and the set of
+        # compiled passes -- is the same for every run: one untimed run compiles them, the timed one finds them in the cache.
+        def rrun():
+            st.set_zero_state()
+            rstep()
+
+        c5_prep = settle(rrun, 3)           # untimed
         st.set_zero_state()
-        c5_prep = settle(rstep, 6)          # untimed: compiles the passes
         p1, s1, ps1, pb1 = st.peer_steps, st.steps, st.peer_seconds, st.peer_bytes
         j_before = _lib.jit_stats()
         rdt = timed(rstep, 1)
         j_after = _lib.jit_stats()
         rp = st.steps - s1
-        c5 = {"workload": f"random 1q(RZ.RY.RZ)/CZ circuit, {args.c5_layers} layers on {n} qubits, seed 0", "gates": len(rgates),
+        c5 = {"workload": f"random 1q(RZ.RY.RZ)/CZ circuit, {args.c5_layers} layers on {n} qubits, seed 0, from |0...0>", "gates": len(rgates),
               "seconds_per_circuit": rdt, "gates_per_s": len(rgates) / rdt, "value_30q_equivalent": len(rgates) * 2.0 ** (n - 30) / rdt,
               "hbm_passes": rp, "exchange_passes": st.peer_steps - p1,
               "roofline": _sharded_roofline(L, rdt, rp, st.peer_steps - p1, st.peer_seconds - ps1, st.peer_bytes - pb1),
