@@ -32,6 +32,7 @@ struct JitKernel {
     CUfunction fn = nullptr;
     int threads = 0;
     int prog_bytes = 0;
+    int tma = 0;
 };
 
 namespace {
@@ -53,6 +54,9 @@ const char kHdrPrelude[] =
     ;
 const char kHdrKernel[] =
 #include "build/qv_jit_kernel.cuh.inc"
+    ;
+const char kHdrKernelTma[] =
+#include "build/qv_jit_kernel_tma.cuh.inc"
     ;
 
 // ------------------------------------------------------------------------------------------ NVRTC (dlopen)
@@ -109,6 +113,9 @@ struct Driver {
     CUresult (*launchKernel)(CUfunction, unsigned, unsigned, unsigned, unsigned, unsigned, unsigned, unsigned, CUstream, void**,
                              void**) = nullptr;
     CUresult (*getErrorString)(CUresult, const char**) = nullptr;
+    CUresult (*tensorMapEncodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                     const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                     CUtensorMapL2promotion, CUtensorMapFloatOOBfill) = nullptr;
     std::string error;
 };
 
@@ -126,6 +133,7 @@ Driver& driver() {
         get("cuFuncSetAttribute", (void**)&d.funcSetAttribute);
         get("cuLaunchKernel", (void**)&d.launchKernel);
         get("cuGetErrorString", (void**)&d.getErrorString);
+        get("cuTensorMapEncodeTiled", (void**)&d.tensorMapEncodeTiled);
     });
     return d;
 }
@@ -144,6 +152,7 @@ struct Entry {
     std::vector<char> cubin;
     std::string log;
     int threads = 0, prog_bytes = 0;
+    int tma = 0;
     std::map<int, std::unique_ptr<JitKernel>> loaded;     // device -> kernel
     bool load_failed = false;
 };
@@ -257,6 +266,8 @@ Pool& pool() {
     return *p;
 }
 
+constexpr int kTmaSmemBytes = 2 * 65536 + 1024;      // two tile buffers + slack for the 1024-byte alignment SWIZZLE_128B needs
+
 bool trace_on() {
     static const bool t = getenv("QVMCUDA_TRACE") != nullptr;
     return t;
@@ -292,7 +303,8 @@ JitKernel* load_locked(Entry& e, int device) {
     auto k = std::make_unique<JitKernel>();
     CUresult r = d.moduleLoadData(&k->mod, e.cubin.data());
     if (r == CUDA_SUCCESS) r = d.moduleGetFunction(&k->fn, k->mod, "qvj_kernel");
-    if (r == CUDA_SUCCESS) r = d.funcSetAttribute(k->fn, CU_FUNC_ATTRIBUTE_MAX_DYNAMIC_SHARED_SIZE_BYTES, 65536);
+    if (r == CUDA_SUCCESS)
+        r = d.funcSetAttribute(k->fn, CU_FUNC_ATTRIBUTE_MAX_DYNAMIC_SHARED_SIZE_BYTES, e.tma == 2 ? kTmaSmemBytes : 65536);
     if (r == CUDA_SUCCESS) r = d.funcSetAttribute(k->fn, CU_FUNC_ATTRIBUTE_PREFERRED_SHARED_MEMORY_CARVEOUT, 100);
     if (r != CUDA_SUCCESS) {
         e.load_failed = true;
@@ -302,6 +314,7 @@ JitKernel* load_locked(Entry& e, int device) {
     }
     k->threads = e.threads;
     k->prog_bytes = e.prog_bytes;
+    k->tma = e.tma;
     JitKernel* out = k.get();
     e.loaded[device] = std::move(k);
     return out;
@@ -315,10 +328,11 @@ bool jit_compile_cubin(const JitSource& src, std::vector<char>& cubin, std::stri
         log = n.error;
         return false;
     }
-    const char* hdr_src[] = {kHdrProgram, kHdrOps, kHdrCommon, kHdrPrelude, kHdrKernel};
-    const char* hdr_name[] = {"qv_program.h", "qv_ops.h", "qv_tile_common.cuh", "qv_jit_prelude.cuh", "qv_jit_kernel.cuh"};
+    const char* hdr_src[] = {kHdrProgram, kHdrOps, kHdrCommon, kHdrPrelude, kHdrKernel, kHdrKernelTma};
+    const char* hdr_name[] = {"qv_program.h", "qv_ops.h", "qv_tile_common.cuh", "qv_jit_prelude.cuh", "qv_jit_kernel.cuh",
+                              "qv_jit_kernel_tma.cuh"};
     nvrtcProgram prog = nullptr;
-    nvrtcResult r = n.create(&prog, src.text.c_str(), "qvj_pass.cu", 5, hdr_src, hdr_name);
+    nvrtcResult r = n.create(&prog, src.text.c_str(), "qvj_pass.cu", 6, hdr_src, hdr_name);
     if (r != NVRTC_SUCCESS) {
         log = std::string("nvrtcCreateProgram: ") + n.errstr(r);
         return false;
@@ -391,6 +405,7 @@ void jit_prepare(const std::vector<const Step*>& steps, int device, std::vector<
         auto e = std::make_shared<Entry>();
         e->threads = src.threads;
         e->prog_bytes = src.prog_bytes;
+        e->tma = src.tma;
         g_cache[src.sig] = e;
         ent[i] = e;
         lk.unlock();
@@ -492,9 +507,43 @@ const char* jit_launch(JitKernel* k, const JitLaunch& L) {
     const QvPeers* peers = L.peers;
     const qvc* tables = L.tables;
     qvc* alt = L.alt_own;
-    void* params[4] = {prog.data(), const_cast<QvPeers*>(peers), &tables, &alt};
-    const CUresult r = driver().launchKernel(k->fn, (unsigned)L.grid, 1, 1, (unsigned)k->threads, 1, 1, (unsigned)L.smem, (CUstream)L.stream,
-                                             params, nullptr);
+    CUresult r;
+    if (k->tma) {
+        // the tile as a box of a 5-d view of this device's amplitudes (QvTmaGeom: geometry is data, not part of the kernel)
+        QvPassHeader h;
+        std::memcpy(&h, L.blob, sizeof(h));
+        QvTmaGeom geom;
+        if (!jit_tma_geometry(h, geom)) return "pass geometry does not fit a tensor map";
+        alignas(64) CUtensorMap tmap;
+        cuuint64_t gdim[5] = {16, 1, 1, 1, 1}, gstride[4] = {128, 128, 128, 128};
+        cuuint32_t box[5] = {16, 1, 1, 1, 1}, estride[5] = {1, 1, 1, 1, 1};
+        const cuuint64_t total_bytes = (cuuint64_t)16 << h.n_local_bits;
+        for (int i = 0; i < 4; i++) {
+            if (geom.len[i]) {
+                gdim[i + 1] = (cuuint64_t)1 << geom.len[i];
+                gstride[i] = (cuuint64_t)16 << geom.start[i];
+                box[i + 1] = geom.is_tile[i] ? (cuuint32_t)1 << geom.len[i] : 1u;
+            } else {
+                gstride[i] = total_bytes;      // unused dimension of extent 1
+            }
+        }
+        void* base = (void*)peers->base[(h.fixed_bits >> h.n_local_bits) & (QV_MAX_PEERS - 1)];
+        r = driver().tensorMapEncodeTiled(&tmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 5, base, gdim, gstride, box, estride,
+                                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) {
+            err = "cuTensorMapEncodeTiled: " + cu_err(r);
+            return err.c_str();
+        }
+        void* params[6] = {prog.data(), const_cast<QvPeers*>(peers), &tables, &alt, &tmap, &geom};
+        const unsigned grid = k->tma == 2 ? (unsigned)std::min<uint64_t>(h.n_tiles, (uint64_t)L.sm_count) : (unsigned)L.grid;
+        const unsigned smem = k->tma == 2 ? (unsigned)kTmaSmemBytes : (unsigned)L.smem;
+        r = driver().launchKernel(k->fn, grid, 1, 1, (unsigned)k->threads, 1, 1, smem, (CUstream)L.stream, params, nullptr);
+    } else {
+        void* params[4] = {prog.data(), const_cast<QvPeers*>(peers), &tables, &alt};
+        r = driver().launchKernel(k->fn, (unsigned)L.grid, 1, 1, (unsigned)k->threads, 1, 1, (unsigned)L.smem, (CUstream)L.stream, params,
+                                  nullptr);
+    }
     if (r != CUDA_SUCCESS) {
         err = cu_err(r);
         return err.c_str();

@@ -14,7 +14,7 @@
 
 #include "qv_sched.h"
 
-#define QVJIT_VERSION "qvjit-5"
+#define QVJIT_VERSION "qvjit-7"
 
 struct QvPeers;
 struct qvc;
@@ -29,10 +29,18 @@ struct JitSource {
     int mode = 0;           // 0 local pass, 2 pull pass
     int prog_bytes = 0;     // size of the kernel's control-program parameter
     int threads = 0;
+    int tma = 0;            // 0 LDGSTS tile loads; 1 classic kernel with one cp.async.bulk.tensor per tile; 2 persistent double-buffered
+                            // kernel fed by cp.async.bulk.tensor (1 and 2 need a tensor map at launch)
 };
 
 // Front end (no CUDA needed; also used by the test emulator, which compiles the text for the host).
+// variant bits: 1 rolled group loop, 2 two CTAs per SM, 4 fences between micro-ops (experiments), 8 persistent TMA-fed kernel,
+// 16 classic kernel with the tile loaded by one tensor copy (8 / 16: local passes whose tile is a box of a <= 5-dimensional
+// view of the state; other passes fall back to the LDGSTS loads).
 JitSource jit_generate(const Step& st, int variant = 0);
+
+// Tile geometry for the tensor-memory accelerator; false when the tile's bit runs do not fit five dimensions.
+bool jit_tma_geometry(const QvPassHeader& h, QvTmaGeom& geom);
 
 // NVRTC: source -> cubin for sm_100a.  Works without a GPU (build-time prewarming, CPU tests).  log receives the
 // compiler's output (ptxas -v statistics included).
@@ -57,6 +65,7 @@ struct JitLaunch {
     size_t blob_bytes;
     int grid;
     size_t smem;
+    int sm_count;
     void* stream;
     const QvPeers* peers;
     const qvc* tables;

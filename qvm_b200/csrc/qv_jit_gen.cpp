@@ -104,6 +104,31 @@ std::string index_expr(const QvUop& u, const uint8_t* blob) {
 
 }  // namespace
 
+bool jit_tma_geometry(const QvPassHeader& h, QvTmaGeom& geom) {
+    std::memset(&geom, 0, sizeof(geom));
+    if (h.T != QV_MAX_TILE_BITS || h.uses_peers || h.pull) return false;
+    uint64_t tilemask = 0;
+    for (uint32_t k = 0; k < h.n_tile_segs; k++)
+        for (uint32_t b = 0; b < h.tile_segs[k].len; b++) tilemask |= 1ull << (h.tile_segs[k].dst + b);
+    if ((tilemask & 15ull) != 15ull) return false;                  // the low four bits are always inside
+    const uint32_t n = h.n_local_bits;
+    uint32_t runs = 0;
+    uint32_t b = 3;
+    while (b < n) {
+        const bool in = (tilemask >> b) & 1ull;
+        uint32_t e = b;
+        while (e < n && (((tilemask >> e) & 1ull) != 0) == in && (!in || e - b < 8)) e++;     // a box side holds <= 256
+        if (runs == 4) return false;
+        geom.start[runs] = (uint8_t)b;
+        geom.len[runs] = (uint8_t)(e - b);
+        geom.is_tile[runs] = in ? 1 : 0;
+        runs++;
+        b = e;
+    }
+    geom.n_runs = runs;
+    return true;
+}
+
 JitSource jit_generate(const Step& st, int variant) {
     JitSource js;
     if (st.kind != Step::TILE) {
@@ -127,8 +152,13 @@ JitSource jit_generate(const Step& st, int variant) {
         return js;
     }
     const int NS = 1 << M;
-    const int threads = 1 << h.threads_log2;
+    QvTmaGeom geom;
+    const bool tma_ok = M == 3 && !h.pull && !wants_wide_swizzle(h) && jit_tma_geometry(h, geom);
+    const bool tma = (variant & 8) != 0 && tma_ok;                         // persistent, double-buffered
+    const bool tma_load = !tma && (variant & 16) != 0 && tma_ok;           // classic kernel, tile loaded by one tensor copy
+    const int threads = tma ? 512 : (1 << h.threads_log2);
     const int iters = (4096 >> M) / threads;
+    js.tma = tma ? 2 : tma_load ? 1 : 0;
     const QvRound* rounds = reinterpret_cast<const QvRound*>(blob + h.off_rounds);
     const QvUop* uops = reinterpret_cast<const QvUop*>(blob + h.off_uops);
     js.mode = h.pull ? 2 : 0;
@@ -145,6 +175,8 @@ JitSource jit_generate(const Step& st, int variant) {
     o("#define QVJ_M %d\n#define QVJ_THREADS %d\n#define QVJ_MIN_CTAS %d\n#define QVJ_MODE %d\n#define QVJ_PROG_BYTES %d\n", M, threads,
       min_ctas, js.mode, js.prog_bytes);
     const bool wide = wants_wide_swizzle(h);
+    if (tma) o("#define QVJ_TMA 1\n");
+    if (tma_load) o("#define QVJ_TMA_LOAD 1\n");
     o("#define QVJ_HAS_SCALE %d\n#define QVJ_STORE_PERM %d\n#define QVJ_HAS_TABLES %d\n#define QVJ_WIDE_SWZ %d\n", h.has_scale ? 1 : 0,
       h.store_perm ? 1 : 0, (h.n_sources | h.n_preds | h.n_slice_entries) ? 1 : 0, wide ? 1 : 0);
     o("#include \"qv_jit_prelude.cuh\"\n\n");
@@ -266,7 +298,7 @@ JitSource jit_generate(const Step& st, int variant) {
       "                               const qvc* s_slice, const uint8_t* s_pred) {\n    switch (r) {\n");
     for (uint32_t r = 0; r < h.n_rounds; r++) o("        case %u: qvj_round_%u(tile, tid, blob, tables, s_slice, s_pred); break;\n", r, r);
     o("        default: break;\n    }\n}\n#endif\n");
-    o("#include \"qv_jit_kernel.cuh\"\n");
+    o("#include \"%s\"\n", tma ? "qv_jit_kernel_tma.cuh" : "qv_jit_kernel.cuh");
     js.text = std::move(o.s);
     js.sig = fnv1a(js.text, fnv1a(QVJIT_VERSION));
     js.ok = true;

@@ -20,13 +20,44 @@
 
 struct QvjProg { uint8_t bytes[QVJ_PROG_BYTES]; };
 
+#if !defined(QVJ_TMA_LOAD)
+#define QVJ_TMA_LOAD 0
+#endif
+#if QVJ_TMA_LOAD
+// Variant: the tile is loaded by the tensor-memory accelerator -- ONE cp.async.bulk.tensor per tile, issued by one thread,
+// completion on an mbarrier -- instead of 16 LDGSTS per thread; everything else as below (three CTAs per SM).  See
+// qv_jit_kernel_tma.cuh for the tile-as-a-box view and why SWIZZLE_128B reproduces qv_swz.
+struct alignas(64) QvjTensorMap { unsigned long long opaque[16]; };      // CUtensorMap
+__device__ __forceinline__ uint32_t qvj_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void qvj_mbar_wait(uint32_t mbar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "QVJ_WAIT:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra QVJ_DONE;\n"
+        "bra QVJ_WAIT;\n"
+        "QVJ_DONE:\n"
+        "}\n" ::"r"(mbar), "r"(parity) : "memory");
+}
+#endif
+
 extern "C" __global__ void __launch_bounds__(QVJ_THREADS, QVJ_MIN_CTAS)
 qvj_kernel(const __grid_constant__ QvjProg prog, const __grid_constant__ QvPeers peers,
-           const qvc* __restrict__ tables, qvc* __restrict__ alt_own) {
+           const qvc* __restrict__ tables, qvc* __restrict__ alt_own
+#if QVJ_TMA_LOAD
+           , const __grid_constant__ QvjTensorMap tmap, const __grid_constant__ QvTmaGeom geom
+#endif
+           ) {
     constexpr bool PULL = QVJ_MODE == 2;
     constexpr int THREADS = QVJ_THREADS;
     constexpr int ITERS = 4096 / THREADS;
+#if QVJ_TMA_LOAD
+    extern __shared__ __align__(1024) uint8_t qv_smem_raw[];      // SWIZZLE_128B wants the box on a 1024-byte boundary
+    __shared__ __align__(8) unsigned long long s_mbar;
+#else
     extern __shared__ __align__(16) uint8_t qv_smem_raw[];
+#endif
     qvc* tile = reinterpret_cast<qvc*>(qv_smem_raw);
 #if QVJ_HAS_TABLES
     __shared__ qvc s_slice[QV_SLICE_ENTRIES];
@@ -66,11 +97,38 @@ qvj_kernel(const __grid_constant__ QvjProg prog, const __grid_constant__ QvPeers
     const double out_scale = h->out_scale;
 #endif
 
+#if QVJ_TMA_LOAD
+    const uint32_t mbar = qvj_smem_u32(&s_mbar);
+    if (tid == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(mbar));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    uint32_t tile_no = 0;
+#endif
+
     for (uint64_t t = blockIdx.x; t < n_tiles; t += gridDim.x) {
         const uint64_t base = qv_gather(t, h->base_segs, h->n_base_segs) | fixed_bits;
         const uint64_t pbase = (base | glo) & local_mask;
 
         // ---- HBM -> shared memory (asynchronous 16-byte copies, all in flight at once)
+#if QVJ_TMA_LOAD
+        if (tid == 0) {
+            const uint64_t lbase = base & local_mask;
+            int32_t c1 = geom.is_tile[0] ? 0 : (int32_t)((lbase >> geom.start[0]) & ((1ull << geom.len[0]) - 1ull));
+            int32_t c2 = geom.is_tile[1] ? 0 : (int32_t)((lbase >> geom.start[1]) & ((1ull << geom.len[1]) - 1ull));
+            int32_t c3 = geom.is_tile[2] ? 0 : (int32_t)((lbase >> geom.start[2]) & ((1ull << geom.len[2]) - 1ull));
+            int32_t c4 = geom.is_tile[3] ? 0 : (int32_t)((lbase >> geom.start[3]) & ((1ull << geom.len[3]) - 1ull));
+            // the previous tile's write-back read this buffer through the generic proxy (it ended with a barrier)
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mbar), "r"(65536u) : "memory");
+            asm volatile(
+                "cp.async.bulk.tensor.5d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5, %6}], [%7];" ::"r"(
+                    qvj_smem_u32(tile)),
+                "l"(&tmap), "r"(0), "r"(c1), "r"(c2), "r"(c3), "r"(c4), "r"(mbar)
+                : "memory");
+        }
+#else
         if (!PULL) {
             const char* tsrc = reinterpret_cast<const char*>(own + pbase);
 #pragma unroll
@@ -84,6 +142,7 @@ qvj_kernel(const __grid_constant__ QvjProg prog, const __grid_constant__ QvPeers
             }
         }
         asm volatile("cp.async.commit_group;" ::: "memory");
+#endif
 
 #if QVJ_HAS_TABLES
         {   // per-tile tables, built while the copies fly (same construction as the interpreter kernel)
@@ -102,8 +161,16 @@ qvj_kernel(const __grid_constant__ QvjProg prog, const __grid_constant__ QvPeers
             }
         }
 #endif
+#if QVJ_TMA_LOAD
+        qvj_mbar_wait(mbar, tile_no & 1u);
+        tile_no++;
+#if QVJ_HAS_TABLES
+        __syncthreads();      // the slices were written by other threads
+#endif
+#else
         asm volatile("cp.async.wait_group 0;" ::: "memory");
         __syncthreads();
+#endif
 
         // ---- the rounds: straight-line code emitted by the pass compiler
         QVJ_RUN_ROUNDS(tile, tid, blob, tables, s_slice, s_pred)

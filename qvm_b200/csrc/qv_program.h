@@ -201,6 +201,19 @@ struct QvPassHeader {
     uint64_t hi_src[32];            // S(hi_off[i])
 };
 
+struct qvc;
+struct QvPeers {
+    qvc* base[QV_MAX_PEERS];   // shard base pointer of every rank (own pointer at [rank])
+};
+
+// Geometry of a tile for the tensor-memory accelerator (qv_jit_kernel_tma.cuh): dimension 0 of the 5-d view = index bits 0..2
+// (eight amplitudes = 16 doubles = 128 bytes); dimensions 1..4 = runs of consecutive index bits >= 3 that are all inside
+// (is_tile) or all outside the tile; unused dimensions have len 0.
+struct QvTmaGeom {
+    uint8_t start[4], len[4], is_tile[4];
+    uint32_t n_runs;
+};
+
 // A k>=3 dense gate runs as its own pass through the generic kernel.
 struct QvBigGate {
     uint32_t k;

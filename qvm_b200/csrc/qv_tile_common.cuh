@@ -6,9 +6,6 @@
 #endif
 
 #include "qv_ops.h"
-struct QvPeers {
-    qvc* base[QV_MAX_PEERS];   // shard base pointer of every rank (own pointer at [rank])
-};
 
 // Streaming 128-bit accesses that do not allocate in L1: L1 is kept for the tile
 // program (ops, matrices, diagonal tables), which every CTA re-reads.

@@ -194,6 +194,7 @@ int launch_tile_p(qvmcuda_state* s, const qv::Step& st, const QvPassHeader& h, c
         J.blob_bytes = L.blob_bytes;
         J.grid = L.grid;
         J.smem = L.smem;
+        J.sm_count = s->sm_count;
         J.stream = (void*)s->stream;
         J.peers = L.peers;
         J.tables = L.tables;
