@@ -133,7 +133,14 @@ Driver& driver() {
         get("cuFuncSetAttribute", (void**)&d.funcSetAttribute);
         get("cuLaunchKernel", (void**)&d.launchKernel);
         get("cuGetErrorString", (void**)&d.getErrorString);
-        get("cuTensorMapEncodeTiled", (void**)&d.tensorMapEncodeTiled);
+        {   // optional: without it the tiles are loaded with LDGSTS
+            const std::string keep = d.error;
+            get("cuTensorMapEncodeTiled", (void**)&d.tensorMapEncodeTiled);
+            if (d.error != keep) {
+                d.error = keep;
+                d.tensorMapEncodeTiled = nullptr;
+            }
+        }
     });
     return d;
 }
@@ -273,15 +280,22 @@ bool trace_on() {
     return t;
 }
 
-// Generator variant of a step: QVMCUDA_JIT_VARIANT forces one; otherwise passes whose FP64 work dominates (layers of dense
-// gates: bound by the FP64 pipe, not by HBM) get two CTAs per SM with up to 128 registers per thread -- measured 6 % faster
-// on 25-qubit random layers (gpurun_out/r2b_configs_v{0,2}.jsonl) -- and everything else three CTAs with 80.
+// Generator variant of a step: QVMCUDA_JIT_VARIANT forces one; otherwise
+//  * the tile is loaded by ONE tensor copy (bit 16) wherever the driver offers cuTensorMapEncodeTiled and the tile is a box of a
+//    5-d view of the state -- measured 36.8 vs 37.1 ms per QFT-30, 3 % fewer instructions (gpurun_out/r2j_*); the persistent
+//    double-buffered TMA kernel (bit 8) lost: 53.0 ms, one 16-warp CTA per SM cannot hide the latencies of the rounds that three
+//    independent CTAs hide (profiles/r02_tma_variants.md), so it is never chosen automatically;
+//  * passes whose FP64 work dominates (layers of dense gates: bound by the FP64 pipe, not by HBM) get two CTAs per SM with up to
+//    128 registers per thread (bit 2) -- 6 % faster on 25-qubit random layers (gpurun_out/r2b_configs_v{0,2}.jsonl) -- everything
+//    else three CTAs with 80.
 int variant_of(const Step& st) {
     static const int forced = getenv("QVMCUDA_JIT_VARIANT") ? atoi(getenv("QVMCUDA_JIT_VARIANT")) : -1;
     if (forced >= 0) return forced;
     Tape one;
     one.steps.push_back(st);
-    return tape_cost(one) > 180.0 ? 2 : 0;
+    int v = tape_cost(one) > 180.0 ? 2 : 0;
+    if (driver().error.empty() && driver().tensorMapEncodeTiled) v |= 16;
+    return v;
 }
 
 uint32_t real_uops(const Step& st) {
@@ -460,7 +474,12 @@ void jit_precompile(const std::vector<const Step*>& steps, int& n_eligible, int&
     std::condition_variable cv;
     for (const Step* st : steps) {
         if (st->kind != Step::TILE || real_uops(*st) < jit_min_uops()) continue;
-        JitSource src = jit_generate(*st, variant_of(*st));
+        // without a driver (build container) the variant the GPU box will pick is unknown: compile with and without the
+        // single-copy tile load
+        std::vector<int> variants = {variant_of(*st)};
+        if (!(variants[0] & 16) && !getenv("QVMCUDA_JIT_VARIANT")) variants.push_back(variants[0] | 16);
+        for (int v : variants) {
+        JitSource src = jit_generate(*st, v);
         if (!src.ok || seen.count(src.sig)) continue;
         seen[src.sig] = true;
         n_eligible++;
@@ -485,6 +504,7 @@ void jit_precompile(const std::vector<const Step*>& steps, int& n_eligible, int&
             }
             cv.notify_all();
         });
+        }
     }
     std::unique_lock<std::mutex> lk(mu);
     for (auto& j : jobs) {

@@ -14,7 +14,7 @@
 
 #include "qv_sched.h"
 
-#define QVJIT_VERSION "qvjit-7"
+#define QVJIT_VERSION "qvjit-8"
 
 struct QvPeers;
 struct qvc;
