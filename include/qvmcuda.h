@@ -182,6 +182,12 @@ int qvmcuda_shard_attach_alt(qvmcuda_state *s, const uint8_t *handles /* world*6
 #define QVMCUDA_STEP_REMAP 2u
 int qvmcuda_shard_compile(qvmcuda_state *s, int n_gates, const int32_t *ks, const int32_t *qubits,
                           const double *matrices, uint32_t flags, qvmcuda_tape **out);
+/* The same schedule WITHOUT a device: what rank RANK of WORLD ranks would run for this gate list from the layout l2p
+ * (n_total = log2(shard length) + log2(world) entries; overwritten with the layout the tape leaves behind).  remap_pull
+ * says whether the ranks will have the alternate shard buffer.  For planning and for filling the pass-compiler's kernel
+ * cache ahead of time (qvmcuda_tape_jit_precompile); such a tape cannot be run. */
+int qvmcuda_shard_plan(int n_total, int world, int rank, int remap_pull, int32_t *l2p, int n_gates, const int32_t *ks,
+                       const int32_t *qubits, const double *matrices, uint32_t flags, qvmcuda_tape **out);
 int qvmcuda_tape_num_steps(qvmcuda_tape *t, int *n_steps);
 int qvmcuda_tape_step_flags(qvmcuda_tape *t, int step, uint32_t *flags);
 /* info[0] = step flags, [1] = kind (0 tile pass, 1 generic dense gate, 2 stand-alone pull remap), [2] = atoms in the step,

@@ -71,6 +71,8 @@ _SIGS = {
     "qvmcuda_shard_export_alt": [C.c_void_p, C.c_void_p],
     "qvmcuda_shard_attach_alt": [C.c_void_p, C.c_void_p],
     "qvmcuda_shard_compile": [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.POINTER(C.c_void_p)],
+    "qvmcuda_shard_plan": [C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32,
+                           C.POINTER(C.c_void_p)],
     "qvmcuda_tape_num_steps": [C.c_void_p, C.POINTER(C.c_int)],
     "qvmcuda_tape_step_flags": [C.c_void_p, C.c_int, C.POINTER(C.c_uint32)],
     "qvmcuda_tape_step_info": [C.c_void_p, C.c_int, C.c_void_p],

@@ -17,6 +17,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <sstream>
+#include <deque>
 #include <stdexcept>
 
 namespace qv {
@@ -1321,6 +1322,27 @@ Tape compile(const std::vector<Gate>& gates, int n_bits, const CompileOptions& o
         if (getenv("QV_SCHED_DEBUG")) fprintf(stderr, "euler split: cost fused %.1f split %.1f\n", cf, cs);
         return cs < cf ? split : fused;
     }
+    if (opt.fuse && opt.route_swaps < 0) {
+        // Exact SWAP gates either run where they stand (folded into a pass's write-back when they trail it, else a pass of
+        // their own) or are absorbed as relabelings whose physical permutation is spread over the spare tile slots of the
+        // gate passes (route_swaps = 1).  Both tapes leave the state in the same layout; keep the cheaper one.
+        CompileOptions o = opt;
+        o.route_swaps = 0;
+        const int nl = opt.n_local_bits > 0 ? opt.n_local_bits : n_bits;
+        bool any = false;
+        for (const Gate& g : gates)
+            if (is_exact_swap(g)) any = true;
+        for (size_t q = 0; q < l2p_in.size(); q++)
+            if (l2p_in[q] != (int)q) any = true;
+        if (nl != n_bits || opt.absorb_swaps || !any) return compile(gates, n_bits, o, l2p_in);
+        Tape plain = compile(gates, n_bits, o, l2p_in);
+        o.route_swaps = 1;
+        Tape routed = compile(gates, n_bits, o, l2p_in);
+        const double cp = tape_cost(plain), cr = tape_cost(routed);
+        if (getenv("QV_SCHED_DEBUG")) fprintf(stderr, "swap routing: cost plain %.1f (%zu steps) routed %.1f (%zu steps)\n", cp,
+                                              plain.steps.size(), cr, routed.steps.size());
+        return cr < cp ? routed : plain;
+    }
     Tape tape;
     tape.n_bits = n_bits;
     std::vector<int> w2p = l2p_in;          // wire q starts as logical qubit q
@@ -1355,6 +1377,13 @@ Tape compile(const std::vector<Gate>& gates, int n_bits, const CompileOptions& o
     const int cap_high = geo.T - geo.lmin;
     Layout lay{&w2p};
 
+    // Swap routing (single device, fused): exact SWAP gates are absorbed as relabelings and the physical permutation that brings
+    // the state back to the canonical layout (logical qubit q on physical bit q) is executed for free by the write-back of the
+    // gate passes: a pass may permute the index bits inside its tile, so a wire whose final position lies in the tile goes there,
+    // and a pass reserves a tile slot for the final position of a wire it mixes while there is room.  What is left at the end
+    // (if anything) takes permutation-only passes.  The 30-qubit QFT runs in 5 passes this way instead of 4 + 2.
+    const bool routing = opt.fuse && opt.route_swaps > 0 && g_bits == 0 && !opt.absorb_swaps && opt.store_perm;
+
     // 1. analyse gates into atoms (wire space)
     std::vector<Atom> atoms;
     std::vector<int> gate_of;
@@ -1362,7 +1391,7 @@ Tape compile(const std::vector<Gate>& gates, int n_bits, const CompileOptions& o
         const Gate& g = gates[gi];
         for (int q : g.qubits)
             if (q < 0 || q >= n_bits) throw std::runtime_error("gate qubit out of range");
-        if (opt.absorb_swaps && is_exact_swap(g)) {
+        if ((opt.absorb_swaps || routing) && is_exact_swap(g)) {
             std::swap(wire_of[g.qubits[0]], wire_of[g.qubits[1]]);
             continue;
         }
@@ -1473,6 +1502,99 @@ Tape compile(const std::vector<Gate>& gates, int n_bits, const CompileOptions& o
     std::vector<const Atom*> pending;
     for (const Atom& a : atoms) pending.push_back(&a);
 
+    // ---- swap routing helpers
+    std::vector<int> dest(n_bits, -1);      // final physical bit of every wire: logical qubit q ends on bit q
+    if (routing)
+        for (int q = 0; q < n_bits; q++) dest[wire_of[q]] = q;
+    std::deque<Atom> route_atoms;           // synthesised SWAPs (addresses must stay valid until the pass is built)
+    auto wire_at = [&]() {
+        std::vector<int> p2w(n_bits, -1);
+        for (int wq = 0; wq < n_bits; wq++) p2w[w2p[wq]] = wq;
+        return p2w;
+    };
+    // Spend the spare slots of a tile (bit set tb) on final positions: first those of wires already inside the tile (following
+    // the chain of displaced wires; a slot that brings two wires home goes first), then -- seeds -- whole 2-cycles outside it.
+    auto add_route_slots = [&](uint64_t tb, bool seeds) {
+        const std::vector<int> p2w = wire_at();
+        auto spare = [&]() { return cap_high - popc(tb & ~lowmask); };
+        for (;;) {
+            int best = -1, best_score = 0;
+            for (int p = 0; p < n_bits && spare() > 0; p++) {
+                if (!(tb >> p & 1)) continue;
+                const int d = dest[p2w[p]];
+                if (tb >> d & 1) continue;
+                const int score = (tb >> dest[p2w[d]] & 1) ? 2 : 1;
+                if (score > best_score) {
+                    best_score = score;
+                    best = d;
+                }
+            }
+            if (best >= 0) {
+                tb |= 1ull << best;
+                continue;
+            }
+            if (!seeds || spare() < 2) break;
+            int seed = -1;
+            for (int p = 0; p < n_bits && seed < 0; p++)
+                if (!(tb >> p & 1) && dest[p2w[p]] != p) seed = p;
+            if (seed < 0) break;
+            tb |= 1ull << seed;
+        }
+        for (int b = 0; b < geo.n_local && popc(tb) < geo.T; b++) tb |= 1ull << b;    // pad like build_tile_step
+        return tb;
+    };
+    // The write-back permutation of a pass whose tile holds the bits tb: every wire inside the tile whose final position is
+    // inside too goes there; a wire that loses its place takes the lowest free one (a wire on an always-resident low bit is
+    // inside every later tile).  Appends the SWAP atoms that realise it to `out` and returns the new position of every wire.
+    auto route_in_tile = [&](uint64_t tb, std::vector<const Atom*>& out) {
+        const std::vector<int> p2w = wire_at();
+        std::vector<int> newpos(w2p), ends_at(n_bits, -1);
+        std::vector<int> pos;
+        for (int b = 0; b < n_bits; b++)
+            if (tb >> b & 1) pos.push_back(b);
+        std::vector<char> seated(n_bits, 0);
+        for (int p : pos) {
+            const int wq = p2w[p];
+            if (tb >> dest[wq] & 1) {
+                ends_at[dest[wq]] = wq;
+                seated[wq] = 1;
+            }
+        }
+        for (int p : pos)
+            if (!seated[p2w[p]] && ends_at[p] < 0) {
+                ends_at[p] = p2w[p];
+                seated[p2w[p]] = 1;
+            }
+        for (int p : pos) {
+            const int wq = p2w[p];
+            if (seated[wq]) continue;
+            for (int f : pos)
+                if (ends_at[f] < 0) {
+                    ends_at[f] = wq;
+                    seated[wq] = 1;
+                    break;
+                }
+        }
+        // transpositions of tile positions, applied in order: afterwards position q holds what was at w2p[ends_at[q]]
+        std::vector<int> cur(n_bits);
+        for (int b = 0; b < n_bits; b++) cur[b] = b;
+        for (int q : pos) {
+            const int want = w2p[ends_at[q]];
+            if (cur[q] == want) continue;
+            int q2 = -1;
+            for (int x : pos)
+                if (cur[x] == want) q2 = x;
+            Atom a = swap_proto;
+            a.tw = {p2w[q], p2w[q2]};
+            a.mix = a.touch = (1ull << p2w[q]) | (1ull << p2w[q2]);
+            route_atoms.push_back(std::move(a));
+            out.push_back(&route_atoms.back());
+            std::swap(cur[q], cur[q2]);
+        }
+        for (int q : pos) newpos[ends_at[q]] = q;
+        return newpos;
+    };
+
     // Sharded states never return to the canonical layout (the host maps indices through the layout), so an exact
     // SWAP gate with an operand on a rank bit is a pure relabeling: the two wires exchange their physical bits
     // and nothing crosses NVLink.  Only the atom at the head of the queue may do this (every earlier atom has been
@@ -1565,7 +1687,12 @@ Tape compile(const std::vector<Gate>& gates, int n_bits, const CompileOptions& o
                 if (a->kind == Atom::BIG) blocked = true;
                 else if (a->kind == Atom::DENSE) {
                     const uint64_t pm = phys_mask(a->mix);
-                    if (fits(targets | pm)) targets |= pm;
+                    uint64_t em = pm;       // routing: with the final positions of the wires it mixes, while there is room
+                    if (routing)
+                        for (int wq = 0; wq < n_bits; wq++)
+                            if (a->mix >> wq & 1) em |= 1ull << dest[wq];
+                    if (fits(targets | em)) targets |= em;
+                    else if (fits(targets | pm)) targets |= pm;
                     else blocked = true;
                 }
             }
@@ -1601,6 +1728,15 @@ Tape compile(const std::vector<Gate>& gates, int n_bits, const CompileOptions& o
         // atoms and send the rest back (original order restored: pointers into `atoms` are ordered).
         for (;;) {
             try {
+                if (routing) {
+                    const uint64_t tb = add_route_slots(targets | lowmask, false);
+                    std::vector<const Atom*> with_swaps = in_pass;
+                    const std::vector<int> newpos = route_in_tile(tb, with_swaps);
+                    tape.steps.push_back(build_tile_step(with_swaps, tb, geo, lay));
+                    tape.steps.back().n_gates = (int)in_pass.size();
+                    tape.n_routed += (int)(with_swaps.size() - in_pass.size());
+                    w2p = newpos;
+                } else
                 tape.steps.push_back(build_tile_step(in_pass, targets, geo, lay));
                 break;
             } catch (const std::length_error&) {
@@ -1616,6 +1752,20 @@ Tape compile(const std::vector<Gate>& gates, int n_bits, const CompileOptions& o
         }
         pending.swap(deferred);
     }
+    // routing: whatever is not home yet takes permutation-only passes (every one places at least one wire)
+    while (routing) {
+        bool home = true;
+        for (int wq = 0; wq < n_bits; wq++) home = home && w2p[wq] == dest[wq];
+        if (home) break;
+        const uint64_t tb = add_route_slots(lowmask, true);
+        std::vector<const Atom*> swaps;
+        const std::vector<int> newpos = route_in_tile(tb, swaps);
+        if (swaps.empty()) throw std::runtime_error("scheduler bug: swap routing makes no progress");
+        tape.steps.push_back(build_tile_step(swaps, tb, geo, lay));
+        tape.steps.back().n_gates = 0;
+        tape.n_routed += (int)swaps.size();
+        w2p = newpos;
+    }
     tape.l2p.resize(n_bits);
     for (int q = 0; q < n_bits; q++) tape.l2p[q] = w2p[wire_of[q]];
     fuse_pulls(tape, opt);
@@ -1626,7 +1776,8 @@ std::string describe(const Tape& t) {
     std::ostringstream os;
     os << "tape: n_bits=" << t.n_bits << " gates=" << t.n_gates << " atoms=" << t.n_atoms
        << " steps=" << t.steps.size() << (t.n_fused ? " matrix_merges=" + std::to_string(t.n_fused) : std::string())
-       << (t.n_split ? " euler_splits=" + std::to_string(t.n_split) : std::string()) << (t.n_relabeled ? " relabeled_swaps=" + std::to_string(t.n_relabeled) : std::string()) << "\n";
+       << (t.n_split ? " euler_splits=" + std::to_string(t.n_split) : std::string()) << (t.n_relabeled ? " relabeled_swaps=" + std::to_string(t.n_relabeled) : std::string())
+       << (t.n_routed ? " routed_transpositions=" + std::to_string(t.n_routed) : std::string()) << "\n";
     for (size_t i = 0; i < t.steps.size(); i++) {
         const Step& s = t.steps[i];
         if (s.kind == Step::BIG) {

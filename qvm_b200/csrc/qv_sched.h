@@ -40,6 +40,9 @@ struct CompileOptions {
     int euler_split = 0;         // complex 1q unitaries as diag . real rotation . diag: 1 always, 0 never, -1 = whichever tape the
                                  // cost model prefers.  Off: measured slower on B200 (25-qubit random layers 6.3 vs 5.5 ms,
                                  // gpurun_out/r2c_configs_euler*.jsonl) -- the extra table lookups cost more than the FP64 saved
+    int route_swaps = -1;        // single device, fused: absorb exact SWAP gates as relabelings and execute the permutation back to the
+                                 // canonical layout in the write-back of the gate passes (spare tile slots): 1 always, 0 never (SWAPs
+                                 // run where they stand), -1 = whichever tape the cost model prefers
     bool remap_pull = false;     // remaps as out-of-place pulls into the alternate buffer (needs 2x shard memory)
 };
 
@@ -64,6 +67,7 @@ struct Tape {
     int n_fused = 0;             // atoms merged away by host-side matrix fusion
     int n_split = 0;             // complex 1q unitaries written as diag . rotation . diag (Euler split)
     int n_splittable = 0;        // ... that could have been
+    int n_routed = 0;            // transpositions of index bits executed by write-backs on behalf of absorbed SWAP gates (swap routing)
     int n_relabeled = 0;         // SWAP gates on rank bits executed as relabelings (sharded)
 };
 

@@ -344,6 +344,8 @@ qv::CompileOptions make_options(const qvmcuda_state* s, uint32_t flags) {
     opt.euler_split = euler;
     static const int fuse_mats = getenv("QVMCUDA_FUSE_MATRICES") ? atoi(getenv("QVMCUDA_FUSE_MATRICES")) : 1;
     opt.fuse_matrices = fuse_mats != 0;
+    static const int route = getenv("QVMCUDA_ROUTE_SWAPS") ? atoi(getenv("QVMCUDA_ROUTE_SWAPS")) : -1;   // 1 always, 0 never, -1 cost model
+    opt.route_swaps = route;
     if (s) {
         opt.rank = s->rank;
         opt.n_local_bits = s->n_bits;
@@ -721,6 +723,37 @@ int qvmcuda_shard_compile(qvmcuda_state* s, int n_gates, const int32_t* ks, cons
         return fail(std::string("schedule: ") + e.what());
     }
     layout_tape(t);
+    *out = t;
+    return 0;
+}
+
+int qvmcuda_shard_plan(int n_total, int world, int rank, int remap_pull, int32_t* l2p, int n_gates, const int32_t* ks,
+                       const int32_t* qubits, const double* matrices, uint32_t flags, qvmcuda_tape** out) {
+    if (!out || !l2p) return fail("null argument");
+    *out = nullptr;
+    if (world < 1 || (world & (world - 1)) || rank < 0 || rank >= world) return fail("world must be a power of two, 0 <= rank < world");
+    const int g = log2_exact((uint64_t)world);
+    if (n_total <= g) return fail("fewer qubits than rank bits");
+    std::vector<qv::Gate> gates;
+    if (int rc = gates_from_flat(n_gates, ks, qubits, matrices, gates)) return rc;
+    qvmcuda_tape* t = new qvmcuda_tape();
+    t->flags = flags;
+    t->n_local = n_total - g;
+    t->rank = rank;
+    t->world = world;
+    t->ephemeral = true;
+    try {
+        qv::CompileOptions opt = make_options(nullptr, flags);
+        opt.rank = rank;
+        opt.n_local_bits = n_total - g;
+        opt.remap_pull = remap_pull != 0;
+        t->tape = qv::compile(gates, n_total, opt, std::vector<int>(l2p, l2p + n_total));
+    } catch (const std::exception& e) {
+        delete t;
+        return fail(std::string("schedule: ") + e.what());
+    }
+    layout_tape(t);
+    for (int q = 0; q < n_total; q++) l2p[q] = t->tape.l2p[q];
     *out = t;
     return 0;
 }

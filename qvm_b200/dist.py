@@ -153,7 +153,11 @@ class ShardedState:
         # starts before every shard is initialised
         self._barrier()
 
-    def apply_gates(self, gates, fuse: bool = True, absorb_swaps: bool = False):
+    def apply_gates(self, gates, fuse: bool = True, absorb_swaps: bool = True):
+        """absorb_swaps (default on): a sharded state never returns to the canonical qubit layout -- indices are mapped through
+        `layout()` on the host, dqvm's "record the permutation instead of undoing it" -- so an exact SWAP gate only exchanges
+        the two qubits' entries in the layout; no amplitude moves.  Off: SWAPs between local qubits run as gates (folded into
+        a pass's write-back where they trail it), SWAPs touching a rank bit are still relabelings."""
         tape = self.engine.compile(gates, fuse=fuse, absorb_swaps=absorb_swaps)
         trace = os.environ.get("QVM_DIST_TRACE") and self.rank == 0
         try:
@@ -432,7 +436,7 @@ def bench_sharded(args, rank: int, world: int, local_rank: int):
     wl = f"qft-{n}"
 
     def step():
-        st.apply_gates(gates, fuse=True, absorb_swaps=False)
+        st.apply_gates(gates, fuse=True)
 
     def timed(fn, steps):
         """CUDA events on the stream the kernels run on, bracketed by barrier + synchronize; max over ranks."""
@@ -556,6 +560,8 @@ def bench_sharded(args, rank: int, world: int, local_rank: int):
                        "hbm_passes_per_step": passes_per_step, "exchange_passes_per_step": peer_per_step,
                        "exchange": "tile kernel P2P loads over NVLink (IPC-mapped shards), remap fused into the gate pass; "
                                    "torch.distributed (NCCL) for barriers and scalars only",
+                       "swap_gates": "exact SWAP gates are relabelings of the sharded state's qubit layout (never undone: indices are "
+                                     "mapped on the host); the N = 1 line executes them (canonical layout after every circuit)",
                        "l2_policy": "shard (64 GiB) is far larger than the 126 MB L2; no flush needed",
                        "timing": "CUDA events on the kernels' stream, bracketed by barrier + cudaDeviceSynchronize, max over ranks",
                        "pass_compiler": {"prepare_seconds": prep_s, "prepare_circuits": prep_iters,

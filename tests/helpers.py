@@ -58,12 +58,15 @@ def flatten_circuit(circ):
     return ks, qf, np.ascontiguousarray(mf)
 
 
-def run_emulator(psi, n, circ, fuse=True, tile_bits=12, absorb_swaps=False, reg_bits=0):
-    """reg_bits: 3 / 4 force the 8- / 16-amplitudes-per-thread round format, 0 = the scheduler's own choice."""
+def run_emulator(psi, n, circ, fuse=True, tile_bits=12, absorb_swaps=False, reg_bits=0, route_swaps=-1, l2p_in=None):
+    """reg_bits: 3 / 4 force the 8- / 16-amplitudes-per-thread round format, 0 = the scheduler's own choice.
+    route_swaps: 1 / 0 force / forbid swap routing (absorbed SWAPs, permutation executed by the passes' write-backs),
+    -1 = the scheduler's cost model.  l2p_in: layout the state is in when the circuit starts (default: canonical)."""
     ks, qf, mf = flatten_circuit(circ)
     emulator().qvtest_set_reg_bits(int(reg_bits))
+    emulator().qvtest_set_route_swaps(int(route_swaps))
     desc = C.create_string_buffer(1 << 16)
-    l2p = np.arange(n, dtype=np.int32)
+    l2p = np.arange(n, dtype=np.int32) if l2p_in is None else np.ascontiguousarray(l2p_in, dtype=np.int32).copy()
     p = lambda a: a.ctypes.data_as(C.c_void_p)
     rc = emulator().qvtest_run(p(psi), n, len(circ), p(ks), p(qf), p(mf), int(fuse), tile_bits, int(absorb_swaps),
                                p(l2p), desc, len(desc))

@@ -249,6 +249,8 @@ int g_reg_bits = 0;
 
 extern "C" void qvtest_set_remap_pull(int on) { g_remap_pull = on != 0; }
 extern "C" void qvtest_set_reg_bits(int m) { g_reg_bits = m; }
+int g_route_swaps = -1;
+extern "C" void qvtest_set_route_swaps(int m) { g_route_swaps = m; }
 // compiled-pass mode: csrc_dir = where qv_jit_prelude.cuh & co. live; returns the number of passes run compiled so far
 extern "C" int qvtest_set_jit_host(int on, const char* csrc_dir) {
     g_jit_host = on != 0;
@@ -276,6 +278,7 @@ extern "C" int qvtest_run(double* psi, int n_bits, int n_gates, const int* ks, c
         opt.tile_bits = tile_bits;
         opt.absorb_swaps = absorb_swaps != 0;
         opt.reg_bits = g_reg_bits;
+        opt.route_swaps = g_route_swaps;
         std::vector<int> l2p;
         if (l2p_inout) l2p.assign(l2p_inout, l2p_inout + n_bits);
         qv::Tape tape = qv::compile(gates, n_bits, opt, l2p);
@@ -446,5 +449,10 @@ extern "C" int qvtest_shard_run_step(void* t, int i, double** peers, int rank) {
 extern "C" void qvtest_shard_l2p(void* t, int* out) {
     EmuTape* et = (EmuTape*)t;
     for (size_t i = 0; i < et->tape.l2p.size(); i++) out[i] = et->tape.l2p[i];
+}
+extern "C" void qvtest_shard_describe(void* t, char* out, int len) {
+    const std::string s = qv::describe(((EmuTape*)t)->tape);
+    std::strncpy(out, s.c_str(), len - 1);
+    out[len - 1] = 0;
 }
 extern "C" void qvtest_shard_free(void* t) { delete (EmuTape*)t; }

@@ -45,10 +45,11 @@ def _worker(rank, world, port, q, inplace):
         st.scatter_logical(psi)
         rng = np.random.default_rng(5)
         circ = CC.qft_circuit(range(n)) + helpers.random_circuit(n, 60, rng, max_dense=3) + CC.random_layer_circuit(n, 2, 1)
-        for fuse in (True, False):
+        # absorb: exact SWAP gates as relabelings of the layout (the default for sharded states) or executed as gates
+        for fuse, absorb in ((True, False), (False, True), (True, True)):
             st.set_zero_state()
             st.scatter_logical(psi)
-            st.apply_gates(circ, fuse=fuse)
+            st.apply_gates(circ, fuse=fuse, absorb_swaps=absorb)
             got = st.gather_logical()
             if rank == 0:
                 ref = helpers.run_oracle(psi.copy(), circ)

@@ -142,3 +142,82 @@ def test_too_wide_dense_gate_fails_before_anything_runs():
     with pytest.raises(RuntimeError, match="more than 11 mixing qubits"):
         H.run_emulator(x, n, [(u, (0,)), (big, tuple(range(12)))])
     assert (x == psi).all()      # the schedule is rejected as a whole: the first gate has not been applied
+
+
+# ---------------------------------------------------------------- swap routing
+def _swap_heavy_circuit(n, n_gates, rng):
+    """Random circuit in which every third gate or so is an exact SWAP (also back-to-back and repeated pairs)."""
+    from qvm_b200 import gates as G
+    base = random_circuit(n, n_gates, rng, max_dense=3)
+    out = []
+    for g in base:
+        out.append(g)
+        while n >= 2 and rng.integers(0, 3) == 0:
+            a, b = rng.choice(n, 2, replace=False)
+            out.append((G.gate_matrix("SWAP"), (int(a), int(b))))
+    return out
+
+
+@pytest.mark.parametrize("seed", range(24))
+def test_swap_routing_matches_oracle_and_ends_canonical(seed):
+    """Absorbed SWAP gates + the permutation executed by the passes' write-backs: same state as the oracle, canonical layout
+    (l2p = identity), whatever the tile size; also from a non-canonical starting layout (the tape then canonicalises it)."""
+    rng = np.random.default_rng(4200 + seed)
+    n = int(rng.integers(2, 15))
+    tile_bits = int(rng.integers(3, 13))
+    circ = _swap_heavy_circuit(n, int(rng.integers(4, 50)), rng)
+    a = rand_state(n, seed)
+    b = a.copy()
+    _, desc, l2p = run_emulator(a, n, circ, fuse=True, tile_bits=tile_bits, route_swaps=1, reg_bits=(3, 4, 0)[seed % 3])
+    run_oracle(b, circ)
+    assert list(l2p) == list(range(n)), desc
+    assert_close(a, b)
+    # cost-model choice: same answer, canonical too
+    c = rand_state(n, seed)
+    _, _, l2p = run_emulator(c, n, circ, fuse=True, tile_bits=tile_bits, route_swaps=-1)
+    assert list(l2p) == list(range(n))
+    assert_close(c, b)
+    # start from a permuted layout (as left behind by an absorb_swaps run)
+    perm = rng.permutation(n).astype(np.int32)
+    logical = rand_state(n, 77 + seed)
+    idx = np.arange(1 << n)
+    phys = np.zeros_like(idx)
+    for q in range(n):
+        phys |= ((idx >> q) & 1) << int(perm[q])
+    d = np.empty_like(logical)
+    d[phys] = logical                      # physical bit perm[q] holds logical qubit q
+    e = logical.copy()
+    _, desc, l2p = run_emulator(d, n, circ, fuse=True, tile_bits=tile_bits, route_swaps=1, l2p_in=perm)
+    run_oracle(e, circ)
+    assert list(l2p) == list(range(n)), desc
+    assert_close(d, e)
+
+
+def test_swap_routing_index_tracer():
+    """dqvm's debug wavefunction psi_i = i (dqvm/tests/program-tests.lisp:14-19) through permutation-only circuits: routed
+    SWAP / CNOT / X networks move integer labels exactly."""
+    from qvm_b200 import gates as G
+    n = 13
+    rng = np.random.default_rng(5)
+    circ = []
+    for _ in range(60):
+        a, b = (int(x) for x in rng.choice(n, 2, replace=False))
+        circ.append([(G.gate_matrix("SWAP"), (a, b)), (G.gate_matrix("SWAP"), (a, b)), (G.gate_matrix("CNOT"), (a, b)),
+                     (G.gate_matrix("X"), (a,))][int(rng.integers(0, 4))])
+    psi = np.arange(1 << n).astype(np.complex128)
+    ref = run_oracle(psi.copy(), circ)
+    _, desc, l2p = run_emulator(psi, n, circ, fuse=True, tile_bits=6, route_swaps=1)
+    assert list(l2p) == list(range(n)), desc
+    assert np.array_equal(psi, ref)
+
+
+def test_swap_routing_runs_qft30_in_five_passes():
+    """The 30-qubit QFT (15 trailing SWAPs = a bit reversal): 4 gate passes + 2 permutation passes without routing, 5 passes
+    with it -- the schedule the bench runs.  Schedule only (no 16 GiB state here)."""
+    from qvm_b200 import qvm
+    t = qvm.Tape(30, CC.qft_circuit(range(30)), fuse=True)
+    try:
+        assert t.info()["passes"] == 5, t.describe()
+        assert "routed_transpositions=15" in t.describe()
+    finally:
+        t.close()

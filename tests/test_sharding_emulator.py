@@ -12,12 +12,14 @@ from qvm_b200 import circuits as CC
 @pytest.mark.parametrize("world", [2, 4, 8])
 @pytest.mark.parametrize("fuse", [True, False])
 @pytest.mark.parametrize("pull", [False, True])
-def test_sharded_qft(world, fuse, pull):
+@pytest.mark.parametrize("absorb", [False, True])
+def test_sharded_qft(world, fuse, pull, absorb):
     n, tile_bits = 13, 7
     circ = CC.qft_circuit(range(n))
     a = rand_state(n)
     ref = run_oracle(a.copy(), circ)
-    steps, peer_steps, desc, l2p = run_emulator_sharded(a, n, world, circ, fuse=fuse, tile_bits=tile_bits, remap_pull=pull)
+    steps, peer_steps, desc, l2p = run_emulator_sharded(a, n, world, circ, fuse=fuse, tile_bits=tile_bits, remap_pull=pull,
+                                                        absorb_swaps=absorb)
     assert peer_steps >= 1, desc
     assert_close(unpermute(a, l2p), ref)
 
@@ -30,7 +32,8 @@ def test_sharded_random_circuits(seed):
     circ = random_circuit(n, 50, rng, max_dense=4)
     a = rand_state(n, seed)
     ref = run_oracle(a.copy(), circ)
-    steps, peer_steps, desc, l2p = run_emulator_sharded(a, n, world, circ, fuse=True, tile_bits=7, remap_pull=bool(seed & 1))
+    steps, peer_steps, desc, l2p = run_emulator_sharded(a, n, world, circ, fuse=True, tile_bits=7, remap_pull=bool(seed & 1),
+                                                        absorb_swaps=bool(seed & 2))
     assert_close(unpermute(a, l2p), ref)
 
 
