@@ -397,7 +397,7 @@ uint32_t jit_min_uops() {
     return m;
 }
 
-void jit_prepare(const std::vector<const Step*>& steps, int device, std::vector<JitKernel*>& out) {
+void jit_prepare(const std::vector<const Step*>& steps, int device, std::vector<JitKernel*>& out, int extra_variant) {
     out.assign(steps.size(), nullptr);
     const JitPolicy pol = jit_policy();
     if (pol == JitPolicy::OFF) return;
@@ -406,7 +406,7 @@ void jit_prepare(const std::vector<const Step*>& steps, int device, std::vector<
     for (size_t i = 0; i < steps.size(); i++) {
         const Step& st = *steps[i];
         if (st.kind != Step::TILE || real_uops(st) < jit_min_uops()) continue;
-        JitSource src = jit_generate(st, variant_of(st));
+        JitSource src = jit_generate(st, variant_of(st) | extra_variant);
         if (!src.ok) continue;
         sigs[i] = src.sig;
         std::unique_lock<std::mutex> lk(g_mu);
@@ -461,7 +461,7 @@ void jit_prepare(const std::vector<const Step*>& steps, int device, std::vector<
     }
 }
 
-void jit_precompile(const std::vector<const Step*>& steps, int& n_eligible, int& n_ok, std::string& log) {
+void jit_precompile(const std::vector<const Step*>& steps, int& n_eligible, int& n_ok, std::string& log, bool basis_first) {
     n_eligible = n_ok = 0;
     struct Job {
         JitSource src;
@@ -478,6 +478,8 @@ void jit_precompile(const std::vector<const Step*>& steps, int& n_eligible, int&
         // single-copy tile load
         std::vector<int> variants = {variant_of(*st)};
         if (!(variants[0] & 16) && !getenv("QVMCUDA_JIT_VARIANT")) variants.push_back(variants[0] | 16);
+        // the first pass of a tape may start from a lazily reset state (no tile loads)
+        if (basis_first && st == steps.front()) variants.push_back(variants[0] | kVariantSrcBasis);
         for (int v : variants) {
         JitSource src = jit_generate(*st, v);
         if (!src.ok || seen.count(src.sig)) continue;

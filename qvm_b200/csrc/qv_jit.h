@@ -14,7 +14,7 @@
 
 #include "qv_sched.h"
 
-#define QVJIT_VERSION "qvjit-8"
+#define QVJIT_VERSION "qvjit-9"
 
 struct QvPeers;
 struct qvc;
@@ -36,7 +36,8 @@ struct JitSource {
 // Front end (no CUDA needed; also used by the test emulator, which compiles the text for the host).
 // variant bits: 1 rolled group loop, 2 two CTAs per SM, 4 fences between micro-ops (experiments), 8 persistent TMA-fed kernel,
 // 16 classic kernel with the tile loaded by one tensor copy (8 / 16: local passes whose tile is a box of a <= 5-dimensional
-// view of the state; other passes fall back to the LDGSTS loads).
+// view of the state; other passes fall back to the LDGSTS loads), 32 no tile loads: the source is a basis state that only exists
+// as a flag (lazy reset).
 JitSource jit_generate(const Step& st, int variant = 0);
 
 // Tile geometry for the tensor-memory accelerator; false when the tile's bit runs do not fit five dimensions.
@@ -55,10 +56,12 @@ struct JitKernel;                       // one loaded kernel on one device
 // Make the kernels of these steps available on `device` according to the policy: SYNC compiles the missing ones now
 // (in parallel) and returns when all are loaded; ASYNC queues them and returns at once.  out[i] = the kernel of
 // steps[i] or nullptr (not eligible, below the threshold, still compiling, or failed -- the caller interprets).
-void jit_prepare(const std::vector<const Step*>& steps, int device, std::vector<JitKernel*>& out);
+// extra_variant: generator variant bits OR'd into every step's own choice (kVariantSrcBasis for the first pass after a lazy reset).
+constexpr int kVariantSrcBasis = 32;
+void jit_prepare(const std::vector<const Step*>& steps, int device, std::vector<JitKernel*>& out, int extra_variant = 0);
 
 // Compile the eligible steps into the disk cache only (no device): n_eligible / n_ok count distinct kernels.
-void jit_precompile(const std::vector<const Step*>& steps, int& n_eligible, int& n_ok, std::string& log);
+void jit_precompile(const std::vector<const Step*>& steps, int& n_eligible, int& n_ok, std::string& log, bool basis_first = false);
 
 struct JitLaunch {
     const uint8_t* blob;

@@ -154,8 +154,14 @@ JitSource jit_generate(const Step& st, int variant) {
     const int NS = 1 << M;
     QvTmaGeom geom;
     const bool tma_ok = M == 3 && !h.pull && !wants_wide_swizzle(h) && jit_tma_geometry(h, geom);
-    const bool tma = (variant & 8) != 0 && tma_ok;                         // persistent, double-buffered
-    const bool tma_load = !tma && (variant & 16) != 0 && tma_ok;           // classic kernel, tile loaded by one tensor copy
+    // 32 = the source is a basis state that was never written to HBM (lazy reset): no tile loads at all
+    const bool src_basis = (variant & 32) != 0;
+    if (src_basis && h.pull) {
+        js.why_not = "pull pass from a lazy basis state";
+        return js;
+    }
+    const bool tma = !src_basis && (variant & 8) != 0 && tma_ok;           // persistent, double-buffered
+    const bool tma_load = !src_basis && !tma && (variant & 16) != 0 && tma_ok;   // classic kernel, tile loaded by one tensor copy
     const int threads = tma ? 512 : (1 << h.threads_log2);
     const int iters = (4096 >> M) / threads;
     js.tma = tma ? 2 : tma_load ? 1 : 0;
@@ -177,6 +183,7 @@ JitSource jit_generate(const Step& st, int variant) {
     const bool wide = wants_wide_swizzle(h);
     if (tma) o("#define QVJ_TMA 1\n");
     if (tma_load) o("#define QVJ_TMA_LOAD 1\n");
+    if (src_basis) o("#define QVJ_SRC_BASIS 1\n");
     o("#define QVJ_HAS_SCALE %d\n#define QVJ_STORE_PERM %d\n#define QVJ_HAS_TABLES %d\n#define QVJ_WIDE_SWZ %d\n", h.has_scale ? 1 : 0,
       h.store_perm ? 1 : 0, (h.n_sources | h.n_preds | h.n_slice_entries) ? 1 : 0, wide ? 1 : 0);
     o("#include \"qv_jit_prelude.cuh\"\n\n");

@@ -23,6 +23,13 @@ struct QvjProg { uint8_t bytes[QVJ_PROG_BYTES]; };
 #if !defined(QVJ_TMA_LOAD)
 #define QVJ_TMA_LOAD 0
 #endif
+#if !defined(QVJ_SRC_BASIS)
+#define QVJ_SRC_BASIS 0
+#endif
+// Variant QVJ_SRC_BASIS: the state is a basis vector that was never written to HBM (SET-TO-ZERO-STATE is lazy): nothing is
+// loaded.  A tile that does not contain the non-zero amplitude stays zero under any gate, so it is written back as zeros
+// without running the rounds; the one tile that does is synthesised in shared memory.  The pass costs its 16 B/amplitude of
+// writes only, and the reset itself costs nothing.
 #if QVJ_TMA_LOAD
 // Variant: the tile is loaded by the tensor-memory accelerator -- ONE cp.async.bulk.tensor per tile, issued by one thread,
 // completion on an mbarrier -- instead of 16 LDGSTS per thread; everything else as below (three CTAs per SM).  See
@@ -112,7 +119,24 @@ qvj_kernel(const __grid_constant__ QvjProg prog, const __grid_constant__ QvPeers
         const uint64_t pbase = (base | glo) & local_mask;
 
         // ---- HBM -> shared memory (asynchronous 16-byte copies, all in flight at once)
-#if QVJ_TMA_LOAD
+#if QVJ_SRC_BASIS
+        if (((h->basis_index ^ base) & ~h->tile_mask & local_mask) != 0) {      // uniform over the CTA
+            char* zdst = reinterpret_cast<char*>(own + pbase);
+            qvc z;
+            z.x = 0.0;
+            z.y = 0.0;
+#pragma unroll
+            for (int i = 0; i < ITERS; i++) qv_st_stream(reinterpret_cast<qvc*>(zdst + h->hi_byte[i]), z);
+            continue;
+        }
+#pragma unroll
+        for (int i = 0; i < ITERS; i++) {
+            qvc v;
+            v.x = ((pbase | h->hi_off[i]) == (h->basis_index & local_mask)) ? 1.0 : 0.0;
+            v.y = 0.0;
+            tile[QVJ_SLOT(i)] = v;
+        }
+#elif QVJ_TMA_LOAD
         if (tid == 0) {
             const uint64_t lbase = base & local_mask;
             int32_t c1 = geom.is_tile[0] ? 0 : (int32_t)((lbase >> geom.start[0]) & ((1ull << geom.len[0]) - 1ull));
@@ -161,7 +185,9 @@ qvj_kernel(const __grid_constant__ QvjProg prog, const __grid_constant__ QvPeers
             }
         }
 #endif
-#if QVJ_TMA_LOAD
+#if QVJ_SRC_BASIS
+        __syncthreads();
+#elif QVJ_TMA_LOAD
         qvj_mbar_wait(mbar, tile_no & 1u);
         tile_no++;
 #if QVJ_HAS_TABLES

@@ -194,11 +194,14 @@ struct QvPassHeader {
     // amplitude instead of 4); the product of their factors is applied once, while the tile is written back.
     double out_scale;
     uint32_t has_scale;
-    uint32_t scale_pad;
+    uint32_t src_basis;             // patched at launch time: the state is the basis vector |basis_index> that was never written to
+                                    // HBM (lazy SET-TO-ZERO-STATE): the pass synthesises its tiles instead of loading them
     uint32_t pull;                  // 0: in place
     uint32_t pull_pad;
     QvRemap pull_remap;
     uint64_t hi_src[32];            // S(hi_off[i])
+    uint64_t basis_index;           // src_basis: physical index of the one non-zero amplitude
+    uint64_t tile_mask;             // physical index bits that vary inside a tile
 };
 
 struct qvc;

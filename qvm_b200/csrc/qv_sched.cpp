@@ -1155,6 +1155,7 @@ Step build_tile_step(const std::vector<const Atom*>& atoms_in, uint64_t tile_tar
         for (int i = 0; i < 32; i++) h.st_hi[i] = (uint16_t)swz(image(((uint32_t)i << threads_log2) & ((1u << tm.T) - 1u)));
     }
     h.fixed_bits = fixed;
+    h.tile_mask = tb;
     h.n_tiles = 1ull << nontile.size();
     h.n_local_bits = (uint32_t)geo.n_local;
     h.uses_peers = s > 0 ? 1u : 0u;
@@ -1321,6 +1322,21 @@ Tape compile(const std::vector<Gate>& gates, int n_bits, const CompileOptions& o
         const double cf = tape_cost(fused), cs = tape_cost(split);
         if (getenv("QV_SCHED_DEBUG")) fprintf(stderr, "euler split: cost fused %.1f split %.1f\n", cf, cs);
         return cs < cf ? split : fused;
+    }
+    if (opt.fuse && opt.hoist_remaps < 0) {
+        // sharded, fused pulls: schedule with and without remap hoisting, keep the cheaper tape (ties: hoisted)
+        CompileOptions o = opt;
+        o.hoist_remaps = 0;
+        const int nl = opt.n_local_bits > 0 ? opt.n_local_bits : n_bits;
+        if (nl == n_bits || !opt.remap_pull || !opt.fuse_pull) return compile(gates, n_bits, o, l2p_in);
+        Tape plain = compile(gates, n_bits, o, l2p_in);
+        o.hoist_remaps = 1;
+        Tape hoisted = compile(gates, n_bits, o, l2p_in);
+        if (hoisted.n_hoisted == 0) return plain;
+        const double cp = tape_cost(plain), ch = tape_cost(hoisted);
+        if (getenv("QV_SCHED_DEBUG")) fprintf(stderr, "remap hoisting: cost plain %.1f (%zu steps) hoisted %.1f (%zu steps)\n", cp,
+                                              plain.steps.size(), ch, hoisted.steps.size());
+        return ch <= cp ? hoisted : plain;
     }
     if (opt.fuse && opt.route_swaps < 0) {
         // Exact SWAP gates either run where they stand (folded into a pass's write-back when they trail it, else a pass of
@@ -1653,32 +1669,16 @@ Tape compile(const std::vector<Gate>& gates, int n_bits, const CompileOptions& o
         return tape;
     }
 
-    // 2. greedy pass formation with commutation look-ahead.
-    while (!pending.empty()) {
-        if (relabels(*pending.front())) {
-            const Atom& a = *pending.front();
-            std::swap(w2p[a.tw[0]], w2p[a.tw[1]]);
-            tape.n_relabeled++;
-            pending.erase(pending.begin());
-            continue;
-        }
-        if (pending.front()->kind == Atom::BIG) {
-            if (phys_mask(pending.front()->mix) & ~local_mask) {
-                remap(pending.front()->mix, pending);
-                continue;
-            }
-            tape.steps.push_back(build_big_step(*pending.front(), geo, lay));
-            pending.erase(pending.begin());
-            continue;
-        }
-        std::vector<const Atom*> in_pass, deferred;
-        uint64_t dmix = 0, dtouch = 0, targets = 0;
+    // One pass: the atoms of `pend` (in order) that fit a tile together; an atom that does not fit is deferred together with
+    // everything behind it that does not commute with it.
+    auto form_pass = [&](const std::vector<const Atom*>& pend, std::vector<const Atom*>& in_pass, std::vector<const Atom*>& deferred,
+                         uint64_t& targets) {
+        uint64_t dmix = 0, dtouch = 0;
         size_t est_bytes = sizeof(QvPassHeader);
         size_t n_diag = 0;
-        for (const Atom* a : pending) {
+        for (const Atom* a : pend) {
             bool blocked = (a->mix & dtouch) != 0 || (dmix & a->touch) != 0;
             if (!blocked && a->kind == Atom::DIAG && n_diag + 1 > 4096) blocked = true;
-            // conservative size of the atom in the control program (round + op + chunk + matrix)
             // rough size of the atom in the control program; diagonals merge into shared chunks, so they
             // are cheap -- the real size is checked when the pass is built (see the retry below)
             const size_t need_bytes = a->kind == Atom::DENSE ? sizeof(QvUop) + a->mat.size() * sizeof(cd) + 32 : 16;
@@ -1706,23 +1706,86 @@ Tape compile(const std::vector<Gate>& gates, int n_bits, const CompileOptions& o
                 if (a->kind == Atom::DIAG) n_diag++;
             }
         }
+    };
+    // wires to bring home in one exchange: `need` plus the other rank-bit targets of the queued atoms, while there is room
+    auto globals_wanted = [&](uint64_t need) {
+        for (const Atom* a : pending) {
+            const uint64_t gl = a->mix & ~need;
+            uint64_t extra = 0;
+            for (int wq = 0; wq < n_bits; wq++)
+                if ((gl >> wq & 1) && w2p[wq] >= geo.n_local) extra |= 1ull << wq;
+            int n_glob = 0;
+            for (int wq = 0; wq < n_bits; wq++)
+                if (((need | extra) >> wq & 1) && w2p[wq] >= geo.n_local) n_glob++;
+            if (n_glob <= g_bits) need |= extra;
+        }
+        return need;
+    };
+    const bool hoisting = opt.hoist_remaps > 0 && g_bits > 0 && opt.remap_pull && opt.fuse_pull;
+
+    // 2. greedy pass formation with commutation look-ahead.
+    while (!pending.empty()) {
+        if (relabels(*pending.front())) {
+            const Atom& a = *pending.front();
+            std::swap(w2p[a.tw[0]], w2p[a.tw[1]]);
+            tape.n_relabeled++;
+            pending.erase(pending.begin());
+            continue;
+        }
+        if (pending.front()->kind == Atom::BIG) {
+            if (phys_mask(pending.front()->mix) & ~local_mask) {
+                remap(pending.front()->mix, pending);
+                continue;
+            }
+            tape.steps.push_back(build_big_step(*pending.front(), geo, lay));
+            pending.erase(pending.begin());
+            continue;
+        }
+        std::vector<const Atom*> in_pass, deferred;
+        uint64_t targets = 0;
+        form_pass(pending, in_pass, deferred, targets);
         if (in_pass.empty()) {
             // the front atom needs wires that sit on rank bits: bring them (and the other global
             // targets of the atoms queued right behind it, while there is room) home first.
-            uint64_t need = pending.front()->mix;
+            const uint64_t need = pending.front()->mix;
             if (!(phys_mask(need) & ~local_mask)) throw std::runtime_error("scheduler bug: no atom fits an empty pass");
-            for (const Atom* a : pending) {
-                const uint64_t gl = a->mix & ~need;
-                uint64_t extra = 0;
-                for (int wq = 0; wq < n_bits; wq++)
-                    if ((gl >> wq & 1) && w2p[wq] >= geo.n_local) extra |= 1ull << wq;
-                int n_glob = 0;
-                for (int wq = 0; wq < n_bits; wq++)
-                    if (((need | extra) >> wq & 1) && w2p[wq] >= geo.n_local) n_glob++;
-                if (n_glob <= g_bits) need |= extra;
-            }
-            remap(need, pending);
+            remap(globals_wanted(need), pending);
             continue;
+        }
+        // Remap hoisting (fused pulls): an exchange pass is bound by NVLink, whatever it computes.  If an atom this pass had to
+        // leave behind waits for a wire on a rank bit, try the exchange NOW: when the pass formed after it holds everything this
+        // one holds and more, the exchange rides on this pass instead of costing one of its own later.
+        if (hoisting && !deferred.empty()) {
+            const Atom* trigger = nullptr;
+            for (const Atom* a : deferred)
+                if (phys_mask(a->mix) & ~local_mask) {
+                    trigger = a;
+                    break;
+                }
+            if (trigger) {
+                const std::vector<int> w2p_saved = w2p;
+                const size_t n_steps = tape.steps.size();
+                bool adopted = false;
+                try {
+                    remap(globals_wanted(trigger->mix), pending);
+                    std::vector<const Atom*> in2, def2;
+                    uint64_t t2 = 0;
+                    form_pass(pending, in2, def2, t2);
+                    adopted = in2.size() > in_pass.size() && std::includes(in2.begin(), in2.end(), in_pass.begin(), in_pass.end());
+                    if (adopted) {
+                        in_pass.swap(in2);
+                        deferred.swap(def2);
+                        targets = t2;
+                        tape.n_hoisted++;
+                    }
+                } catch (const std::runtime_error&) {
+                    adopted = false;
+                }
+                if (!adopted) {
+                    w2p = w2p_saved;
+                    tape.steps.resize(n_steps);
+                }
+            }
         }
         // Build the pass; if its control program or chunk count overflows, keep the first half of the
         // atoms and send the rest back (original order restored: pointers into `atoms` are ordered).
@@ -1777,6 +1840,7 @@ std::string describe(const Tape& t) {
     os << "tape: n_bits=" << t.n_bits << " gates=" << t.n_gates << " atoms=" << t.n_atoms
        << " steps=" << t.steps.size() << (t.n_fused ? " matrix_merges=" + std::to_string(t.n_fused) : std::string())
        << (t.n_split ? " euler_splits=" + std::to_string(t.n_split) : std::string()) << (t.n_relabeled ? " relabeled_swaps=" + std::to_string(t.n_relabeled) : std::string())
+       << (t.n_hoisted ? " hoisted_remaps=" + std::to_string(t.n_hoisted) : std::string())
        << (t.n_routed ? " routed_transpositions=" + std::to_string(t.n_routed) : std::string()) << "\n";
     for (size_t i = 0; i < t.steps.size(); i++) {
         const Step& s = t.steps[i];

@@ -43,6 +43,9 @@ struct CompileOptions {
     int route_swaps = -1;        // single device, fused: absorb exact SWAP gates as relabelings and execute the permutation back to the
                                  // canonical layout in the write-back of the gate passes (spare tile slots): 1 always, 0 never (SWAPs
                                  // run where they stand), -1 = whichever tape the cost model prefers
+    int hoist_remaps = -1;       // sharded, fused pulls: do an exchange a later atom needs as part of the CURRENT pass when that pass then
+                                 // holds everything it held before and more (the exchange is NVLink-bound whatever it computes):
+                                 // 1 always, 0 never, -1 = whichever tape the cost model prefers
     bool remap_pull = false;     // remaps as out-of-place pulls into the alternate buffer (needs 2x shard memory)
 };
 
@@ -68,6 +71,7 @@ struct Tape {
     int n_split = 0;             // complex 1q unitaries written as diag . rotation . diag (Euler split)
     int n_splittable = 0;        // ... that could have been
     int n_routed = 0;            // transpositions of index bits executed by write-backs on behalf of absorbed SWAP gates (swap routing)
+    int n_hoisted = 0;           // exchanges moved forward into a gate pass (remap hoisting)
     int n_relabeled = 0;         // SWAP gates on rank bits executed as relabelings (sharded)
 };
 

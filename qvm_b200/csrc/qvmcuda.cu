@@ -1,11 +1,13 @@
 // qvmcuda.cu -- C ABI of libqvmcuda (see include/qvmcuda.h for the contract and
 // the reference interfaces each entry point stands behind).
+#include <algorithm>
 #include <atomic>
 #include <chrono>
 #include <cstdlib>
 #include <cstdio>
 #include <cstring>
 #include <map>
+#include <memory>
 #include <mutex>
 #include <string>
 #include <vector>
@@ -58,6 +60,18 @@ constexpr uint32_t kReduceBlocks = 148 * 8;
 
 }  // namespace
 
+struct qvmcuda_tape;
+// Immediate-mode schedule cache: the reference compiles a loaded program once and runs it many times (multishot loops,
+// COMPILE-LOADED-PROGRAM src/qvm.lisp:166-175); qvmcuda_apply_gates sees the same gate list over and over in that case.  The
+// last few schedules are kept per state, keyed by the exact gate list, flags and starting layout.
+struct QvTapeCacheEntry {
+    uint64_t key = 0;
+    uint32_t flags = 0;
+    std::vector<int> l2p_in;
+    std::vector<qv::Gate> gates;
+    qvmcuda_tape* tape = nullptr;
+};
+
 struct qvmcuda_state {
     std::mutex mu;
     int device = 0;
@@ -69,6 +83,12 @@ struct qvmcuda_state {
     double* d_partial = nullptr;   // kReduceBlocks + 1 doubles
     int sm_count = 148;
     std::vector<int> l2p;          // logical -> physical qubit (identity unless swaps were absorbed)
+    // Lazy reset (single device): SET-TO-ZERO-STATE only records that the state is the basis vector |lazy_index>.  If the next
+    // thing that happens is a compiled gate pass, that pass synthesises its tiles instead of loading them (no 16 B/amplitude
+    // reset write, no 16 B/amplitude read in the first pass); anything else writes the vector first (materialize_locked).
+    bool lazy_basis = false;
+    uint64_t lazy_index = 0;
+    std::vector<QvTapeCacheEntry> tape_cache;      // most recent first
     // multi-GPU
     int rank = 0, world = 1;
     QvPeers peers{};
@@ -303,6 +323,8 @@ const std::vector<qv::JitKernel*>& tape_jit(qvmcuda_state* s, qvmcuda_tape* t) {
     return v;
 }
 
+int materialize_locked(qvmcuda_state* s);
+
 int run_steps(qvmcuda_state* s, const qv::Tape& tape, const std::vector<size_t>& offsets, const uint8_t* d_buf,
               const std::vector<qv::JitKernel*>* jit = nullptr) {
     std::vector<qv::JitKernel*> local;
@@ -310,7 +332,32 @@ int run_steps(qvmcuda_state* s, const qv::Tape& tape, const std::vector<size_t>&
         prepare_jit(s, tape, local);
         jit = &local;
     }
-    for (size_t i = 0; i < tape.steps.size(); i++) {
+    size_t first = 0;
+    if (s->lazy_basis && !tape.steps.empty()) {
+        // first pass after a lazy reset: its compiled no-load variant, with the basis index patched into the header copy
+        const qv::Step& st0 = tape.steps[0];
+        qv::JitKernel* jk = nullptr;
+        if (s->world == 1 && st0.kind == qv::Step::TILE && !st0.uses_peers && (*jit)[0]) {
+            std::vector<const qv::Step*> one = {&st0};
+            std::vector<qv::JitKernel*> got;
+            qv::jit_prepare(one, s->device, got, qv::kVariantSrcBasis);
+            jk = got[0];
+        }
+        if (jk) {
+            qv::Step patched = st0;
+            QvPassHeader h;
+            std::memcpy(&h, patched.blob.data(), sizeof(h));
+            h.src_basis = 1;
+            h.basis_index = s->lazy_index;
+            std::memcpy(patched.blob.data(), &h, sizeof(h));
+            s->lazy_basis = false;
+            if (int rc = launch_step(s, patched, d_buf + offsets[0], jk)) return rc;
+            first = 1;
+        } else if (int rc = materialize_locked(s)) {
+            return rc;
+        }
+    }
+    for (size_t i = first; i < tape.steps.size(); i++) {
         int rc = launch_step(s, tape.steps[i], d_buf + offsets[i], (*jit)[i]);
         if (rc) return rc;
     }
@@ -346,12 +393,24 @@ qv::CompileOptions make_options(const qvmcuda_state* s, uint32_t flags) {
     opt.fuse_matrices = fuse_mats != 0;
     static const int route = getenv("QVMCUDA_ROUTE_SWAPS") ? atoi(getenv("QVMCUDA_ROUTE_SWAPS")) : -1;   // 1 always, 0 never, -1 cost model
     opt.route_swaps = route;
+    static const int hoist = getenv("QVMCUDA_HOIST_REMAPS") ? atoi(getenv("QVMCUDA_HOIST_REMAPS")) : -1;  // 1 always, 0 never, -1 cost model
+    opt.hoist_remaps = hoist;
     if (s) {
         opt.rank = s->rank;
         opt.n_local_bits = s->n_bits;
         opt.remap_pull = s->remap_pull;
     }
     return opt;
+}
+
+int materialize_locked(qvmcuda_state* s) {
+    if (!s->lazy_basis) return 0;
+    s->lazy_basis = false;
+    CK(cudaMemsetAsync(s->d_amps, 0, s->n_amps * sizeof(qvc), s->stream));
+    qv_set_one_kernel<<<1, 1, 0, s->stream>>>(s->d_amps, s->lazy_index);
+    g_launches++;
+    CK(cudaGetLastError());
+    return 0;
 }
 
 // Program data (diagonal tables / big matrices) of a tape go through a persistent pinned staging buffer and a persistent
@@ -392,22 +451,69 @@ int run_gates_locked(qvmcuda_state* s, const std::vector<qv::Gate>& gates, uint3
                             std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count());
         }
     } tracer{trace, t_begin, gates.size()};
-    qvmcuda_tape t;
-    try {
-        const int total_bits = s->n_bits + log2_exact((uint64_t)s->world);
-        t.tape = qv::compile(gates, total_bits, make_options(s, flags), s->l2p);
-    } catch (const std::exception& e) {
-        return fail(std::string("schedule: ") + e.what());
+    // schedule cache: exact match of gate list, flags and starting layout
+    static const size_t cache_slots = getenv("QVMCUDA_TAPE_CACHE") ? (size_t)atoi(getenv("QVMCUDA_TAPE_CACHE")) : 4;
+    uint64_t key = 1469598103934665603ull;
+    auto mix = [&key](const void* p, size_t n) {
+        const uint64_t* w = static_cast<const uint64_t*>(p);
+        for (size_t i = 0; i < n / 8; i++) key = (key ^ w[i]) * 1099511628211ull;
+        const uint8_t* b = static_cast<const uint8_t*>(p) + (n & ~(size_t)7);
+        for (size_t i = 0; i < (n & 7); i++) key = (key ^ b[i]) * 1099511628211ull;
+    };
+    for (const qv::Gate& g : gates) {
+        mix(g.qubits.data(), g.qubits.size() * sizeof(int));
+        mix(g.mat.data(), g.mat.size() * sizeof(qv::cd));
     }
-    layout_tape(&t);
-    if (trace) fprintf(stderr, "[qvmcuda] schedule: %zu steps in %.3f ms\n", t.tape.steps.size(),
-                       std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_begin).count());
+    mix(&flags, sizeof(flags));
+    mix(s->l2p.data(), s->l2p.size() * sizeof(int));
+    qvmcuda_tape* tp = nullptr;
+    for (size_t i = 0; i < s->tape_cache.size() && !tp; i++) {
+        QvTapeCacheEntry& e = s->tape_cache[i];
+        if (e.key != key || e.flags != flags || e.l2p_in != s->l2p || e.gates.size() != gates.size()) continue;
+        bool same = true;
+        for (size_t g = 0; g < gates.size() && same; g++)
+            same = e.gates[g].qubits == gates[g].qubits && e.gates[g].mat == gates[g].mat;
+        if (!same) continue;
+        tp = e.tape;
+        if (i) std::rotate(s->tape_cache.begin(), s->tape_cache.begin() + i, s->tape_cache.begin() + i + 1);
+    }
+    std::unique_ptr<qvmcuda_tape> fresh;
+    if (!tp) {
+        fresh.reset(new qvmcuda_tape());
+        try {
+            const int total_bits = s->n_bits + log2_exact((uint64_t)s->world);
+            fresh->tape = qv::compile(gates, total_bits, make_options(s, flags), s->l2p);
+        } catch (const std::exception& e) {
+            return fail(std::string("schedule: ") + e.what());
+        }
+        fresh->flags = flags;
+        fresh->ephemeral = true;
+        layout_tape(fresh.get());
+        tp = fresh.get();
+        if (trace) fprintf(stderr, "[qvmcuda] schedule: %zu steps in %.3f ms\n", tp->tape.steps.size(),
+                           std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_begin).count());
+        if (cache_slots > 0) {
+            QvTapeCacheEntry e;
+            e.key = key;
+            e.flags = flags;
+            e.l2p_in = s->l2p;
+            e.gates = gates;
+            e.tape = fresh.release();
+            s->tape_cache.insert(s->tape_cache.begin(), std::move(e));
+            while (s->tape_cache.size() > cache_slots) {
+                delete s->tape_cache.back().tape;
+                s->tape_cache.pop_back();
+            }
+        }
+    }
+    qvmcuda_tape& t = *tp;
     if (t.tape.steps.empty()) {
         s->l2p = t.tape.l2p;
         return 0;
     }
-    if (int rc = upload_to_scratch_locked(s, t)) return rc;
-    int rc = run_steps(s, t.tape, t.offsets, s->d_scratch);
+    if (s->scratch_tape != t.id)
+        if (int rc = upload_to_scratch_locked(s, t)) return rc;
+    int rc = run_steps(s, t.tape, t.offsets, s->d_scratch, &tape_jit(s, &t));
     if (rc) return rc;
     s->l2p = t.tape.l2p;
     return 0;
@@ -415,6 +521,7 @@ int run_gates_locked(qvmcuda_state* s, const std::vector<qv::Gate>& gates, uint3
 
 // Undo absorbed swaps so that physical bit q holds logical qubit q again.
 int canonicalize_locked(qvmcuda_state* s) {
+    if (int rc = materialize_locked(s)) return rc;      // every caller is about to touch the amplitudes
     if (l2p_is_identity(s->l2p)) return 0;
     if (s->world > 1) return 0;   // shards keep their layout; the host maps indices through qvmcuda_state_layout
     std::vector<int> l2p = s->l2p;
@@ -443,6 +550,7 @@ int canonicalize_locked(qvmcuda_state* s) {
 }
 
 int reduce_locked(qvmcuda_state* s, uint64_t count, int mode, uint32_t q, uint64_t dim, double* out) {
+    if (int rc = materialize_locked(s)) return rc;
     uint64_t blocks = (count + QV_THREADS - 1) / QV_THREADS;
     if (blocks > kReduceBlocks) blocks = kReduceBlocks;
     if (blocks == 0) blocks = 1;
@@ -481,6 +589,7 @@ int aux_locked(qvmcuda_state* s, uint64_t n_doubles, double** out) {
 }
 
 int elementwise_locked(qvmcuda_state* s, int mode, uint32_t q, uint32_t q2, uint32_t keep, double f) {
+    if (int rc = materialize_locked(s)) return rc;
     uint64_t blocks = (s->n_amps + QV_THREADS - 1) / QV_THREADS;
     const uint64_t cap = (uint64_t)s->sm_count * 8 * 4;
     if (blocks > cap) blocks = cap;
@@ -566,6 +675,8 @@ int qvmcuda_state_destroy(qvmcuda_state* s) {
         if (s->upload_done) cudaEventDestroy(s->upload_done);
         if (s->own_stream && s->stream) cudaStreamDestroy(s->stream);
         s->d_amps = nullptr;
+        for (QvTapeCacheEntry& e : s->tape_cache) delete e.tape;      // ephemeral tapes own no device memory
+        s->tape_cache.clear();
     }
     delete s;
     return 0;
@@ -612,6 +723,7 @@ int qvmcuda_upload(qvmcuda_state* s, const double* src, uint64_t offset, uint64_
     std::lock_guard<std::mutex> lk(s->mu);
     if (offset > s->n_amps || count > s->n_amps - offset) return fail("upload range out of bounds");
     DeviceGuard dg(s->device);
+    if (offset == 0 && count == s->n_amps) s->lazy_basis = false;      // fully overwritten: nothing to write first
     if (int rc = canonicalize_locked(s)) return rc;
     CK(cudaMemcpyAsync(s->d_amps + offset, src, count * sizeof(qvc), cudaMemcpyHostToDevice, s->stream));
     CK(cudaStreamSynchronize(s->stream));
@@ -624,10 +736,11 @@ int qvmcuda_set_basis_state(qvmcuda_state* s, uint64_t basis) {
     if (basis >= s->n_amps) return fail("basis state out of range");
     DeviceGuard dg(s->device);
     for (size_t i = 0; i < s->l2p.size(); i++) s->l2p[i] = (int)i;   // content is replaced: layout resets
-    CK(cudaMemsetAsync(s->d_amps, 0, s->n_amps * sizeof(qvc), s->stream));
-    qv_set_one_kernel<<<1, 1, 0, s->stream>>>(s->d_amps, basis);
-    g_launches++;
-    CK(cudaGetLastError());
+    static const bool lazy = !(getenv("QVMCUDA_LAZY_RESET") && atoi(getenv("QVMCUDA_LAZY_RESET")) == 0);
+    s->lazy_basis = true;
+    s->lazy_index = basis;
+    // shards are read by their peers, and small states gain nothing: write those now
+    if (!lazy || s->world > 1 || s->n_bits < QV_MAX_TILE_BITS) return materialize_locked(s);
     return 0;
 }
 
@@ -642,8 +755,13 @@ int qvmcuda_copy(qvmcuda_state* dst, qvmcuda_state* src) {
     if (int rc = canonicalize_locked(src)) return rc;
     CK(cudaStreamSynchronize(src->stream));
     const uint64_t n = dst->n_amps < src->n_amps ? dst->n_amps : src->n_amps;
-    if (n == dst->n_amps)
+    if (n == dst->n_amps) {
         for (size_t i = 0; i < dst->l2p.size(); i++) dst->l2p[i] = (int)i;
+        dst->lazy_basis = false;       // fully overwritten
+    } else {
+        DeviceGuard dgd(dst->device);
+        if (int rc = materialize_locked(dst)) return rc;
+    }
     CK(cudaMemcpyAsync(dst->d_amps, src->d_amps, n * sizeof(qvc), cudaMemcpyDefault, dst->stream));
     CK(cudaStreamSynchronize(dst->stream));
     return 0;
@@ -807,6 +925,7 @@ int qvmcuda_tape_run_step(qvmcuda_state* s, qvmcuda_tape* t, int step) {
     if (t->n_local != s->n_bits || t->rank != s->rank || t->world != s->world)
         return fail("tape was compiled for a different shard geometry");
     DeviceGuard dg(s->device);
+    if (int rc = materialize_locked(s)) return rc;
     uint8_t* d_buf = nullptr;
     if (int rc = tape_device_buffer(s, t, &d_buf)) return rc;
     const qv::Step& st = t->tape.steps[step];
@@ -836,8 +955,9 @@ int qvmcuda_tape_run(qvmcuda_state* s, qvmcuda_tape* t) {
     if (t->tape.n_bits != s->n_bits) return fail("tape was compiled for a different number of qubits");
     if (s->world != 1) return fail("precompiled tapes are single-device; use qvmcuda_apply_gates on shards");
     DeviceGuard dg(s->device);
-    // a tape is compiled against the identity layout
-    if (int rc = canonicalize_locked(s)) return rc;
+    // a tape is compiled against the identity layout (a lazily reset state is in it: keep it lazy for the first pass)
+    if (!s->lazy_basis)
+        if (int rc = canonicalize_locked(s)) return rc;
     if (t->tape.steps.empty()) {
         s->l2p = t->tape.l2p;
         return 0;
@@ -881,7 +1001,7 @@ int qvmcuda_tape_jit_precompile(qvmcuda_tape* t, int* n_eligible, int* n_ok, cha
     for (const qv::Step& st : t->tape.steps) ptrs.push_back(&st);
     std::string text;
     int ne = 0, nk = 0;
-    qv::jit_precompile(ptrs, ne, nk, text);
+    qv::jit_precompile(ptrs, ne, nk, text, t->world == 1);
     if (n_eligible) *n_eligible = ne;
     if (n_ok) *n_ok = nk;
     if (log && loglen) {
@@ -1025,6 +1145,7 @@ int qvmcuda_collapse(qvmcuda_state* s, int qubit, int keep_bit, double inv_norm)
         // the qubit selects the rank: the whole shard is either kept (scaled) or annihilated
         const int mine = (s->rank >> (pbit - s->n_bits)) & 1;
         if (mine == (keep_bit ? 1 : 0)) return elementwise_locked(s, 0, 0, 0, 0, inv_norm);
+        s->lazy_basis = false;
         CK(cudaMemsetAsync(s->d_amps, 0, s->n_amps * sizeof(qvc), s->stream));
         return 0;
     }
@@ -1035,6 +1156,7 @@ int qvmcuda_collapse(qvmcuda_state* s, int qubit, int keep_bit, double inv_norm)
 // receives the vector's own mass in tree order.  n_shots may be 0 (total only).
 static int sample_locked(qvmcuda_state* s, const double* uniforms, uint64_t n_shots, uint64_t* out, int strict, double base,
                          double* total_out) {
+    if (int rc = materialize_locked(s)) return rc;
     const uint64_t n1 = (s->n_amps + QV_SB - 1) / QV_SB;
     const uint64_t n2 = (n1 + QV_SB - 1) / QV_SB;
     // Persistent scratch (no allocation on the measurement path): the two summation levels + top prefix live
@@ -1251,6 +1373,7 @@ int qvmcuda_set_identity_matrix(qvmcuda_state* s, int n_qubits) {
     DeviceGuard dg(s->device);
     for (size_t i = 0; i < s->l2p.size(); i++) s->l2p[i] = (int)i;
     const uint64_t dim = 1ull << n_qubits;
+    s->lazy_basis = false;         // content is replaced
     CK(cudaMemsetAsync(s->d_amps, 0, s->n_amps * sizeof(qvc), s->stream));
     qv_set_identity_kernel<<<(int)((dim + QV_THREADS - 1) / QV_THREADS), QV_THREADS, 0, s->stream>>>(s->d_amps, dim);
     g_launches++;
@@ -1264,6 +1387,7 @@ int qvmcuda_shard_export(qvmcuda_state* s, uint8_t handle[64]) {
     static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
     std::lock_guard<std::mutex> lk(s->mu);
     DeviceGuard dg(s->device);
+    if (int rc = materialize_locked(s)) return rc;     // peers will read this memory
     cudaIpcMemHandle_t h;
     CK(cudaIpcGetMemHandle(&h, s->d_amps));
     std::memcpy(handle, &h, 64);

@@ -337,7 +337,7 @@ def _sharded_roofline(local_qubits: int, step_seconds: float, passes_per_step: f
                       peer_seconds_per_step: float, peer_bytes_per_step: float):
     """Per-GPU figures for the sharded run.  HBM: every pass reads and writes the rank's whole shard (32 B per amplitude,
     SURVEY 8d), so achieved = 32 * 2^local_qubits * passes / step time.  NVLink: the exchange passes pull
-    (1 - 2^-pairs) of the shard from peer memory; their ingress rate is set against the 900 GB/s per direction of NVLink 5."""
+    (1 - 2^-pairs) of the shard from peer memory; their ingress rate is set against the measured peer-copy rate (770 GB/s per direction, B200_PROFILING.md) and the nominal 900 GB/s."""
     try:
         peaks = _main_attr("measured_peaks")
         peak, src = peaks() if peaks is not None else (6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)")
@@ -349,10 +349,11 @@ def _sharded_roofline(local_qubits: int, step_seconds: float, passes_per_step: f
         nv = None
         if peer_seconds_per_step > 0:
             gbs = peer_bytes_per_step / peer_seconds_per_step / 1e9
-            nv = {"bound": "nvlink", "achieved": gbs, "peak": 900.0, "unit": "GB/s", "frac": gbs / 900.0,
+            nv = {"bound": "nvlink", "achieved": gbs, "peak": 770.0, "unit": "GB/s", "frac": gbs / 770.0,
+                  "nominal_peak": 900.0, "frac_of_nominal": gbs / 900.0,
                   "bytes_pulled_per_gpu_per_step": peer_bytes_per_step, "exchange_ms_per_step": 1e3 * peer_seconds_per_step,
                   "exchange_passes_per_step": peer_passes_per_step,
-                  "peak_source": "NVLink 5: 900 GB/s per direction per GPU (B200_PROFILING.md)",
+                  "peak_source": "measured peer copy, 770 GB/s per direction per GPU (B200_PROFILING.md); nominal NVLink 5: 900",
                   "what": "ingress of the passes that load through a qubit remap from peer shards while applying their gates"}
         return {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                 "frac": (achieved / peak) if achieved else None,

@@ -34,3 +34,4 @@ t("prob_excited(0)", lambda: vec.prob_excited(0))
 t("norm2", vec.norm2)
 t("collapse(3)", lambda: vec.collapse(3, 1, 1.0))
 t("scale", lambda: vec.scale(1.0))
+t("reset + apply_gates(fused)", lambda: (vec.set_zero_state(), vec.apply_gates(gates, fuse=True)))

@@ -470,3 +470,98 @@ def test_probabilities_export(Q, O):
     assert np.array_equal(vec.probabilities(1000, 777), ref[1000:1777])
     assert Q.probabilities_octets(vec.probabilities(0, 4)) == Q.probabilities_octets(ref[:4])
     vec.close()
+
+
+# ---------------------------------------------------------------- lazy reset (SET-TO-ZERO-STATE as a flag)
+@pytest.mark.parametrize("n,basis", [(12, 0), (14, 0), (14, 5), (15, (1 << 15) - 1), (16, 0x8421), (18, 1 << 17)])
+def test_lazy_reset_first_pass_synthesises_its_tiles(Q, O, n, basis):
+    """set_basis_state only records the basis index; the first compiled pass that follows builds its tiles instead of loading
+    them (zero tiles are written back as zeros).  Same amplitudes as the oracle run from the explicit basis vector."""
+    from qvm_b200 import _lib
+    rng = np.random.default_rng(n * 977 + basis)
+    circ = CC.qft_circuit(range(n)) + random_circuit(n, 40, rng, max_dense=3)
+    ref = np.zeros(1 << n, dtype=np.complex128)
+    ref[basis] = 1.0
+    run_oracle(ref, circ)
+    for mode in ("apply_gates", "tape", "unfused"):
+        vec = Q.DeviceVector(1 << n)
+        junk = rand_state(n, 3)
+        vec.upload(junk)                      # the buffer holds something else: a skipped reset would show
+        vec.set_basis_state(basis)
+        l0 = _lib.launch_count()
+        if mode == "apply_gates":
+            vec.apply_gates(circ, fuse=True)
+        elif mode == "tape":
+            tape = Q.Tape(n, circ, fuse=True)
+            vec.run_tape(tape)
+            tape.close()
+        else:
+            vec.apply_gates(circ, fuse=False)  # first pass runs on the interpreter: the vector is written first
+        assert _lib.launch_count() > l0
+        assert_close(vec.download(), ref)
+        vec.close()
+
+
+def test_lazy_reset_is_invisible_to_every_reader(Q, O):
+    n = 14
+    for basis in (0, 9, (1 << n) - 2):
+        want = np.zeros(1 << n, dtype=np.complex128)
+        want[basis] = 1.0
+        u = np.random.default_rng(1).random(64)
+
+        def fresh():
+            v = Q.DeviceVector(1 << n)
+            v.upload(rand_state(n, 8))
+            v.set_basis_state(basis)
+            return v
+
+        v = fresh(); assert np.array_equal(v.download(), want); v.close()
+        v = fresh(); assert v.norm2() == 1.0; v.close()
+        for q in (0, 3, n - 1):
+            v = fresh(); assert v.prob_excited(q) == float((basis >> q) & 1); v.close()
+        v = fresh(); assert (v.sample(u, strict=False) == basis).all(); v.close()
+        v = fresh(); p = v.probabilities(); assert np.array_equal(p, np.abs(want) ** 2); v.close()
+        v = fresh(); w = Q.DeviceVector(1 << n); w.copy_from(v); assert np.array_equal(w.download(), want); v.close(); w.close()
+        v = fresh(); v.collapse(0, basis & 1, 1.0); assert np.array_equal(v.download(), want); v.close()
+        v = fresh(); v.upload(want[:8] * 0 + 2.0, offset=0); got = v.download()      # partial upload lands on the written vector
+        chk = want.copy(); chk[:8] = 2.0
+        assert np.array_equal(got, chk); v.close()
+        # two resets in a row, then gates
+        v = fresh(); v.set_zero_state(); v.apply_gates([(G.gate_matrix("H"), (q,)) for q in range(n)], fuse=True)
+        assert_close(v.download(), np.full(1 << n, 2.0 ** (-n / 2), dtype=np.complex128)); v.close()
+
+
+def test_schedule_cache_hits_only_on_identical_programs(Q, O):
+    """qvmcuda_apply_gates keeps its last few schedules per state (the reference compiles a loaded program once and runs it
+    many times): a repeated gate list is served from the cache, a list that differs in one angle, one qubit or the starting
+    layout is not."""
+    n = 13
+    rng = np.random.default_rng(77)
+    base = CC.qft_circuit(range(n)) + random_circuit(n, 30, rng, max_dense=3)
+    variants = [base]
+    v = list(base)
+    v[5] = (G.gate_matrix("RZ", [0.123]), (4,))
+    variants.append(v)
+    v = list(base)
+    v[7] = (v[7][0], tuple((q + 1) % n for q in v[7][1]))
+    variants.append(v)
+    variants += [random_circuit(n, 25, rng, max_dense=3) for _ in range(4)]     # more programs than cache slots
+    psi = rand_state(n, 5)
+    vec = Q.DeviceVector(1 << n)
+    for rep in range(3):
+        for circ in variants:
+            vec.upload(psi)
+            vec.apply_gates(circ, fuse=True)
+            ref = run_oracle(psi.copy(), circ)
+            assert_close(vec.download(), ref)
+    # same program twice in a row without re-upload (state differs, schedule identical), then from an absorbed-swap layout
+    vec.upload(psi)
+    vec.apply_gates(base, fuse=True)
+    vec.apply_gates(base, fuse=True)
+    ref = run_oracle(run_oracle(psi.copy(), base), base)
+    assert_close(vec.download(), ref)
+    vec.upload(psi)
+    vec.apply_gates(base, fuse=True, absorb_swaps=True)     # leaves a permuted layout behind
+    vec.apply_gates(base, fuse=True)                        # same list, different starting layout: must not reuse the tape above
+    assert_close(vec.download(), ref)
+    vec.close()

@@ -99,3 +99,29 @@ def test_repeated_application_carries_the_layout(world, pull):
         assert_close(unpermute(a, l2p), ref)
     assert relabeled >= 1      # at least one run met a SWAP on a rank bit
     assert not (l2p == np.arange(n)).all()
+
+
+def test_remap_hoisting_folds_the_exchange_into_a_gate_pass():
+    """Fused pulls: an exchange a later gate needs is done as part of the current pass when that pass then holds everything it
+    held and more (an exchange pass is NVLink-bound whatever it computes).  Hoisted schedules reproduce the oracle; the QFT on
+    8 emulated ranks needs fewer steps than with hoisting off."""
+    from helpers import emulator
+    hoisted = 0
+    for world, n, tb in [(2, 13, 7), (4, 14, 6), (8, 16, 8), (8, 14, 7)]:
+        circ = CC.qft_circuit(range(n))
+        a = rand_state(n)
+        ref = run_oracle(a.copy(), circ)
+        steps, peer_steps, desc, l2p = run_emulator_sharded(a, n, world, circ, fuse=True, tile_bits=tb, remap_pull=True, absorb_swaps=True)
+        assert_close(unpermute(a, l2p), ref)
+        hoisted += "hoisted_remaps" in desc
+    assert hoisted >= 2
+    rng = np.random.default_rng(11)
+    for seed in range(12):
+        world = int(rng.choice([2, 4, 8]))
+        n = int(rng.integers(12, 16))
+        circ = random_circuit(n, 80, rng, max_dense=4)
+        a = rand_state(n, seed)
+        ref = run_oracle(a.copy(), circ)
+        _, _, desc, l2p = run_emulator_sharded(a, n, world, circ, fuse=True, tile_bits=int(rng.integers(6, 9)), remap_pull=True,
+                                               absorb_swaps=bool(seed & 1))
+        assert_close(unpermute(a, l2p), ref)
