@@ -127,6 +127,8 @@ struct qvmcuda_tape {
     int n_local = 0, rank = 0, world = 1; // geometry the tape was compiled for
     uint64_t id = next_tape_id();         // identifies the tape whose data sits in a state's scratch buffer
     bool ephemeral = false;               // shard tapes are compiled per run: their data goes through the state's scratch
+    bool state_owned = false;             // lives in a state's schedule cache: qvmcuda_tape_destroy only returns it
+    std::atomic<int> checked_out{0};      // handles given out by qvmcuda_shard_compile and not yet destroyed
     // compiled passes (qv_jit.h) per device: jit[dev][step] = kernel or nullptr (interpreter); complete = no step is
     // still waiting for the asynchronous compiler
     std::map<int, std::vector<qv::JitKernel*>> jit;
@@ -440,18 +442,19 @@ int upload_to_scratch_locked(qvmcuda_state* s, const qvmcuda_tape& t) {
     return 0;
 }
 
-// compile + upload + run in immediate mode (state mutex held)
-int run_gates_locked(qvmcuda_state* s, const std::vector<qv::Gate>& gates, uint32_t flags) {
+void drop_tape_cache_locked(qvmcuda_state* s) {
+    for (size_t i = s->tape_cache.size(); i-- > 0;)
+        if (s->tape_cache[i].tape->checked_out.load() == 0) {
+            delete s->tape_cache[i].tape;
+            s->tape_cache.erase(s->tape_cache.begin() + i);
+        }
+}
+
+// Schedule of `gates` from the state's current layout: from the state's cache when the exact gate list, flags and starting
+// layout were seen before, else compiled now (and cached).  The tape stays owned by the state.
+int cached_tape_locked(qvmcuda_state* s, const std::vector<qv::Gate>& gates, uint32_t flags, qvmcuda_tape** out) {
     static const bool trace = getenv("QVMCUDA_TRACE") != nullptr;
     const auto t_begin = std::chrono::steady_clock::now();
-    struct Tracer {
-        bool on; std::chrono::steady_clock::time_point t0; size_t n;
-        ~Tracer() {
-            if (on) fprintf(stderr, "[qvmcuda] apply_gates: %zu gates, host time %.3f ms\n", n,
-                            std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count());
-        }
-    } tracer{trace, t_begin, gates.size()};
-    // schedule cache: exact match of gate list, flags and starting layout
     static const size_t cache_slots = getenv("QVMCUDA_TAPE_CACHE") ? (size_t)atoi(getenv("QVMCUDA_TAPE_CACHE")) : 4;
     uint64_t key = 1469598103934665603ull;
     auto mix = [&key](const void* p, size_t n) {
@@ -466,46 +469,63 @@ int run_gates_locked(qvmcuda_state* s, const std::vector<qv::Gate>& gates, uint3
     }
     mix(&flags, sizeof(flags));
     mix(s->l2p.data(), s->l2p.size() * sizeof(int));
-    qvmcuda_tape* tp = nullptr;
-    for (size_t i = 0; i < s->tape_cache.size() && !tp; i++) {
+    for (size_t i = 0; i < s->tape_cache.size(); i++) {
         QvTapeCacheEntry& e = s->tape_cache[i];
         if (e.key != key || e.flags != flags || e.l2p_in != s->l2p || e.gates.size() != gates.size()) continue;
         bool same = true;
         for (size_t g = 0; g < gates.size() && same; g++)
             same = e.gates[g].qubits == gates[g].qubits && e.gates[g].mat == gates[g].mat;
         if (!same) continue;
-        tp = e.tape;
+        *out = e.tape;
         if (i) std::rotate(s->tape_cache.begin(), s->tape_cache.begin() + i, s->tape_cache.begin() + i + 1);
+        return 0;
     }
-    std::unique_ptr<qvmcuda_tape> fresh;
-    if (!tp) {
-        fresh.reset(new qvmcuda_tape());
-        try {
-            const int total_bits = s->n_bits + log2_exact((uint64_t)s->world);
-            fresh->tape = qv::compile(gates, total_bits, make_options(s, flags), s->l2p);
-        } catch (const std::exception& e) {
-            return fail(std::string("schedule: ") + e.what());
-        }
-        fresh->flags = flags;
-        fresh->ephemeral = true;
-        layout_tape(fresh.get());
-        tp = fresh.get();
-        if (trace) fprintf(stderr, "[qvmcuda] schedule: %zu steps in %.3f ms\n", tp->tape.steps.size(),
-                           std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_begin).count());
-        if (cache_slots > 0) {
-            QvTapeCacheEntry e;
-            e.key = key;
-            e.flags = flags;
-            e.l2p_in = s->l2p;
-            e.gates = gates;
-            e.tape = fresh.release();
-            s->tape_cache.insert(s->tape_cache.begin(), std::move(e));
-            while (s->tape_cache.size() > cache_slots) {
-                delete s->tape_cache.back().tape;
-                s->tape_cache.pop_back();
-            }
-        }
+    std::unique_ptr<qvmcuda_tape> fresh(new qvmcuda_tape());
+    try {
+        const int total_bits = s->n_bits + log2_exact((uint64_t)s->world);
+        fresh->tape = qv::compile(gates, total_bits, make_options(s, flags), s->l2p);
+    } catch (const std::exception& e) {
+        return fail(std::string("schedule: ") + e.what());
     }
+    fresh->flags = flags;
+    fresh->n_local = s->n_bits;
+    fresh->rank = s->rank;
+    fresh->world = s->world;
+    fresh->ephemeral = true;
+    fresh->state_owned = true;
+    layout_tape(fresh.get());
+    if (trace) fprintf(stderr, "[qvmcuda] schedule: %zu steps in %.3f ms\n", fresh->tape.steps.size(),
+                       std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_begin).count());
+    QvTapeCacheEntry e;
+    e.key = key;
+    e.flags = flags;
+    e.l2p_in = s->l2p;
+    e.gates = gates;
+    e.tape = fresh.release();
+    *out = e.tape;
+    s->tape_cache.insert(s->tape_cache.begin(), std::move(e));
+    // evict the least recently used schedules nobody holds a handle to (the newest one always stays)
+    for (size_t i = s->tape_cache.size(); i-- > 1 && s->tape_cache.size() > std::max<size_t>(cache_slots, 1);)
+        if (s->tape_cache[i].tape->checked_out.load() == 0) {
+            delete s->tape_cache[i].tape;
+            s->tape_cache.erase(s->tape_cache.begin() + i);
+        }
+    return 0;
+}
+
+// compile + upload + run in immediate mode (state mutex held)
+int run_gates_locked(qvmcuda_state* s, const std::vector<qv::Gate>& gates, uint32_t flags) {
+    static const bool trace = getenv("QVMCUDA_TRACE") != nullptr;
+    const auto t_begin = std::chrono::steady_clock::now();
+    struct Tracer {
+        bool on; std::chrono::steady_clock::time_point t0; size_t n;
+        ~Tracer() {
+            if (on) fprintf(stderr, "[qvmcuda] apply_gates: %zu gates, host time %.3f ms\n", n,
+                            std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count());
+        }
+    } tracer{trace, t_begin, gates.size()};
+    qvmcuda_tape* tp = nullptr;
+    if (int rc = cached_tape_locked(s, gates, flags, &tp)) return rc;
     qvmcuda_tape& t = *tp;
     if (t.tape.steps.empty()) {
         s->l2p = t.tape.l2p;
@@ -827,20 +847,11 @@ int qvmcuda_shard_compile(qvmcuda_state* s, int n_gates, const int32_t* ks, cons
     std::vector<qv::Gate> gates;
     if (int rc = gates_from_flat(n_gates, ks, qubits, matrices, gates)) return rc;
     std::lock_guard<std::mutex> lk(s->mu);
-    qvmcuda_tape* t = new qvmcuda_tape();
-    t->flags = flags;
-    t->n_local = s->n_bits;
-    t->rank = s->rank;
-    t->world = s->world;
-    t->ephemeral = true;
-    try {
-        const int total_bits = s->n_bits + log2_exact((uint64_t)s->world);
-        t->tape = qv::compile(gates, total_bits, make_options(s, flags), s->l2p);
-    } catch (const std::exception& e) {
-        delete t;
-        return fail(std::string("schedule: ") + e.what());
-    }
-    layout_tape(t);
+    // served from the state's schedule cache: a sharded state keeps the layout a circuit leaves behind, so a circuit run in a
+    // loop cycles through a few (layout, schedule) pairs; the handle is returned with qvmcuda_tape_destroy as usual
+    qvmcuda_tape* t = nullptr;
+    if (int rc = cached_tape_locked(s, gates, flags, &t)) return rc;
+    t->checked_out++;
     *out = t;
     return 0;
 }
@@ -1032,6 +1043,10 @@ int qvmcuda_tape_describe(qvmcuda_tape* t, char* buf, uint64_t buflen) {
 
 int qvmcuda_tape_destroy(qvmcuda_tape* t) {
     if (!t) return 0;
+    if (t->state_owned) {      // a handle from qvmcuda_shard_compile: the tape stays in its state's schedule cache
+        t->checked_out--;
+        return 0;
+    }
     for (auto& kv : t->d_blobs) {
         DeviceGuard dg(kv.first);
         cudaFree(kv.second);
@@ -1400,6 +1415,7 @@ int qvmcuda_shard_attach(qvmcuda_state* s, int rank, int world, const uint8_t* h
     if (rank < 0 || rank >= world) return fail("rank out of range");
     std::lock_guard<std::mutex> lk(s->mu);
     DeviceGuard dg(s->device);
+    drop_tape_cache_locked(s);        // schedules depend on rank / world / the alternate buffer
     for (int r = 0; r < world; r++) {
         if (r == rank) {
             s->peers.base[r] = s->d_amps;
@@ -1442,6 +1458,7 @@ int qvmcuda_shard_attach_alt(qvmcuda_state* s, const uint8_t* handles) {
     std::lock_guard<std::mutex> lk(s->mu);
     if (s->world < 2 || !s->d_alt) return fail("attach the shards and export the alternate buffer first");
     DeviceGuard dg(s->device);
+    drop_tape_cache_locked(s);        // schedules depend on rank / world / the alternate buffer
     for (int r = 0; r < s->world; r++) {
         if (r == s->rank) {
             s->peers_alt.base[r] = s->d_alt;
