@@ -172,6 +172,11 @@ int qvmcuda_shard_attach(qvmcuda_state *s, int rank, int world, const uint8_t *h
  * Protocol: every rank calls export_alt, the host all-gathers the handles, every rank calls attach_alt. */
 int qvmcuda_shard_export_alt(qvmcuda_state *s, uint8_t handle[64]);
 int qvmcuda_shard_attach_alt(qvmcuda_state *s, const uint8_t *handles /* world*64 */);
+/* The same attachment for ONE host process that drives several devices (a single Lisp image with N GPUs): states[r] becomes
+ * rank r of world; peers are reached through CUDA peer access, no IPC handles.  want_alt != 0 also gives every shard the
+ * alternate buffer for pull remaps (all shards or none: without the memory every shard falls back to in-place exchanges).
+ * The host then runs every step on every shard and synchronises all of them around steps flagged QVMCUDA_STEP_PEER. */
+int qvmcuda_shard_attach_local(qvmcuda_state *const *states, int world, int want_alt);
 /* Schedule a gate run against the shard's current qubit layout (gate qubits are LOGICAL, 0 <= q <
  * log2(shard length) + log2(world); every rank must pass the same gate list).  The tape is run step by
  * step: a step whose flags have QVMCUDA_STEP_PEER set reads/writes peer shards over NVLink, so the host

@@ -1475,4 +1475,56 @@ int qvmcuda_shard_attach_alt(qvmcuda_state* s, const uint8_t* handles) {
     return 0;
 }
 
+// One host process driving several devices (the shape of a single Lisp image with N GPUs): the shards are states of the SAME
+// process, so peers are reached through plain peer access instead of IPC handles.  With want_alt every state gets the alternate
+// buffer (pull remaps), all or none.
+int qvmcuda_shard_attach_local(qvmcuda_state* const* states, int world, int want_alt) {
+    if (!states) return fail("null argument");
+    if (world < 2 || world > QV_MAX_PEERS || (world & (world - 1))) return fail("world size must be 2, 4 or 8");
+    for (int r = 0; r < world; r++) {
+        if (!states[r]) return fail("null shard");
+        if (states[r]->n_amps != states[0]->n_amps) return fail("shards differ in length");
+        for (int q = 0; q < r; q++)
+            if (states[q] == states[r] || states[q]->device == states[r]->device) return fail("every shard needs its own device");
+    }
+    for (int r = 0; r < world; r++) {
+        qvmcuda_state* s = states[r];
+        std::lock_guard<std::mutex> lk(s->mu);
+        DeviceGuard dg(s->device);
+        if (int rc = materialize_locked(s)) return rc;
+        for (int q = 0; q < world; q++) {
+            if (q == r) continue;
+            int can = 0;
+            CK(cudaDeviceCanAccessPeer(&can, s->device, states[q]->device));
+            if (!can) return fail("devices cannot access each other's memory");
+            const cudaError_t e = cudaDeviceEnablePeerAccess(states[q]->device, 0);
+            if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) return fail(cudaGetErrorString(e));
+            cudaGetLastError();
+        }
+        if (want_alt && !s->d_alt) {
+            const cudaError_t e = cudaMalloc((void**)&s->d_alt, s->n_amps * sizeof(qvc));
+            if (e != cudaSuccess) {
+                cudaGetLastError();
+                want_alt = 0;       // all or none: fall back to in-place exchanges
+            }
+        }
+    }
+    for (int r = 0; r < world; r++) {
+        qvmcuda_state* s = states[r];
+        std::lock_guard<std::mutex> lk(s->mu);
+        drop_tape_cache_locked(s);
+        for (int q = 0; q < world; q++) {
+            s->peers.base[q] = states[q]->d_amps;
+            s->peers_alt.base[q] = want_alt ? states[q]->d_alt : nullptr;
+        }
+        s->rank = r;
+        s->world = world;
+        s->remap_pull = want_alt != 0;
+        const int total = s->n_bits + log2_exact((uint64_t)world);
+        s->l2p.resize(total);
+        for (int i = 0; i < total; i++) s->l2p[i] = i;
+    }
+    return 0;
+}
+
 }  // extern "C"

@@ -312,6 +312,100 @@ class ShardedState:
 
 
 # --------------------------------------------------------------------------------------- bench (N > 1)
+class LocalShardGroup:
+    """All shards of one state in ONE host process, one device each (`qvmcuda_shard_attach_local`): the shape of a single
+    Lisp image driving several GPUs.  Same schedules, kernels and exchange passes as ShardedState; the barriers around peer
+    steps are stream synchronisations of every shard instead of collective barriers.  Also what lets ncu profile an exchange
+    pass (it cannot follow IPC-mapped memory across processes)."""
+
+    def __init__(self, n_qubits: int, devices: Sequence[int], want_alt: bool = True):
+        from . import _lib as L
+        from .qvm import DeviceVector
+        self.L = L
+        self.world = len(devices)
+        self.g = _log2(self.world)
+        self.n = n_qubits
+        self.n_local = n_qubits - self.g
+        self.vecs = [DeviceVector(1 << self.n_local, d) for d in devices]
+        arr = (C.c_void_p * self.world)(*[v.handle for v in self.vecs])
+        L.check(L.lib().qvmcuda_shard_attach_local(arr, self.world, int(want_alt)))
+        self.steps = self.peer_steps = 0
+        self.set_zero_state()
+
+    def _sync(self):
+        for v in self.vecs:
+            v.synchronize()
+
+    def set_zero_state(self):
+        self._sync()
+        for r, v in enumerate(self.vecs):
+            v.set_basis_state(0)
+            if r:
+                v.scale(0.0)
+        self._sync()
+
+    def layout(self) -> np.ndarray:
+        out = np.zeros(self.n, dtype=np.int32)
+        self.L.check(self.L.lib().qvmcuda_state_layout(self.vecs[0].handle, self.L.ptr(out), self.n))
+        return out
+
+    def apply_gates(self, gates, fuse: bool = True, absorb_swaps: bool = True):
+        L = self.L
+        ks, qf, mf = L.flatten_gates(gates)
+        flags = (L.FUSE if fuse else 0) | (L.ABSORB_SWAPS if absorb_swaps else 0)
+        tapes = []
+        for v in self.vecs:
+            h = C.c_void_p()
+            L.check(L.lib().qvmcuda_shard_compile(v.handle, len(gates), L.ptr(ks), L.ptr(qf), L.ptr(mf), flags, C.byref(h)))
+            tapes.append(h)
+        try:
+            n = C.c_int()
+            L.check(L.lib().qvmcuda_tape_num_steps(tapes[0], C.byref(n)))
+            for i in range(n.value):
+                f = C.c_uint32()
+                L.check(L.lib().qvmcuda_tape_step_flags(tapes[0], i, C.byref(f)))
+                peer = f.value & STEP_PEER
+                if peer:
+                    self._sync()          # every shard complete before anyone reads it remotely
+                for v, t in zip(self.vecs, tapes):
+                    L.check(L.lib().qvmcuda_tape_run_step(v.handle, t, i))
+                if peer:
+                    self._sync()          # remote reads / writes landed before local work resumes
+                    self.peer_steps += 1
+                self.steps += 1
+            for v, t in zip(self.vecs, tapes):
+                L.check(L.lib().qvmcuda_tape_commit(v.handle, t))
+        finally:
+            for t in tapes:
+                L.lib().qvmcuda_tape_destroy(t)
+
+    def norm2(self) -> float:
+        return float(sum(v.norm2() for v in self.vecs))
+
+    def prob_excited(self, q: int) -> float:
+        return float(sum(v.prob_excited(q) for v in self.vecs))
+
+    def scatter_logical(self, psi: np.ndarray):
+        """Canonical layout: shard r holds amplitudes r * 2^n_local ... (tests / small states)."""
+        self.set_zero_state()
+        for r, v in enumerate(self.vecs):
+            v.upload(np.ascontiguousarray(psi[r << self.n_local:(r + 1) << self.n_local]))
+
+    def gather_logical(self) -> np.ndarray:
+        self._sync()
+        phys = np.concatenate([v.download() for v in self.vecs])
+        l2p = self.layout()
+        idx = np.arange(phys.size)
+        src = np.zeros_like(idx)
+        for q in range(self.n):
+            src |= ((idx >> q) & 1) << int(l2p[q])
+        return phys[src]
+
+    def close(self):
+        for v in self.vecs:
+            v.close()
+
+
 def _main_attr(name):
     """bench.py runs as __main__ under torchrun: borrow its helpers (ClockSampler, measured_peaks) when present."""
     import sys
@@ -355,8 +449,15 @@ def _sharded_roofline(local_qubits: int, step_seconds: float, passes_per_step: f
                   "exchange_passes_per_step": peer_passes_per_step,
                   "peak_source": "measured peer copy, 770 GB/s per direction per GPU (B200_PROFILING.md); nominal NVLink 5: 900",
                   "what": "ingress of the passes that load through a qubit remap from peer shards while applying their gates"}
+        local = None
+        n_local_passes = passes_per_step - peer_passes_per_step
+        if n_local_passes > 0 and step_seconds > peer_seconds_per_step:
+            la = bytes_per_pass * n_local_passes / (step_seconds - peer_seconds_per_step) / 1e9
+            local = {"achieved": la, "frac": la / peak, "passes_per_step": n_local_passes,
+                     "ms_per_pass": 1e3 * (step_seconds - peer_seconds_per_step) / n_local_passes,
+                     "what": "the passes that touch only the rank's own shard (HBM-bound): step time minus the exchange passes"}
         return {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                "frac": (achieved / peak) if achieved else None,
+                "frac": (achieved / peak) if achieved else None, "local_passes": local,
                 "traffic": (bytes_per_pass * ratio) if ratio else None,
                 "traffic_source": (traffic.get("source", "") + "; DRAM bytes per pass scale with the shard") if ratio else None,
                 "kernel": "compiled gate passes (qvj_kernel) + qv_tile_kernel per GPU, average over the passes of a step "

@@ -105,3 +105,37 @@ def test_sharded_state_over_nvlink(world, inplace):
         p.join(timeout=60)
     for rank, msg in results:
         assert msg == "ok", f"rank {rank}: {msg}"
+
+
+@pytest.mark.parametrize("want_alt", [True, False])
+def test_single_process_shard_group(want_alt):
+    """One host process, one shard per device (qvmcuda_shard_attach_local: peer access instead of IPC handles) -- the shape of a
+    single Lisp image driving several GPUs.  Same schedules and exchange passes as the one-process-per-GPU path."""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    import helpers
+    from oracle import oracle as O
+    from qvm_b200 import circuits as CC
+    from qvm_b200.dist import LocalShardGroup
+    world = 4 if torch.cuda.device_count() >= 4 else 2
+    n = 18 + (world.bit_length() - 1)
+    grp = LocalShardGroup(n, list(range(world)), want_alt=want_alt)
+    psi = helpers.rand_state(n, 33)
+    rng = np.random.default_rng(9)
+    circ = CC.qft_circuit(range(n)) + helpers.random_circuit(n, 50, rng, max_dense=3)
+    ref = helpers.run_oracle(psi.copy(), circ)
+    for fuse, absorb in ((True, True), (True, False), (False, True)):
+        grp.scatter_logical(psi)
+        grp.apply_gates(circ, fuse=fuse, absorb_swaps=absorb)
+        helpers.assert_close(grp.gather_logical(), ref)
+    assert grp.peer_steps >= 1
+    assert abs(grp.norm2() - 1) < 1e-12
+    for qb in (0, 5, n - 1):
+        assert abs(grp.prob_excited(qb) - O.prob_excited(ref, qb)) < 1e-12
+    # twice in a row from the layout the first run leaves behind
+    grp.scatter_logical(psi)
+    grp.apply_gates(circ)
+    grp.apply_gates(circ)
+    helpers.assert_close(grp.gather_logical(), helpers.run_oracle(ref.copy(), circ))
+    grp.close()
