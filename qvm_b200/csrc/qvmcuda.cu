@@ -133,6 +133,8 @@ struct qvmcuda_tape {
     // still waiting for the asynchronous compiler
     std::map<int, std::vector<qv::JitKernel*>> jit;
     std::map<int, bool> jit_complete;
+    // no-load variant of the first pass (lazy reset), per device; looked up once
+    std::map<int, qv::JitKernel*> jit_basis;
 };
 
 namespace {
@@ -328,7 +330,7 @@ const std::vector<qv::JitKernel*>& tape_jit(qvmcuda_state* s, qvmcuda_tape* t) {
 int materialize_locked(qvmcuda_state* s);
 
 int run_steps(qvmcuda_state* s, const qv::Tape& tape, const std::vector<size_t>& offsets, const uint8_t* d_buf,
-              const std::vector<qv::JitKernel*>* jit = nullptr) {
+              const std::vector<qv::JitKernel*>* jit = nullptr, qvmcuda_tape* owner = nullptr) {
     std::vector<qv::JitKernel*> local;
     if (!jit) {
         prepare_jit(s, tape, local);
@@ -340,13 +342,21 @@ int run_steps(qvmcuda_state* s, const qv::Tape& tape, const std::vector<size_t>&
         const qv::Step& st0 = tape.steps[0];
         qv::JitKernel* jk = nullptr;
         if (s->world == 1 && st0.kind == qv::Step::TILE && !st0.uses_peers && (*jit)[0]) {
-            std::vector<const qv::Step*> one = {&st0};
-            std::vector<qv::JitKernel*> got;
-            qv::jit_prepare(one, s->device, got, qv::kVariantSrcBasis);
-            jk = got[0];
+            auto cached = owner ? owner->jit_basis.find(s->device) : std::map<int, qv::JitKernel*>::iterator();
+            if (owner && cached != owner->jit_basis.end()) {
+                jk = cached->second;
+            } else {
+                std::vector<const qv::Step*> one = {&st0};
+                std::vector<qv::JitKernel*> got;
+                qv::jit_prepare(one, s->device, got, qv::kVariantSrcBasis);
+                jk = got[0];
+                if (owner && qv::jit_policy() != qv::JitPolicy::ASYNC) owner->jit_basis[s->device] = jk;
+            }
         }
         if (jk) {
-            qv::Step patched = st0;
+            qv::Step patched;               // the control program only: the tables already sit in d_buf
+            patched.kind = qv::Step::TILE;
+            patched.blob = st0.blob;
             QvPassHeader h;
             std::memcpy(&h, patched.blob.data(), sizeof(h));
             h.src_basis = 1;
@@ -533,7 +543,7 @@ int run_gates_locked(qvmcuda_state* s, const std::vector<qv::Gate>& gates, uint3
     }
     if (s->scratch_tape != t.id)
         if (int rc = upload_to_scratch_locked(s, t)) return rc;
-    int rc = run_steps(s, t.tape, t.offsets, s->d_scratch, &tape_jit(s, &t));
+    int rc = run_steps(s, t.tape, t.offsets, s->d_scratch, &tape_jit(s, &t), &t);
     if (rc) return rc;
     s->l2p = t.tape.l2p;
     return 0;
@@ -975,7 +985,7 @@ int qvmcuda_tape_run(qvmcuda_state* s, qvmcuda_tape* t) {
     }
     uint8_t* d_buf = nullptr;
     if (int rc = tape_device_buffer(s, t, &d_buf)) return rc;
-    if (int rc = run_steps(s, t->tape, t->offsets, d_buf, &tape_jit(s, t))) return rc;
+    if (int rc = run_steps(s, t->tape, t->offsets, d_buf, &tape_jit(s, t), t)) return rc;
     s->l2p = t->tape.l2p;
     return 0;
 }

@@ -56,6 +56,12 @@ class DeviceVector:
         L.check(L.lib().qvmcuda_download(self.handle, L.ptr(out), offset, count))
         return out
 
+    def download_into(self, dst: np.ndarray, offset: int = 0) -> None:
+        """Straight into caller-owned memory (a POSIX shared-memory mapping, a memory-mapped dump): no intermediate buffer."""
+        if dst.dtype != np.complex128 or not dst.flags["C_CONTIGUOUS"] or not dst.flags["WRITEABLE"]:
+            raise ValueError("destination must be a writable contiguous complex128 array")
+        L.check(L.lib().qvmcuda_download(self.handle, L.ptr(dst), offset, dst.size))
+
     def upload(self, data, offset: int = 0) -> None:
         a = np.ascontiguousarray(data, dtype=np.complex128)
         L.check(L.lib().qvmcuda_upload(self.handle, L.ptr(a), offset, a.size))

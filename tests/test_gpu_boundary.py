@@ -260,3 +260,28 @@ def test_unitary_qvm_matches_gate_products(Q, O):
         e[c] = 1.0
         H.assert_close(u[:, c], H.run_oracle(e, circ))
     np.testing.assert_allclose(u.conj().T @ u, np.eye(1 << n), atol=1e-13)
+
+
+def test_shared_memory_persistent_wavefunction(Q, O, tmp_path):
+    """The app's --shared mode on a device state: the POSIX shared-memory object holds the host-visible copy; refresh() downloads
+    the device state straight into the mapping, a client attaches through the info socket, push() uploads what it wrote."""
+    import uuid
+    from qvm_b200 import shm
+    n = 12
+    m = Q.make_qvm(n)
+    name = f"QVMGPU{uuid.uuid4().hex[:10]}"
+    sw = shm.share_wavefunction(m, name, socket_dir=str(tmp_path))
+    try:
+        view = shm.attach(name, str(tmp_path))
+        assert view[0] == 1.0 and not view[1:].any()
+        m.load_program("\n".join(f"H {q}" for q in range(n)) + "\nCNOT 0 1\n").run()
+        assert view[0] == 1.0                      # not refreshed yet: the amplitudes live in HBM
+        sw.refresh()
+        H.assert_close(view, np.full(1 << n, 2.0 ** (-n / 2), dtype=np.complex128))
+        psi = H.rand_state(n, 4)
+        view[:] = psi
+        sw.push()
+        H.assert_close(m.amplitudes, psi)
+        del view
+    finally:
+        sw.close()
