@@ -172,6 +172,14 @@ int qvmcuda_shard_attach(qvmcuda_state *s, int rank, int world, const uint8_t *h
  * Protocol: every rank calls export_alt, the host all-gathers the handles, every rank calls attach_alt. */
 int qvmcuda_shard_export_alt(qvmcuda_state *s, uint8_t handle[64]);
 int qvmcuda_shard_attach_alt(qvmcuda_state *s, const uint8_t *handles /* world*64 */);
+/* Collective reset of a sharded state (BRING-TO-ZERO-STATE, src/wavefunction.lisp:80-91, on shards): the rank that owns the
+ * non-zero amplitude calls qvmcuda_set_basis_state, every other rank qvmcuda_shard_clear (all zeros; with an alternate buffer
+ * attached the zeros are not even written until something reads them), and EVERY rank then tells the library which ranks hold
+ * only zeros (bit r of mask).  Until the first exchange step, pull passes do not fetch those ranks' amplitudes over NVLink
+ * and local passes on an all-zero shard are skipped.  The host must reset the mask (0) on every rank when any rank's content
+ * changes by other means (an upload); gate runs keep it valid by construction. */
+int qvmcuda_shard_clear(qvmcuda_state *s);
+int qvmcuda_shard_set_zero_ranks(qvmcuda_state *s, uint32_t mask);
 /* The same attachment for ONE host process that drives several devices (a single Lisp image with N GPUs): states[r] becomes
  * rank r of world; peers are reached through CUDA peer access, no IPC handles.  want_alt != 0 also gives every shard the
  * alternate buffer for pull remaps (all shards or none: without the memory every shard falls back to in-place exchanges).

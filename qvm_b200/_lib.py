@@ -70,6 +70,8 @@ _SIGS = {
     "qvmcuda_shard_attach": [C.c_void_p, C.c_int, C.c_int, C.c_void_p],
     "qvmcuda_shard_export_alt": [C.c_void_p, C.c_void_p],
     "qvmcuda_shard_attach_alt": [C.c_void_p, C.c_void_p],
+    "qvmcuda_shard_clear": [C.c_void_p],
+    "qvmcuda_shard_set_zero_ranks": [C.c_void_p, C.c_uint32],
     "qvmcuda_shard_attach_local": [C.c_void_p, C.c_int, C.c_int],
     "qvmcuda_shard_compile": [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.POINTER(C.c_void_p)],
     "qvmcuda_shard_plan": [C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32,

@@ -14,7 +14,7 @@
 
 #include "qv_sched.h"
 
-#define QVJIT_VERSION "qvjit-9"
+#define QVJIT_VERSION "qvjit-10"
 
 struct QvPeers;
 struct qvc;

@@ -159,10 +159,13 @@ qvj_kernel(const __grid_constant__ QvjProg prog, const __grid_constant__ QvPeers
             for (int i = 0; i < ITERS; i++) qv_cp_async16(tile + QVJ_SLOT(i), reinterpret_cast<const qvc*>(tsrc + h->hi_byte[i]));
         } else {
             const uint64_t sbase = qv_remap_index(base | glo, h->pull_remap);
+            const uint32_t zero_ranks = h->zero_ranks;
 #pragma unroll
             for (int i = 0; i < ITERS; i++) {
                 const uint64_t p = sbase ^ h->hi_src[i];
-                qv_cp_async16(tile + QVJ_SLOT(i), peers.base[(p >> n_local) & (QV_MAX_PEERS - 1)] + (p & local_mask));
+                const uint32_t pr = (uint32_t)(p >> n_local) & (QV_MAX_PEERS - 1);
+                // a shard known to hold only zeros (right after a reset) is not fetched: the copy zero-fills
+                qv_cp_async16_z(tile + QVJ_SLOT(i), peers.base[pr] + (p & local_mask), (zero_ranks >> pr & 1u) ? 0u : 16u);
             }
         }
         asm volatile("cp.async.commit_group;" ::: "memory");

@@ -197,7 +197,8 @@ struct QvPassHeader {
     uint32_t src_basis;             // patched at launch time: the state is the basis vector |basis_index> that was never written to
                                     // HBM (lazy SET-TO-ZERO-STATE): the pass synthesises its tiles instead of loading them
     uint32_t pull;                  // 0: in place
-    uint32_t pull_pad;
+    uint32_t zero_ranks;            // pull passes, patched at launch: ranks whose CURRENT buffer is known to hold only zeros (a
+                                    // sharded state right after a reset): their amplitudes are not fetched, the copy zero-fills
     QvRemap pull_remap;
     uint64_t hi_src[32];            // S(hi_off[i])
     uint64_t basis_index;           // src_basis: physical index of the one non-zero amplitude

@@ -32,6 +32,13 @@ __device__ __forceinline__ void qv_cp_async16(qvc* smem_dst, const qvc* gsrc) {
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gsrc) : "memory");
 }
 
+// The same copy with a run-time source size of 16 or 0 bytes: 0 reads nothing and fills the 16 bytes with zeros (amplitudes of
+// a shard that is known to be all zeros are not fetched over NVLink).
+__device__ __forceinline__ void qv_cp_async16_z(qvc* smem_dst, const qvc* gsrc, uint32_t src_bytes) {
+    const uint32_t d = (uint32_t)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(d), "l"(gsrc), "r"(src_bytes) : "memory");
+}
+
 struct QvProgSmall { uint8_t bytes[QV_PROG_SMALL_BYTES]; };
 struct QvProgLarge { uint8_t bytes[QV_PROG_LARGE_BYTES]; };
 

@@ -50,6 +50,7 @@ qv_tile_kernel(const __grid_constant__ PROG prog, const __grid_constant__ QvPeer
     const uint32_t n_local = h->n_local_bits;
     const uint64_t local_mask = (1ull << n_local) - 1ull;
     const uint32_t n_rounds = h->n_rounds;
+    const uint32_t zero_ranks = PULL ? h->zero_ranks : 0u;      // ranks whose current buffer is known to be all zeros
     const QvRound* rounds = reinterpret_cast<const QvRound*>(blob + h->off_rounds);
     const QvUop* uops = reinterpret_cast<const QvUop*>(blob + h->off_uops);
     const QvSource* sources = reinterpret_cast<const QvSource*>(blob + h->off_sources);
@@ -88,16 +89,20 @@ qv_tile_kernel(const __grid_constant__ PROG prog, const __grid_constant__ QvPeer
 #pragma unroll
             for (int i = 0; i < ITERS; i++) {
                 const uint64_t p = PULL ? (sbase ^ h->hi_src[i]) : (pbase | h->hi_off[i]);
-                const qvc* src = (PEERS || PULL) ? peers.base[(p >> n_local) & (QV_MAX_PEERS - 1)] + (p & local_mask) : own + p;
-                qv_cp_async16(my_tile + i * THREADS, src);
+                const uint32_t pr = (uint32_t)(p >> n_local) & (QV_MAX_PEERS - 1);
+                const qvc* src = (PEERS || PULL) ? peers.base[pr] + (p & local_mask) : own + p;
+                if (PULL) qv_cp_async16_z(my_tile + i * THREADS, src, (zero_ranks >> pr & 1u) ? 0u : 16u);
+                else qv_cp_async16(my_tile + i * THREADS, src);
             }
         } else {
             for (uint32_t i = 0; i < iters; i++) {
                 const uint32_t e = tid + i * THREADS;
                 if (e < tile_n) {
                     const uint64_t p = PULL ? (sbase ^ h->hi_src[i]) : (pbase | h->hi_off[i]);
-                    const qvc* src = (PEERS || PULL) ? peers.base[(p >> n_local) & (QV_MAX_PEERS - 1)] + (p & local_mask) : own + p;
-                    qv_cp_async16(my_tile + i * THREADS, src);
+                    const uint32_t pr = (uint32_t)(p >> n_local) & (QV_MAX_PEERS - 1);
+                    const qvc* src = (PEERS || PULL) ? peers.base[pr] + (p & local_mask) : own + p;
+                    if (PULL) qv_cp_async16_z(my_tile + i * THREADS, src, (zero_ranks >> pr & 1u) ? 0u : 16u);
+                    else qv_cp_async16(my_tile + i * THREADS, src);
                 }
             }
         }

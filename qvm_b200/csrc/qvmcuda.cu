@@ -57,6 +57,7 @@ int log2_exact(uint64_t n) {
 }
 
 constexpr uint32_t kReduceBlocks = 148 * 8;
+constexpr uint64_t kLazyAllZero = ~0ull;
 
 }  // namespace
 
@@ -87,7 +88,10 @@ struct qvmcuda_state {
     // thing that happens is a compiled gate pass, that pass synthesises its tiles instead of loading them (no 16 B/amplitude
     // reset write, no 16 B/amplitude read in the first pass); anything else writes the vector first (materialize_locked).
     bool lazy_basis = false;
-    uint64_t lazy_index = 0;
+    uint64_t lazy_index = 0;       // kLazyAllZero: the vector holds only zeros (a shard of a freshly reset sharded state)
+    // sharded: ranks (bit r) whose CURRENT buffer is known to hold only zeros -- set by the host right after a collective reset
+    // (qvmcuda_shard_set_zero_ranks), cleared by the first exchange step.  Pull passes do not fetch those ranks' amplitudes.
+    uint32_t zero_ranks = 0;
     std::vector<QvTapeCacheEntry> tape_cache;      // most recent first
     // multi-GPU
     int rank = 0, world = 1;
@@ -200,8 +204,17 @@ int launch_tile_p(qvmcuda_state* s, const qv::Step& st, const QvPassHeader& h, c
     } else if (h.uses_peers) {
         mode = 1;
     }
+    std::vector<uint8_t> patched;
+    const uint8_t* blob = st.blob.data();
+    if (mode == 2 && s->zero_ranks) {      // known-zero shards: the pass zero-fills instead of fetching them
+        patched = st.blob;
+        QvPassHeader hp = h;
+        hp.zero_ranks = s->zero_ranks;
+        std::memcpy(patched.data(), &hp, sizeof(hp));
+        blob = patched.data();
+    }
     QvTileLaunch L;
-    L.blob = st.blob.data();
+    L.blob = blob;
     L.blob_bytes = st.blob.size();
     L.full = full;
     L.grid = tile_grid(s, h.n_tiles);
@@ -305,9 +318,12 @@ int launch_remap(qvmcuda_state* s, const qv::Step& st) {
 }
 
 int launch_step(qvmcuda_state* s, const qv::Step& st, const uint8_t* d_data, qv::JitKernel* jk = nullptr) {
-    if (st.kind == qv::Step::TILE) return launch_tile(s, st, d_data, jk);
-    if (st.kind == qv::Step::BIG) return launch_big(s, st, d_data);
-    return launch_remap(s, st);
+    int rc;
+    if (st.kind == qv::Step::TILE) rc = launch_tile(s, st, d_data, jk);
+    else if (st.kind == qv::Step::BIG) rc = launch_big(s, st, d_data);
+    else rc = launch_remap(s, st);
+    if (st.uses_peers || st.kind == qv::Step::REMAP) s->zero_ranks = 0;     // after an exchange nobody is known to be zero
+    return rc;
 }
 
 // kernels of the compiled passes of a tape on the state's device (nullptr entries run through the interpreter kernel)
@@ -419,6 +435,7 @@ int materialize_locked(qvmcuda_state* s) {
     if (!s->lazy_basis) return 0;
     s->lazy_basis = false;
     CK(cudaMemsetAsync(s->d_amps, 0, s->n_amps * sizeof(qvc), s->stream));
+    if (s->lazy_index == kLazyAllZero) return 0;
     qv_set_one_kernel<<<1, 1, 0, s->stream>>>(s->d_amps, s->lazy_index);
     g_launches++;
     CK(cudaGetLastError());
@@ -861,6 +878,27 @@ int qvmcuda_shard_compile(qvmcuda_state* s, int n_gates, const int32_t* ks, cons
     // loop cycles through a few (layout, schedule) pairs; the handle is returned with qvmcuda_tape_destroy as usual
     qvmcuda_tape* t = nullptr;
     if (int rc = cached_tape_locked(s, gates, flags, &t)) return rc;
+    if (s->lazy_basis) {
+        // A shard that holds only zeros stays unwritten if nothing will read it: local passes map zeros to zeros (skipped),
+        // and a fused pull pass does not fetch ranks flagged in zero_ranks.  Anything else (in-place peer pass, stand-alone
+        // remap kernel, dense k >= 3 gate) reads memory: write the zeros NOW, before the host's barrier in front of the first
+        // exchange step, because peers read this buffer.
+        bool stay = s->lazy_index == kLazyAllZero && (s->zero_ranks >> s->rank & 1u);
+        for (const qv::Step& st : t->tape.steps) {
+            if (!stay) break;
+            if (st.kind != qv::Step::TILE) stay = false;
+            else if (st.uses_peers) {
+                QvPassHeader h;
+                std::memcpy(&h, st.blob.data(), sizeof(h));
+                stay = h.pull != 0;
+                break;
+            }
+        }
+        if (!stay) {
+            DeviceGuard dg(s->device);
+            if (int rc = materialize_locked(s)) return rc;
+        }
+    }
     t->checked_out++;
     *out = t;
     return 0;
@@ -946,10 +984,21 @@ int qvmcuda_tape_run_step(qvmcuda_state* s, qvmcuda_tape* t, int step) {
     if (t->n_local != s->n_bits || t->rank != s->rank || t->world != s->world)
         return fail("tape was compiled for a different shard geometry");
     DeviceGuard dg(s->device);
-    if (int rc = materialize_locked(s)) return rc;
+    const qv::Step& st = t->tape.steps[step];
+    if (s->lazy_basis && s->lazy_index == kLazyAllZero && st.kind == qv::Step::TILE) {
+        QvPassHeader h;
+        std::memcpy(&h, st.blob.data(), sizeof(h));
+        if (!st.uses_peers) return 0;                  // zeros in, zeros out: nothing to run, nothing to write
+        if (h.pull && s->remap_pull && (s->zero_ranks >> s->rank & 1u)) {
+            s->lazy_basis = false;                     // nobody fetches this buffer; the pass writes the alternate one in full
+        } else if (int rc = materialize_locked(s)) {
+            return rc;
+        }
+    } else if (int rc = materialize_locked(s)) {
+        return rc;
+    }
     uint8_t* d_buf = nullptr;
     if (int rc = tape_device_buffer(s, t, &d_buf)) return rc;
-    const qv::Step& st = t->tape.steps[step];
     return launch_step(s, st, d_buf + t->offsets[step], tape_jit(s, t)[step]);
 }
 
@@ -1482,6 +1531,26 @@ int qvmcuda_shard_attach_alt(qvmcuda_state* s, const uint8_t* handles) {
         s->peers_alt.base[r] = (qvc*)p;
     }
     s->remap_pull = true;
+    return 0;
+}
+
+int qvmcuda_shard_clear(qvmcuda_state* s) {
+    if (!s) return fail("null argument");
+    std::lock_guard<std::mutex> lk(s->mu);
+    DeviceGuard dg(s->device);
+    for (size_t i = 0; i < s->l2p.size(); i++) s->l2p[i] = (int)i;   // content is replaced: layout resets
+    static const bool lazy = !(getenv("QVMCUDA_LAZY_RESET") && atoi(getenv("QVMCUDA_LAZY_RESET")) == 0);
+    s->lazy_basis = true;
+    s->lazy_index = kLazyAllZero;
+    if (!lazy || s->world < 2 || !s->remap_pull) return materialize_locked(s);
+    return 0;
+}
+
+int qvmcuda_shard_set_zero_ranks(qvmcuda_state* s, uint32_t mask) {
+    if (!s) return fail("null argument");
+    std::lock_guard<std::mutex> lk(s->mu);
+    if (s->world < 2) return fail("not a shard");
+    s->zero_ranks = mask & ((1u << s->world) - 1u);
     return 0;
 }
 

@@ -95,9 +95,8 @@ class CudaShardEngine:
         return out
 
     def set_basis_local(self, index): self.vec.set_basis_state(index)
-    def clear(self):
-        self.vec.set_basis_state(0)
-        self.vec.scale(0.0)
+    def clear(self): self.L.check(self.L.lib().qvmcuda_shard_clear(self.vec.handle))
+    def set_zero_ranks(self, mask): self.L.check(self.L.lib().qvmcuda_shard_set_zero_ranks(self.vec.handle, int(mask)))
     def norm2(self): return self.vec.norm2()
     def prob_excited(self, q): return self.vec.prob_excited(q)
     def collapse(self, q, keep, inv): self.vec.collapse(q, keep, inv)
@@ -127,6 +126,9 @@ class ShardedState:
         # read peer shards and the bytes this rank pulled over NVLink in them
         self.peer_seconds = 0.0
         self.peer_bytes = 0.0
+        # ranks whose shard is known to hold only zeros (right after a collective reset; every rank keeps the same mask because
+        # every method that changes content is collective): their amplitudes are not fetched by the first exchange pass
+        self._zero_ranks = 0
         self.set_zero_state()
 
     # ---- plumbing -------------------------------------------------------------------------------
@@ -149,6 +151,7 @@ class ShardedState:
             self.engine.set_basis_local(0)
         else:
             self.engine.clear()
+        self._zero_ranks = ((1 << self.world) - 1) & ~1
         # content replaced: layout resets inside the engine (set_basis_state); barrier so that no peer pass
         # starts before every shard is initialised
         self._barrier()
@@ -158,6 +161,8 @@ class ShardedState:
         `layout()` on the host, dqvm's "record the permutation instead of undoing it" -- so an exact SWAP gate only exchanges
         the two qubits' entries in the layout; no amplitude moves.  Off: SWAPs between local qubits run as gates (folded into
         a pass's write-back where they trail it), SWAPs touching a rank bit are still relabelings."""
+        if hasattr(self.engine, "set_zero_ranks"):
+            self.engine.set_zero_ranks(self._zero_ranks)     # before compile: it decides whether an all-zero shard is ever written
         tape = self.engine.compile(gates, fuse=fuse, absorb_swaps=absorb_swaps)
         trace = os.environ.get("QVM_DIST_TRACE") and self.rank == 0
         try:
@@ -188,6 +193,7 @@ class ShardedState:
                         self.peer_bytes += shard_bytes * frac
                     self._barrier()       # remote writes must have landed before local work resumes
                     self.peer_steps += 1
+                    self._zero_ranks = 0  # after an exchange every shard may hold amplitudes
                 self.steps += 1
             self.engine.commit(tape)
         finally:
@@ -295,6 +301,7 @@ class ShardedState:
         mm = np.memmap(filename, dtype=np.complex128, mode="r", shape=(1 << self.n,))
         lo = self.rank << self.n_local
         self.engine.upload(np.ascontiguousarray(mm[lo: lo + (1 << self.n_local)]))
+        self._zero_ranks = 0
         del mm
         self._barrier()
 
@@ -304,6 +311,7 @@ class ShardedState:
         self._barrier()
         lo = self.rank << self.n_local
         self.engine.upload(np.ascontiguousarray(psi[lo: lo + (1 << self.n_local)]))
+        self._zero_ranks = 0
         self._barrier()
 
     def close(self):
@@ -330,6 +338,7 @@ class LocalShardGroup:
         arr = (C.c_void_p * self.world)(*[v.handle for v in self.vecs])
         L.check(L.lib().qvmcuda_shard_attach_local(arr, self.world, int(want_alt)))
         self.steps = self.peer_steps = 0
+        self._zero_ranks = 0
         self.set_zero_state()
 
     def _sync(self):
@@ -338,10 +347,10 @@ class LocalShardGroup:
 
     def set_zero_state(self):
         self._sync()
-        for r, v in enumerate(self.vecs):
-            v.set_basis_state(0)
-            if r:
-                v.scale(0.0)
+        self.vecs[0].set_basis_state(0)
+        for v in self.vecs[1:]:
+            self.L.check(self.L.lib().qvmcuda_shard_clear(v.handle))
+        self._zero_ranks = ((1 << self.world) - 1) & ~1
         self._sync()
 
     def layout(self) -> np.ndarray:
@@ -354,6 +363,8 @@ class LocalShardGroup:
         ks, qf, mf = L.flatten_gates(gates)
         flags = (L.FUSE if fuse else 0) | (L.ABSORB_SWAPS if absorb_swaps else 0)
         tapes = []
+        for v in self.vecs:
+            L.check(L.lib().qvmcuda_shard_set_zero_ranks(v.handle, self._zero_ranks))
         for v in self.vecs:
             h = C.c_void_p()
             L.check(L.lib().qvmcuda_shard_compile(v.handle, len(gates), L.ptr(ks), L.ptr(qf), L.ptr(mf), flags, C.byref(h)))
@@ -372,6 +383,7 @@ class LocalShardGroup:
                 if peer:
                     self._sync()          # remote reads / writes landed before local work resumes
                     self.peer_steps += 1
+                    self._zero_ranks = 0
                 self.steps += 1
             for v, t in zip(self.vecs, tapes):
                 L.check(L.lib().qvmcuda_tape_commit(v.handle, t))
@@ -390,6 +402,7 @@ class LocalShardGroup:
         self.set_zero_state()
         for r, v in enumerate(self.vecs):
             v.upload(np.ascontiguousarray(psi[r << self.n_local:(r + 1) << self.n_local]))
+        self._zero_ranks = 0
 
     def gather_logical(self) -> np.ndarray:
         self._sync()

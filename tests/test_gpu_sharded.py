@@ -55,6 +55,22 @@ def _worker(rank, world, port, q, inplace):
                 ref = helpers.run_oracle(psi.copy(), circ)
                 helpers.assert_close(got, ref)
         assert st.peer_steps >= 1
+        # straight from the collective reset: the shards of ranks != 0 are known to hold only zeros (never written in pull mode),
+        # the first exchange pass does not fetch them
+        zero = np.zeros(1 << n, dtype=np.complex128)
+        zero[0] = 1.0
+        zref = helpers.run_oracle(zero.copy(), circ)
+        for fuse in (True, False):
+            st.set_zero_state()
+            st.apply_gates(circ, fuse=fuse)
+            got = st.gather_logical()
+            if rank == 0:
+                helpers.assert_close(got, zref)
+        st.set_zero_state()
+        assert abs(st.norm2() - 1) == 0 and st.prob_excited(n - 1) == 0.0       # readers of a never-written shard
+        st.set_zero_state()
+        st.scatter_logical(psi)
+        st.apply_gates(circ, fuse=True)
         assert abs(st.norm2() - 1) < 1e-12
         ref = helpers.run_oracle(psi.copy(), circ)
         for qb in (0, 7, n - 2, n - 1):
@@ -133,6 +149,12 @@ def test_single_process_shard_group(want_alt):
     assert abs(grp.norm2() - 1) < 1e-12
     for qb in (0, 5, n - 1):
         assert abs(grp.prob_excited(qb) - O.prob_excited(ref, qb)) < 1e-12
+    # from the reset state: zero shards are not fetched by the first exchange
+    zero = np.zeros(1 << n, dtype=np.complex128)
+    zero[0] = 1.0
+    grp.set_zero_state()
+    grp.apply_gates(circ)
+    helpers.assert_close(grp.gather_logical(), helpers.run_oracle(zero, circ))
     # twice in a row from the layout the first run leaves behind
     grp.scatter_logical(psi)
     grp.apply_gates(circ)
