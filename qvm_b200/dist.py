@@ -505,6 +505,11 @@ def sharded_parity_check(dist_mod, rank: int, world: int, device: int, n_small: 
             phys = st.gather_physical()
             idx = st.sample_physical(u, False)
             res = {"exchange_passes": st.peer_steps}
+            # ... and straight from the collective reset (the known-zero-shards path: lazily cleared shards, the first exchange
+            # pass does not fetch them)
+            st.set_zero_state()
+            st.apply_gates(circ, fuse=True)
+            got0 = st.gather_logical()
             if rank == 0:
                 from oracle import oracle as O      # the checker, not the thing measured
                 if ref is None:
@@ -515,7 +520,12 @@ def sharded_parity_check(dist_mod, rank: int, world: int, device: int, n_small: 
                 res["max_abs_err"] = float(err.max())
                 res["amplitudes_ok"] = bool((err <= 1e-14 + 1e-12 * np.abs(ref)).all())
                 res["sampler_bit_exact"] = bool((idx == O.sample_tree_sharded(phys, world, u, False)).all())
-                ok_all = ok_all and res["amplitudes_ok"] and res["sampler_bit_exact"]
+                ref0 = np.zeros(1 << n_small, dtype=np.complex128)
+                ref0[0] = 1.0
+                for m, q in circ:
+                    O.apply_matrix(ref0, m, q)
+                res["amplitudes_ok_from_reset"] = bool((np.abs(got0 - ref0) <= 1e-14 + 1e-12 * np.abs(ref0)).all())
+                ok_all = ok_all and res["amplitudes_ok"] and res["sampler_bit_exact"] and res["amplitudes_ok_from_reset"]
             st.close()
             out["modes"][mode] = res
         finally:
