@@ -485,9 +485,13 @@ int cached_tape_locked(qvmcuda_state* s, const std::vector<qv::Gate>& gates, uin
     static const size_t cache_slots = getenv("QVMCUDA_TAPE_CACHE") ? (size_t)atoi(getenv("QVMCUDA_TAPE_CACHE")) : 4;
     uint64_t key = 1469598103934665603ull;
     auto mix = [&key](const void* p, size_t n) {
-        const uint64_t* w = static_cast<const uint64_t*>(p);
-        for (size_t i = 0; i < n / 8; i++) key = (key ^ w[i]) * 1099511628211ull;
-        const uint8_t* b = static_cast<const uint8_t*>(p) + (n & ~(size_t)7);
+        const uint8_t* raw = static_cast<const uint8_t*>(p);
+        for (size_t i = 0; i < n / 8; i++) {
+            uint64_t w;
+            std::memcpy(&w, raw + 8 * i, 8);      // the qubit lists are only 4-byte aligned
+            key = (key ^ w) * 1099511628211ull;
+        }
+        const uint8_t* b = raw + (n & ~(size_t)7);
         for (size_t i = 0; i < (n & 7); i++) key = (key ^ b[i]) * 1099511628211ull;
     };
     for (const qv::Gate& g : gates) {
@@ -1102,8 +1106,10 @@ int qvmcuda_tape_describe(qvmcuda_tape* t, char* buf, uint64_t buflen) {
 
 int qvmcuda_tape_destroy(qvmcuda_tape* t) {
     if (!t) return 0;
-    if (t->state_owned) {      // a handle from qvmcuda_shard_compile: the tape stays in its state's schedule cache
-        t->checked_out--;
+    if (t->state_owned) {      // a handle from qvmcuda_shard_compile: the tape stays in its state's schedule cache (destroy the
+                               // handle before the state it came from)
+        int c = t->checked_out.load();
+        while (c > 0 && !t->checked_out.compare_exchange_weak(c, c - 1)) {}
         return 0;
     }
     for (auto& kv : t->d_blobs) {
