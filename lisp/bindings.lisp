@@ -54,6 +54,23 @@
 (defcuda density-measure-discard "qvmcuda_density_measure_discard" (state :pointer) (n-qubits :int) (qubit :int))
 (defcuda density-diag-probs "qvmcuda_density_diag_probs" (state :pointer) (n-qubits :int) (out :pointer))
 
+;;; expectation / unitary-qvm rows (app/src/api/expectation.lisp:78-107, src/unitary-qvm.lisp:30-137)
+(defcuda density-expectation "qvmcuda_density_expectation" (state :pointer) (n-qubits :int) (op-matrix :pointer) (out :pointer))
+(defcuda set-identity-matrix "qvmcuda_set_identity_matrix" (state :pointer) (n-qubits :int))
+;;; several devices under one Lisp image (INTEGRATION.md section 3c): STATES is a foreign array of WORLD state pointers
+(defcuda shard-attach-local "qvmcuda_shard_attach_local" (states :pointer) (world :int) (want-alt :int))
+(defcuda shard-compile "qvmcuda_shard_compile" (state :pointer) (n-gates :int) (ks :pointer) (qubits :pointer)
+  (matrices :pointer) (flags :uint32) (out :pointer))
+(defcuda tape-num-steps "qvmcuda_tape_num_steps" (tape :pointer) (n-steps :pointer))
+(defcuda tape-step-flags "qvmcuda_tape_step_flags" (tape :pointer) (step :int) (flags :pointer))
+(defcuda tape-run-step "qvmcuda_tape_run_step" (state :pointer) (tape :pointer) (step :int))
+(defcuda tape-commit "qvmcuda_tape_commit" (state :pointer) (tape :pointer))
+(defcuda tape-destroy "qvmcuda_tape_destroy" (tape :pointer))
+(defcuda state-layout "qvmcuda_state_layout" (state :pointer) (l2p :pointer) (n :int))
+(defcuda shard-clear "qvmcuda_shard_clear" (state :pointer))
+(defcuda shard-set-zero-ranks "qvmcuda_shard_set_zero_ranks" (state :pointer) (mask :uint32))
+
+(defconstant +step-peer+ 1)
 (defconstant +fuse+ 1)
 (defconstant +absorb-swaps+ 2)
 
