@@ -290,7 +290,7 @@ def run_ours(args):
         ratios = {"gpu_one_gate_per_pass_vs_cpu_one_gate_per_pass": unfused["gates_per_s"] / cpu["value"],
                   "gpu_fused_vs_cpu_one_gate_per_pass": value / cpu["value"],
                   "note": "like for like is the first (both sides one HBM/DRAM pass per gate); the second also contains the "
-                          "scheduler's packing of 480 gates into 6 passes, which a same-support matrix fusion on the CPU side "
+                          "scheduler's packing of 480 gates into a handful of passes (config.hbm_passes_per_step), which a same-support matrix fusion on the CPU side "
                           "would not give the QFT (no two consecutive gates act on the same qubits)"}
 
     print(json.dumps({
