@@ -1341,7 +1341,8 @@ Tape compile(const std::vector<Gate>& gates, int n_bits, const CompileOptions& o
     if (opt.fuse && opt.route_swaps < 0) {
         // Exact SWAP gates either run where they stand (folded into a pass's write-back when they trail it, else a pass of
         // their own) or are absorbed as relabelings whose physical permutation is spread over the spare tile slots of the
-        // gate passes (route_swaps = 1).  Both tapes leave the state in the same layout; keep the cheaper one.
+        // gate passes (route_swaps = 1).  From the canonical layout both tapes end in the canonical layout; from another one
+        // (left behind by an absorb_swaps run) the plain tape keeps it and the routed tape canonicalises.  Keep the cheaper one.
         CompileOptions o = opt;
         o.route_swaps = 0;
         const int nl = opt.n_local_bits > 0 ? opt.n_local_bits : n_bits;
