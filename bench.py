@@ -225,8 +225,8 @@ def run_ours(args):
     prep_s = time.perf_counter() - t_prep
     j1 = _lib.jit_stats()
 
-    # ---- headline: fused tape, state resident in HBM
-    vec.set_zero_state()
+    # ---- headline: fused tape, state resident in HBM (the state the preparation run left behind: a reset here would be lazy and
+    #      make the first pass of the first step a cheaper write-only pass)
     clocks = ClockSampler(local_rank)
     dt, launches = timed(lambda: vec.run_tape(tape), args.steps, args.warmup)
     clk = clocks.stop()
