@@ -1800,8 +1800,9 @@ Tape compile(const std::vector<Gate>& gates, int n_bits, const CompileOptions& o
                     tape.steps.back().n_gates = (int)in_pass.size();
                     tape.n_routed += (int)(with_swaps.size() - in_pass.size());
                     w2p = newpos;
-                } else
-                tape.steps.push_back(build_tile_step(in_pass, targets, geo, lay));
+                } else {
+                    tape.steps.push_back(build_tile_step(in_pass, targets, geo, lay));
+                }
                 break;
             } catch (const std::length_error&) {
                 if (in_pass.size() < 2) throw std::runtime_error("scheduler: a single atom overflows a pass");
