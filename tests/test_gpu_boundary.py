@@ -285,3 +285,32 @@ def test_shared_memory_persistent_wavefunction(Q, O, tmp_path):
         del view
     finally:
         sw.close()
+
+
+def test_copy_wavefunction_every_length_combination(Q):
+    """tests/wavefunction-tests.lisp:35-75 (test-copy-wavefunction): COPY-WAVEFUNCTION copies min(|src|, |dst|) amplitudes for every
+    combination of vector lengths and leaves the rest of the destination alone (a device state has at least one qubit, so the
+    reference's 1-element case starts at 2 here)."""
+    srcs = {k: np.arange(1, k + 1).astype(np.complex128) for k in (2, 4, 8, 16)}
+    for ks, a in srcs.items():
+        for kd in (2, 4, 8, 16):
+            s, d = Q.DeviceVector(ks), Q.DeviceVector(kd)
+            s.upload(a)
+            d.upload(np.full(kd, -7.0, dtype=np.complex128))
+            d.copy_from(s)
+            got = d.download()
+            m = min(ks, kd)
+            assert np.array_equal(got[:m], a[:m]) and (got[m:] == -7.0).all()
+            s.close()
+            d.close()
+
+
+def test_unitary_qvm_reference_known_answers(Q):
+    """tests/unitary-tests.lisp:3-24: CNOT 0 1; CNOT 1 0; CNOT 0 1 is the SWAP matrix; a unitary QVM refuses MEASURE."""
+    u = Q.parsed_program_unitary_matrix("CNOT 0 1\nCNOT 1 0\nCNOT 0 1", 2)
+    swap = np.array([[1, 0, 0, 0], [0, 0, 1, 0], [0, 1, 0, 0], [0, 0, 0, 1]], dtype=np.complex128)
+    assert np.array_equal(u, swap)
+    m = Q.UnitaryQVM(2)
+    m.load_program("CNOT 0 1\nMEASURE 0")
+    with pytest.raises(Exception):
+        m.run()
