@@ -123,3 +123,111 @@ def test_gate_tests(Q):
         amps = Q.run_program(1, "DEFGATE G(%a):\n    cos(%a), sin(%a)\n    -sin(%a), cos(%a)\n\nG(0.0) 0").amplitudes
         assert amps[0] == 1.0 and amps[1] == 0.0
     _modes(Q, run)
+
+
+# ---------------------------------------------------------------- tests/density-qvm-tests.lisp, tests/noisy-qvm-tests.lisp
+def _pauli_noise_map(px, py, pz):
+    """MAKE-PAULI-NOISE-MAP src/noisy-qvm.lisp:43-66 (the identity term comes first, as PUSH leaves it)."""
+    from qvm_b200 import gates as G
+    ops = [math.sqrt(p) * G.gate_matrix(s) for s, p in zip("XYZ", (px, py, pz))]
+    psum = px + py + pz
+    if psum < 1:
+        ops.insert(0, math.sqrt(1.0 - psum) * np.eye(2, dtype=np.complex128))
+    return ops
+
+
+def _pauli_perturbed_1q_gate(name, px, py, pz):
+    """MAKE-PAULI-PERTURBED-1Q-GATE src/noisy-qvm.lisp:69-78: the ideal gate followed by the noisy identity."""
+    from qvm_b200 import gates as G
+    u = G.gate_matrix(name)
+    return [v @ u for v in _pauli_noise_map(px, py, pz)]
+
+
+def _trace(m):
+    return float(np.real(np.trace(m.state.matrix_view())))
+
+
+def _purity(m):
+    rho = m.state.matrix_view()
+    return float(np.real(np.trace(rho @ rho)))
+
+
+def test_density_qvm_parametric_gate_and_force_measurement(Q):
+    """test-density-qvm-parametric-gate :25-34, -force-measurement-1q :36-44, -force-measurement-4q :46-60."""
+    m = Q.make_density_qvm(1)
+    m.load_program("DEFGATE G(%a):\n    cos(%a), sin(%a)\n    -sin(%a), cos(%a)\n\nG(0.0) 0").run()
+    assert abs(np.real(m.state.matrix_view()[0, 0]) - 1) < 1e-4
+    m = Q.make_density_qvm(1)
+    m.load_program("H 0").run()
+    m.state.vec.density_collapse(1, 0, 1, 1 / 0.5)                 # (force-measurement 1 0 state 0.5)
+    assert abs(_trace(m) - 1) < 1e-12 and abs(np.real(m.state.matrix_view()[1, 1]) - 1) < 1e-12
+    m = Q.make_density_qvm(4)
+    m.load_program("H 0\nCNOT 0 1\nCNOT 1 3\nH 3").run()
+    assert abs(_trace(m) - 1) < 1e-12
+    p = m.state.vec.density_prob_excited(4, 3)
+    m.state.vec.density_collapse(4, 3, 1, 1 / p)
+    assert abs(_trace(m) - 1) < 1e-12
+
+
+@pytest.mark.parametrize("p", [0.1, 0.4, 0.5, 0.6, 0.9])
+def test_density_qvm_unitary_evolution_preserves_purity(Q, p):
+    """test-density-qvm-1q-purity :90-98 and -2q-purity :100-108: mixtures loaded through (setf amplitudes)."""
+    expected = (1 - p) ** 2 + p ** 2
+    m = Q.make_density_qvm(1)
+    m.amplitudes = np.diag([1 - p, p]).astype(np.complex128).ravel()
+    assert abs(_purity(m) - expected) < 1e-12
+    m.load_program("H 0").run()
+    assert abs(_purity(m) - expected) < 1e-12
+    m = Q.make_density_qvm(2)
+    m.amplitudes = np.kron(np.diag([1 - p, p]), np.full((2, 2), 0.5)).astype(np.complex128).ravel()
+    assert abs(_purity(m) - expected) < 1e-12
+    m.load_program("CNOT 0 1").run()
+    assert abs(_purity(m) - expected) < 1e-12
+
+
+def test_density_qvm_noisy_readout_and_measure_all(Q):
+    """test-noisy-readout-2q-qvm (tests/noisy-qvm-tests.lisp:114-139) on the density QVM (:110-112) and
+    test-density-qvm-noisy-measure-all :116-140: POVM (0.8 0.1 / 0.2 0.9) on qubit 1."""
+    m = Q.make_density_qvm(2, seed=7)
+    m.load_program("DECLARE ro BIT[2]\nMEASURE 0 ro[0]\nMEASURE 1 ro[1]")
+    wanted = {0, 1}
+    tries = 500
+    while wanted and tries > 0:
+        tries -= 1
+        m.reset_quantum_state()
+        m.set_readout_povm(1, (0.8, 0.1, 0.2, 0.9))
+        m.registers["ro"][:] = 0
+        m.run()
+        assert m.registers["ro"][0] == 0
+        wanted.discard(int(m.registers["ro"][1]))
+    assert tries > 0
+    m = Q.make_density_qvm(2, seed=11)
+    m.load_program("X 0\nX 1")
+    wanted = {(1, 1), (1, 0)}
+    tries = 500
+    while wanted and tries > 0:
+        tries -= 1
+        m.reset_quantum_state()
+        m.set_readout_povm(1, (0.8, 0.1, 0.2, 0.9))
+        m.run()
+        wanted.discard(tuple(m.measure_all()))
+    assert tries > 0
+
+
+def test_noisy_x_gate_with_certain_bit_flip(Q):
+    """test-density-qvm-noisy-x-gate :158-169 and test-noisy-x-gate (tests/noisy-qvm-tests.lisp:98-112): X followed by a bit flip
+    with probability 1 measures 0 -- on the density QVM (one superoperator) and on the pure-state QVM (stochastic Kraus)."""
+    kraus = _pauli_perturbed_1q_gate("X", 1.0, 0.0, 0.0)
+    m = Q.make_density_qvm(2)
+    m.set_noisy_gate("X", (0,), kraus)
+    m.load_program("DECLARE ro BIT\nX 0\nMEASURE 0 ro").run()
+    assert m.registers["ro"][0] == 0
+    for compiled in (False, True):
+        Q.compile_before_running = compiled
+        try:
+            m = Q.make_qvm(2, seed=3)
+            m.set_superoperator("X", (0,), kraus)
+            m.load_program("DECLARE ro BIT\nX 0\nMEASURE 0 ro").run()
+            assert m.registers["ro"][0] == 0
+        finally:
+            Q.compile_before_running = False
