@@ -34,9 +34,19 @@ def emulator():
         srcs = [os.path.join(SUPPORT, "qv_emulator.cpp"), os.path.join(ROOT, "qvm_b200", "csrc", "qv_sched.cpp"),
                 os.path.join(ROOT, "qvm_b200", "csrc", "qv_jit_gen.cpp")]
         deps = srcs + [os.path.join(ROOT, "qvm_b200", "csrc", f) for f in ("qv_ops.h", "qv_program.h", "qv_sched.h", "qv_jit.h")]
-        if not os.path.exists(so) or any(os.path.getmtime(d) > os.path.getmtime(so) for d in deps):
-            subprocess.check_call(["/usr/bin/g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-Wno-unknown-pragmas",
-                                   "-o", so] + srcs + ["-ldl"])
+        def stale():
+            return not os.path.exists(so) or any(os.path.getmtime(d) > os.path.getmtime(so) for d in deps)
+        if stale():
+            # pytest-xdist workers race here after a source change: one builds (into a temporary name, renamed when complete),
+            # the others wait for the lock and find the library fresh
+            import fcntl
+            with open(so + ".lock", "w") as lock:
+                fcntl.flock(lock, fcntl.LOCK_EX)
+                if stale():
+                    tmp = f"{so}.{os.getpid()}.tmp"
+                    subprocess.check_call(["/usr/bin/g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-Wno-unknown-pragmas",
+                                           "-o", tmp] + srcs + ["-ldl"])
+                    os.replace(tmp, so)
         _EMU = C.CDLL(so)
         _EMU.qvtest_run.restype = C.c_int
     return _EMU
