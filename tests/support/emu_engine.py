@@ -37,9 +37,20 @@ class EmuShardEngine:
             raise RuntimeError(err.value.decode())
         return C.c_void_p(t)
 
+    def set_zero_ranks(self, mask):
+        """The host's claim "these ranks hold only zeros" (qvmcuda_shard_set_zero_ranks): the emulator does not use it, it CHECKS
+        it at the first exchange step -- the moment the CUDA path would skip fetching those shards."""
+        self.zero_ranks = int(mask)
+
     def num_steps(self, tape): return self.emu.qvtest_shard_num_steps(tape)
     def step_flags(self, tape, i): return self.emu.qvtest_shard_step_flags(tape, i)
-    def run_step(self, tape, i): self.emu.qvtest_shard_run_step(tape, i, self.ptrs, self.rank)
+    def run_step(self, tape, i):
+        if getattr(self, "zero_ranks", 0) and (self.step_flags(tape, i) & 1):
+            for r in range(self.world):
+                if self.zero_ranks >> r & 1:
+                    assert not self.shards[r].any(), f"rank {r} was declared all-zero but holds amplitudes"
+            self.zero_ranks = 0
+        self.emu.qvtest_shard_run_step(tape, i, self.ptrs, self.rank)
     def commit(self, tape): self.emu.qvtest_shard_l2p(tape, self.l2p.ctypes.data_as(C.c_void_p))
     def free_tape(self, tape): self.emu.qvtest_shard_free(tape)
     def synchronize(self): pass

@@ -73,6 +73,18 @@ def _worker(rank, world, port, q):
         dist.barrier()
         if rank == 0:
             os.remove(path)
+        # straight from the collective reset: ranks != 0 are declared all-zero until the first exchange (the emulator engine checks
+        # the claim where the CUDA path relies on it); an upload in between must withdraw it
+        zero = np.zeros(1 << n, dtype=np.complex128)
+        zero[0] = 1.0
+        st.set_zero_state()
+        assert st._zero_ranks == ((1 << world) - 1) & ~1
+        st.apply_gates(circ, fuse=True)
+        assert st._zero_ranks == 0
+        helpers.assert_close(st.gather_logical(), helpers.run_oracle(zero.copy(), circ))
+        st.set_zero_state()
+        st.scatter_logical(psi)
+        assert st._zero_ranks == 0
         # back to the layout the run left behind (the checks below pick a rank-selecting qubit)
         st.set_zero_state()
         st.scatter_logical(psi)
